@@ -1,0 +1,252 @@
+"""Generate the golden vectors under tests/golden/ by running the REFERENCE (google-research/
+torchsde v0.2.6, mounted read-only at /root/reference) in this container on the CPU.
+
+    python tests/golden/make_golden.py
+
+The reference cannot travel to the GPU box, so its outputs are committed as small .npz fixtures
+together with this script.  `trampoline` (a pure-python dependency of the reference that is not
+installed and cannot be downloaded here) is provided by oracle/refshim/trampoline.py.
+
+What is recorded
+  solver_*.npz   reference `sdeint` output for one (problem, method, dtype) with the Brownian
+                 increments it consumed (so any solver can be replayed on identical increments);
+  bridge_*.npz   reference Brownian-bridge / merge / Davie-Foster outputs for fixed inputs and fixed
+                 normals (its `_randn` is monkey-patched to serve recorded arrays);
+  adjoint_*.npz  reference `sdeint_adjoint` (reversible_heun / adjoint_reversible_heun) gradients.
+"""
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, 'oracle', 'refshim'))
+sys.path.insert(0, '/root/reference')
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torchsde  # noqa: E402  (the reference)
+from torchsde._brownian import brownian_interval as ref_bi  # noqa: E402
+
+from tests import problems  # noqa: E402
+
+assert torchsde.__version__ == '0.2.6'
+
+
+class Recorder:
+    """Wraps a reference BrownianInterval and logs every query + answer."""
+
+    def __init__(self, bm):
+        self.bm = bm
+        self.shape = bm.shape
+        self.levy_area_approximation = bm.levy_area_approximation
+        self.log = []
+
+    def __call__(self, ta, tb=None, return_U=False, return_A=False):
+        out = self.bm(ta, tb, return_U=True) if self.bm._have_H else (self.bm(ta, tb), None)
+        W, U = out
+        self.log.append((float(ta), float(tb), W.numpy().copy(), None if U is None else U.numpy().copy()))
+        return (W, U) if return_U else W
+
+
+def solver_case(name, kind, method, sde_type, d, m, dtype, B=4, ts=None, dt=0.05, options=None, seed=0):
+    torch.manual_seed(1234 + seed)
+    tdt = torch.float64 if dtype == 'f64' else torch.float32
+    sde = problems.make(kind, d, m, sde_type, dtype=tdt, seed=seed)
+    y0 = (0.1 + 0.5 * torch.rand(B, d, dtype=torch.float64)).to(tdt)
+    ts = torch.tensor(ts, dtype=tdt)
+    levy = 'space-time' if method == 'srk' else 'none'
+    bm_m = d if kind == 'gbm' else m
+    bm = torchsde.BrownianInterval(float(ts[0]), float(ts[-1]), size=(B, bm_m), dtype=tdt, entropy=77 + seed,
+                                   levy_area_approximation=levy)
+    rec = Recorder(bm)
+    with torch.no_grad():
+        out = torchsde.sdeint(sde, y0, ts, bm=rec, method=method, dt=dt, options=options,
+                              extra=(method == 'reversible_heun'))
+    if method == 'reversible_heun':
+        ys, extra = out
+    else:
+        ys, extra = out, ()
+    save = dict(y0=y0.numpy(), ts=ts.numpy(), dt=np.float64(dt), ys=ys.numpy(),
+                ta=np.array([r[0] for r in rec.log]), tb=np.array([r[1] for r in rec.log]),
+                W=np.stack([r[2] for r in rec.log]),
+                kind=kind, method=method, sde_type=sde_type, d=d, m=m, dtype=dtype, seed=seed,
+                grad_free=bool(options and options.get('grad_free')))
+    if rec.log[0][3] is not None:
+        save['U'] = np.stack([r[3] for r in rec.log])
+    for i, e in enumerate(extra):
+        save[f'extra{i}'] = e.numpy()
+    np.savez_compressed(os.path.join(HERE, f'solver_{name}.npz'), **save)
+    print('wrote', name, ys.shape, len(rec.log), 'increments')
+
+
+def all_solver_cases():
+    aligned = [0.0, 0.1, 0.2, 0.3]
+    ragged = np.linspace(0.0, 0.3, 5).tolist()  # spacing 0.075 vs dt 0.05: exercises linear_interp
+    cases = []
+    for dtype in ('f64', 'f32'):
+        for method, opts in (('euler', None), ('milstein', None), ('milstein', {'grad_free': True}), ('srk', None)):
+            tag = method + ('_gf' if opts else '')
+            cases.append((f'gbm_ito_{tag}_{dtype}', 'gbm', method, 'ito', 6, 6, dtype, aligned, opts))
+        for method in ('milstein', 'heun', 'midpoint', 'euler_heun', 'reversible_heun'):
+            cases.append((f'gbm_strat_{method}_{dtype}', 'gbm', method, 'stratonovich', 8, 8, dtype, aligned, None))
+    cases.append(('gbm_ito_milstein_ragged_f64', 'gbm', 'milstein', 'ito', 6, 6, 'f64', ragged, None))
+    cases.append(('gbm_ito_srk_ragged_f32', 'gbm', 'srk', 'ito', 8, 8, 'f32', ragged, None))
+    for method, opts in (('euler', None), ('milstein', None), ('milstein', {'grad_free': True}), ('srk', None)):
+        tag = method + ('_gf' if opts else '')
+        cases.append((f'scalar_ito_{tag}_f64', 'scalar', method, 'ito', 5, 1, 'f64', aligned, opts))
+    for method in ('milstein', 'heun', 'midpoint', 'euler_heun', 'reversible_heun'):
+        cases.append((f'scalar_strat_{method}_f64', 'scalar', method, 'stratonovich', 5, 1, 'f64', aligned, None))
+    for (d, m) in ((3, 2), (4, 8)):
+        for method in ('euler', 'milstein', 'srk'):
+            cases.append((f'additive{d}x{m}_ito_{method}_f64', 'additive', method, 'ito', d, m, 'f64', aligned, None))
+        cases.append((f'general{d}x{m}_ito_euler_f64', 'general', 'euler', 'ito', d, m, 'f64', aligned, None))
+        for method in ('heun', 'midpoint', 'euler_heun', 'reversible_heun'):
+            cases.append((f'general{d}x{m}_strat_{method}_f64', 'general', method, 'stratonovich', d, m, 'f64',
+                          aligned, None))
+            cases.append((f'additive{d}x{m}_strat_{method}_f64', 'additive', method, 'stratonovich', d, m, 'f64',
+                          aligned, None))
+    cases.append(('general4x8_ito_euler_f32', 'general', 'euler', 'ito', 4, 8, 'f32', ragged, None))
+    cases.append(('additive4x8_ito_srk_f32', 'additive', 'srk', 'ito', 4, 8, 'f32', aligned, None))
+    for i, (name, kind, method, sde_type, d, m, dtype, ts, opts) in enumerate(cases):
+        solver_case(name, kind, method, sde_type, d, m, dtype, ts=ts, options=opts, seed=i % 5)
+
+
+def ito_diagonal_fixture():
+    """diagnostics/ito_diagonal.py:26-53, run A (B=16, ts=linspace(0,2,10), dt=0.1) with the
+    reference's own NeuralDiagonal(d=5), seeds as diagnostics/utils.py:123-127."""
+    import random
+    from tests import problems as my_problems
+    sys.path.insert(0, '/root/reference')
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('ref_problems', '/root/reference/tests/problems.py')
+    ref_problems = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_problems)
+    torch.set_default_dtype(torch.float64)
+    torch.manual_seed(1147481649)
+    np.random.seed(1147481649)
+    random.seed(1147481649)
+    B, d = 16, 5
+    t0, t1, steps, dt = 0., 2., 10, 1e-1
+    ts = torch.linspace(t0, t1, steps=steps)
+    sde = ref_problems.NeuralDiagonal(d=d)
+    y0 = torch.full((B, d), fill_value=0.1)
+    mine = my_problems.MLPDiagonal(d)
+    mine.load_state_dict(sde.state_dict())
+    for method, opts, tag in (('euler', None, 'euler'), ('milstein', None, 'milstein'),
+                              ('milstein', dict(grad_free=True), 'milstein_gf'), ('srk', None, 'srk')):
+        bm = torchsde.BrownianInterval(t0=t0, t1=t1, size=(B, d), dtype=y0.dtype,
+                                       levy_area_approximation='space-time', entropy=1147481649)
+        rec = Recorder(bm)
+        with torch.no_grad():
+            ys = torchsde.sdeint(sde, y0, ts, rec, method=method, dt=dt, options=opts)
+            ys_mine_def = torchsde.sdeint(mine, y0, ts, Recorder(torchsde.BrownianInterval(
+                t0=t0, t1=t1, size=(B, d), dtype=y0.dtype, levy_area_approximation='space-time',
+                entropy=1147481649)), method=method, dt=dt, options=opts)
+        assert torch.equal(ys, ys_mine_def)  # tests/problems.MLPDiagonal == reference NeuralDiagonal
+        save = dict(y0=y0.numpy(), ts=ts.numpy(), dt=np.float64(dt), ys=ys.numpy(),
+                    ta=np.array([r[0] for r in rec.log]), tb=np.array([r[1] for r in rec.log]),
+                    W=np.stack([r[2] for r in rec.log]), U=np.stack([r[3] for r in rec.log]),
+                    method=method, grad_free=bool(opts), d=d)
+        for k, v in sde.state_dict().items():
+            save['param.' + k] = v.numpy()
+        np.savez_compressed(os.path.join(HERE, f'ito_diagonal_{tag}.npz'), **save)
+        print('wrote ito_diagonal', tag)
+    torch.set_default_dtype(torch.float32)
+
+
+def bridge_cases():
+    """Bridge / merge / Levy-area formulas of the reference with its normals pinned."""
+    rng = np.random.RandomState(7)
+    for levy in ('none', 'space-time', 'davie', 'foster'):
+        for dtype, tdt in (('f64', torch.float64), ('f32', torch.float32)):
+            B, m = 5, 3
+            served = {}
+
+            def fake_randn(size, dtype_, device, seed, _served=served, _tdt=tdt):
+                key = (tuple(size), int(seed))
+                if key not in _served:
+                    _served[key] = torch.from_numpy(rng.randn(*size)).to(_tdt)
+                return _served[key]
+
+            orig = ref_bi._randn
+            ref_bi._randn = fake_randn
+            try:
+                W0 = torch.from_numpy(rng.randn(B, m)).to(tdt)
+                H0 = torch.from_numpy(rng.randn(B, m) * 0.3).to(tdt)
+                bm = torchsde.BrownianInterval(0.0, 1.0, size=(B, m), dtype=tdt, entropy=5,
+                                               levy_area_approximation=levy, W=W0, H=H0)
+                queries = [(0.0, 0.3), (0.3, 0.45), (0.45, 1.0), (0.1, 0.2), (0.2, 0.7), (0.05, 0.95)]
+                outs = []
+                for (a, b) in queries:
+                    r = bm(a, b, return_U=levy != 'none', return_A=levy in ('davie', 'foster'))
+                    outs.append(r if isinstance(r, tuple) else (r,))
+                # dump the tree: every split node with its normals
+                nodes = []
+
+                def walk(node, path):
+                    if node._midway is None:
+                        return
+                    x1 = served.get(((B, m), int(node._W_seed)))
+                    x2 = served.get(((B, m), int(node._H_seed)))
+                    nodes.append((path, node._start, node._midway, node._end, x1, x2,
+                                  int(node._left_a_seed), int(node._right_a_seed)))
+                    walk(node._left_child, path + 'L')
+                    walk(node._right_child, path + 'R')
+
+                walk(bm, '')
+                save = dict(W0=W0.numpy(), H0=H0.numpy(), levy=levy, queries=np.array(queries),
+                            top_a_seed=int(bm._top_a_seed))
+                for i, o in enumerate(outs):
+                    for j, x in enumerate(o):
+                        save[f'out{i}_{j}'] = x.numpy()
+                save['n_nodes'] = len(nodes)
+                for i, (path, s, mid, e, x1, x2, las, ras) in enumerate(nodes):
+                    save[f'node{i}_path'] = path
+                    save[f'node{i}_t'] = np.array([s, mid, e])
+                    if x1 is not None:
+                        save[f'node{i}_x1'] = x1.numpy()
+                    if x2 is not None:
+                        save[f'node{i}_x2'] = x2.numpy()
+                    save[f'node{i}_aseeds'] = np.array([las, ras], dtype=np.int64)
+                for (size, seed), val in served.items():
+                    if len(size) == 3:
+                        save[f'anoise_{seed}'] = val.numpy()
+                np.savez_compressed(os.path.join(HERE, f'bridge_{levy}_{dtype}.npz'), **save)
+                print('wrote bridge', levy, dtype, len(nodes), 'nodes')
+            finally:
+                ref_bi._randn = orig
+
+
+def adjoint_cases():
+    for name, kind, d, m in (('gbm', 'gbm', 6, 6), ('general', 'general', 4, 8), ('scalar', 'scalar', 5, 1),
+                             ('additive', 'additive', 3, 2)):
+        torch.manual_seed(99)
+        tdt = torch.float64
+        sde = problems.make(kind, d, m, 'stratonovich', dtype=tdt, seed=3)
+        B = 4
+        y0 = (0.1 + 0.5 * torch.rand(B, d, dtype=tdt)).requires_grad_(True)
+        ts = torch.tensor([0.0, 0.1, 0.2, 0.3], dtype=tdt)
+        bm_m = d if kind == 'gbm' else m
+        bm = torchsde.BrownianInterval(0.0, 0.3, size=(B, bm_m), dtype=tdt, entropy=11)
+        rec = Recorder(bm)
+        ys = torchsde.sdeint_adjoint(sde, y0, ts, bm=rec, method='reversible_heun',
+                                     adjoint_method='adjoint_reversible_heun', dt=0.05)
+        weights = torch.linspace(0.5, 1.5, ys.numel(), dtype=tdt).reshape(ys.shape)
+        loss = (ys * weights).sum()
+        loss.backward()
+        save = dict(y0=y0.detach().numpy(), ts=ts.numpy(), dt=np.float64(0.05), ys=ys.detach().numpy(),
+                    weights=weights.numpy(), grad_y0=y0.grad.numpy(), kind=kind, d=d, m=m,
+                    ta=np.array([r[0] for r in rec.log]), tb=np.array([r[1] for r in rec.log]),
+                    W=np.stack([r[2] for r in rec.log]))
+        for n, p in sde.named_parameters():
+            save['grad.' + n] = p.grad.numpy()
+        np.savez_compressed(os.path.join(HERE, f'adjoint_{name}.npz'), **save)
+        print('wrote adjoint', name)
+
+
+if __name__ == '__main__':
+    all_solver_cases()
+    ito_diagonal_fixture()
+    bridge_cases()
+    adjoint_cases()

@@ -1,0 +1,282 @@
+"""`sdeint_adjoint` for the algebraically reversible pair reversible_heun / adjoint_reversible_heun.
+
+Reference: torchsde/_core/adjoint.py (`_SdeintAdjointMethod` :29-127, `sdeint_adjoint` :130-278,
+`_select_default_adjoint_method` :281-296) and methods/reversible_heun.py:76-144
+(`AdjointReversibleHeun.step`).
+
+The reference packs (y, adj_y, adj_f, adj_g, adj_z, adj_params...) into one flat vector with a dummy
+batch dimension and re-enters `autograd.Function.apply` once per output interval, copying the whole
+augmented state through `flatten` / `flat_to_shape` on every step (adjoint.py:75-79,114-119;
+reversible_heun.py:142; adjoint_sde.py:104).  Here the augmented state stays in separate buffers,
+and one backward step is exactly
+    kernel A (reconstruct z1, first half of the adjoint bookkeeping)
+    user f_and_g at z0 + one torch.autograd.grad (the vjp)          <- user code, stays in torch
+    user f_and_g at z1
+    kernel B (reconstruct y1, second half of the bookkeeping)
+with the Brownian increment of the step regenerated from the Philox counter in both kernels
+(the same cells the forward pass consumed, addressed in reverse: `ReverseBrownian` semantics,
+_brownian/derived.py:27-30).
+
+Not implemented yet (SURVEY §8(f) "next"): the generic `AdjointSDE` path for
+euler/milstein/midpoint adjoints, double backward, adaptive adjoint stepping.
+"""
+import ctypes
+import warnings
+
+import torch
+from torch import nn
+
+from . import base_solver
+from . import methods
+from . import schedule as schedule_lib
+from . import sdeint as sdeint_mod
+from .base_solver import _contig
+from .. import _cabi
+from .._brownian import BrownianInterval, ReverseBrownian
+from ..settings import METHODS, NOISE_TYPES, SDE_TYPES, LEVY_AREA_APPROXIMATIONS
+
+_check = _cabi.check
+
+
+def _p(t):
+    return t.data_ptr()
+
+
+class AdjointReversibleHeun(base_solver.BaseSDESolver):
+    """Class-attribute / constructor contract of methods/reversible_heun.py:76-96.  It can only be
+    used as `adjoint_method`; the backward integration is driven by `_ReversibleAdjoint` below."""
+    weak_order = 1.0
+    sde_type = SDE_TYPES.stratonovich
+    noise_types = NOISE_TYPES.all()
+    levy_area_approximations = LEVY_AREA_APPROXIMATIONS.all()
+
+    def __init__(self, sde, **kwargs):
+        if not getattr(sde, 'is_adjoint_sde', False):
+            raise ValueError(f"{METHODS.adjoint_reversible_heun} can only be used for adjoint_method.")
+        self.strong_order = 1.0 if sde.noise_type == NOISE_TYPES.additive else 0.5
+        super(AdjointReversibleHeun, self).__init__(sde=sde, **kwargs)
+
+    def init_extra_solver_state(self, t0, y0):
+        raise RuntimeError("Please report a bug to torchsde_b200.")
+
+    def _step(self, c, y0, extra0, out):
+        raise RuntimeError("Please report a bug to torchsde_b200.")
+
+
+class _BackwardEngine(base_solver.BaseSDESolver):
+    """Runs AdjointReversibleHeun.step (reversible_heun.py:98-144) over the reversed time grid."""
+    weak_order = 1.0
+    strong_order = 0.5
+    sde_type = SDE_TYPES.stratonovich
+    noise_types = NOISE_TYPES.all()
+    levy_area_approximations = LEVY_AREA_APPROXIMATIONS.all()
+
+    def __init__(self, sde, bm, dt, params):
+        super(_BackwardEngine, self).__init__(sde=sde, bm=bm, dt=dt, adaptive=False, rtol=None, atol=None,
+                                              dt_min=None, options={})
+        self.params = list(params)
+
+    def aux_times(self, t0, t1, dt):
+        return [-t0, -t1]  # forward-time arguments of f_and_g (reversible_heun.py:122,133)
+
+    def scalars(self, dt):
+        return {'half_dt': float(0.5 * dt)}
+
+    def _step(self, c, y0, extra0, out):
+        raise RuntimeError("internal")
+
+    def run(self, ys, ts, grad_ys, extras, grad_extras):
+        """Backward sweep over all output intervals (adjoint.py:97-119).  Returns
+        adj_y0, (adj_f, adj_g, adj_z), adj_params."""
+        lib = _cabi.lib()
+        T = ts.numel()
+        y = _contig(ys[-1])
+        self._prepare(y)
+        L = self._L
+        neg_ts = -ts
+        # One schedule per interval [-ts[i], -ts[i-1]], exactly as the reference re-enters integrate().
+        scheds = [schedule_lib.build_schedule(torch.stack([neg_ts[i], neg_ts[i - 1]]), self.dt)
+                  for i in range(T - 1, 0, -1)]
+        bounds = [scheds[0].bounds[0]]
+        for s in scheds:
+            bounds.extend(s.bounds[1:])
+        merged = schedule_lib.Schedule(None, [st for s in scheds for st in s.steps], [])
+        merged.bounds = bounds
+        binding = self._bind(merged)
+        self._feed = base_solver.NoiseFeed(self, self.bm, binding)
+        ctxs = self._contexts(merged, ts)
+
+        f0, g0, z0 = (_contig(x.detach()) for x in extras)
+        adj_y = _contig(grad_ys[-1]).clone()
+        adj_f, adj_g, adj_z = (_contig(x).clone() for x in grad_extras)
+        adj_params = [torch.zeros_like(p) for p in self.params]
+        sde = self.sde
+        k = 0
+        for n, sched in enumerate(scheds):
+            i = T - 1 - n
+            for _ in range(sched.n_steps):
+                c = ctxs[k]
+                k += 1
+                t_fwd0, t_fwd1 = c.aux_t
+                half_dt = c.scalars['half_dt']
+                z1 = torch.empty_like(y)
+                adj_f_mid = torch.empty_like(adj_f)
+                adj_g_mid = torch.empty_like(adj_g)
+                _check(lib.tsde_adjoint_reversible_heun_a(
+                    L, self._feed.get(c), _p(y), _p(z0), _p(f0), _p(g0), _p(adj_y), _p(adj_f), _p(adj_g),
+                    c.dt, half_dt, _p(z1), _p(adj_f_mid), _p(adj_g_mid)), "tsde_adjoint_reversible_heun_a")
+                with torch.enable_grad():
+                    z0r = z0.detach().requires_grad_()
+                    re_f0, re_g0 = sde.f_and_g(t_fwd0, z0r)
+                    outs, gouts = [], []
+                    for o, go in ((re_f0, adj_f_mid), (re_g0, adj_g_mid)):
+                        if o.requires_grad:
+                            outs.append(o)
+                            gouts.append(go.view_as(o))
+                    if outs:
+                        vjps = torch.autograd.grad(outs, [z0r] + self.params, gouts, allow_unused=True)
+                    else:
+                        vjps = [None] * (1 + len(self.params))
+                vjp_z = vjps[0] if vjps[0] is not None else torch.zeros_like(z0)
+                for ap, v in zip(adj_params, vjps[1:]):
+                    if v is not None:
+                        ap.add_(v)
+                f1, g1 = sde.f_and_g(t_fwd1, z1)
+                f1, g1 = _contig(f1), _contig(g1)
+                y1 = torch.empty_like(y)
+                adj_y1 = torch.empty_like(adj_y)
+                adj_z1 = torch.empty_like(adj_z)
+                adj_f1 = torch.empty_like(adj_f)
+                adj_g1 = torch.empty_like(adj_g)
+                _check(lib.tsde_adjoint_reversible_heun_b(
+                    L, self._feed.get(c), _p(y), _p(f0), _p(f1), _p(g0), _p(g1), _p(adj_y), _p(adj_z),
+                    _p(_contig(vjp_z)), c.dt, half_dt, _p(y1), _p(adj_y1), _p(adj_z1), _p(adj_f1), _p(adj_g1)),
+                    "tsde_adjoint_reversible_heun_b")
+                y, adj_y, adj_z, adj_f, adj_g = y1, adj_y1, adj_z1, adj_f1, adj_g1
+                f0, g0, z0 = f1, g1, z1
+            # adjoint.py:114-116
+            y = _contig(ys[i - 1])
+            adj_y = adj_y + grad_ys[i - 1]
+        return adj_y, (adj_f, adj_g, adj_z), adj_params
+
+
+class _AdjointMarker:
+    """Stands in for the reference's AdjointSDE where only its type/attributes are inspected."""
+    is_adjoint_sde = True
+
+    def __init__(self, forward_sde):
+        self.forward_sde = forward_sde
+        self.sde_type = forward_sde.sde_type
+        # adjoint_sde.py:33-38
+        self.noise_type = {
+            NOISE_TYPES.general: NOISE_TYPES.general,
+            NOISE_TYPES.additive: NOISE_TYPES.general,
+            NOISE_TYPES.scalar: NOISE_TYPES.scalar,
+            NOISE_TYPES.diagonal: NOISE_TYPES.diagonal,
+        }[forward_sde.noise_type]
+
+
+class _SdeintAdjointMethod(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, sde, ts, dt, bm, solver, options, n_extras, y0, *extras_and_params):
+        ctx.sde, ctx.dt, ctx.bm, ctx.n_extras = sde, dt, bm, n_extras
+        extras = tuple(x.detach() for x in extras_and_params[:n_extras])
+        params = extras_and_params[n_extras:]
+        ys, extras_out = sdeint_mod._integrate(solver, y0.detach(), ts, extras, options)
+        ctx.save_for_backward(ys, ts, *extras_out, *params)
+        return (ys, *extras_out)
+
+    @staticmethod
+    def backward(ctx, grad_ys, *grad_extras):
+        ys, ts, *rest = ctx.saved_tensors
+        extras = rest[:ctx.n_extras]
+        params = rest[ctx.n_extras:]
+        grad_extras = [torch.zeros_like(e) if g is None else g for g, e in zip(grad_extras, extras)]
+        with torch.no_grad():
+            engine = _BackwardEngine(ctx.sde, ReverseBrownian(ctx.bm), ctx.dt, params)
+            adj_y, adj_extras, adj_params = engine.run(ys, ts, grad_ys, extras, grad_extras)
+        return (None, None, None, None, None, None, None, adj_y, *adj_extras, *adj_params)
+
+
+def sdeint_adjoint(sde, y0, ts, bm=None, method=None, adjoint_method=None, dt=1e-3, adaptive=False,
+                   adjoint_adaptive=False, rtol=1e-5, adjoint_rtol=1e-5, atol=1e-4, adjoint_atol=1e-4,
+                   dt_min=1e-5, options=None, adjoint_options=None, adjoint_params=None, names=None,
+                   logqp=False, extra=False, extra_solver_state=None, **unused_kwargs):
+    """Numerically integrate an SDE with stochastic adjoint support (reference docstring:
+    adjoint.py:152-222)."""
+    sdeint_mod.handle_unused_kwargs(unused_kwargs, msg="`sdeint_adjoint`")
+    del unused_kwargs
+
+    if adjoint_params is None and not isinstance(sde, nn.Module):
+        raise ValueError('`sde` must be an instance of nn.Module to specify the adjoint parameters; alternatively they '
+                         'can be specified explicitly via the `adjoint_params` argument. If there are no parameters '
+                         'then it is allowable to set `adjoint_params=()`.')
+
+    sde, y0, ts, bm, method, options = sdeint_mod.check_contract(sde, y0, ts, bm, method, adaptive, options, names,
+                                                                 logqp)
+    sdeint_mod.assert_no_grad(['ts', 'dt', 'rtol', 'adjoint_rtol', 'atol', 'adjoint_atol', 'dt_min'],
+                              [ts, dt, rtol, adjoint_rtol, atol, adjoint_atol, dt_min])
+    adjoint_params = tuple(sde.parameters()) if adjoint_params is None else tuple(adjoint_params)
+    adjoint_params = [p for p in adjoint_params if p.requires_grad]
+    adjoint_method = _select_default_adjoint_method(sde, method, adjoint_method)
+    adjoint_options = {} if adjoint_options is None else adjoint_options.copy()
+
+    if method == METHODS.reversible_heun:  # adjoint.py:243-257
+        if adjoint_method != METHODS.adjoint_reversible_heun:
+            warnings.warn(f"method={repr(method)}, but adjoint_method!={repr(METHODS.adjoint_reversible_heun)}.")
+        if adaptive or adjoint_adaptive:
+            warnings.warn(f"A limitation of the current method={repr(method)} implementation is "
+                          f"that it does not save the time steps used. This means that it may not be perfectly "
+                          f"accurate when used with `adaptive` or `adjoint_adaptive`.")
+        else:
+            num_steps = (ts - ts[0]) / dt
+            if not torch.allclose(num_steps, num_steps.round()):
+                warnings.warn(f"The spacing between time points `ts` is not an integer multiple of the time step `dt`. "
+                              f"This means that the backward pass (which is forced to step to each of `ts` to get "
+                              f"dL/dy(t) for t in ts) will not perfectly mimick the forward pass (which does not step "
+                              f"to each `ts`, and instead interpolates to them). This means that "
+                              f"method={repr(method)} may not be perfectly accurate.")
+
+    solver_fn = methods.select(method=method, sde_type=sde.sde_type)
+    solver = solver_fn(sde=sde, bm=bm, dt=dt, adaptive=adaptive, rtol=rtol, atol=atol, dt_min=dt_min,
+                       options=options)
+    # constructor-time contract of the adjoint solver (errors as in the reference)
+    adjoint_solver_fn = methods.select(method=adjoint_method, sde_type=sde.sde_type)
+    adjoint_solver_fn(sde=_AdjointMarker(sde), bm=ReverseBrownian(bm), dt=dt, adaptive=adjoint_adaptive,
+                      rtol=adjoint_rtol, atol=adjoint_atol, dt_min=dt_min, options=adjoint_options)
+    if not (method == METHODS.reversible_heun and adjoint_method == METHODS.adjoint_reversible_heun):
+        raise NotImplementedError(
+            "torchsde_b200: sdeint_adjoint currently implements the reversible pair "
+            "method='reversible_heun', adjoint_method='adjoint_reversible_heun'; the generic AdjointSDE "
+            "path is not implemented yet.")
+    if adaptive or adjoint_adaptive:
+        raise NotImplementedError("torchsde_b200: adaptive time-stepping is not implemented yet.")
+
+    _cabi.require_cuda(y0)
+    if extra_solver_state is None:
+        # built with autograd enabled (adjoint.py:270-271): the adjoints of (f0, g0, z0) returned by
+        # backward() flow on to y0 and the parameters through these ordinary torch ops
+        extra_solver_state = solver.init_extra_solver_state(ts[0], y0)
+
+    ys, *extra_solver_state = _SdeintAdjointMethod.apply(
+        sde, ts, dt, bm, solver, options, len(extra_solver_state), y0, *extra_solver_state, *adjoint_params)
+    return sdeint_mod.parse_return(y0, ys, extra_solver_state, extra, logqp)
+
+
+def _select_default_adjoint_method(sde, method, adjoint_method):
+    """adjoint.py:281-296."""
+    if adjoint_method is not None:
+        return adjoint_method
+    elif method == METHODS.reversible_heun:
+        return METHODS.adjoint_reversible_heun
+    else:
+        return {
+            SDE_TYPES.ito: {
+                NOISE_TYPES.diagonal: METHODS.milstein,
+                NOISE_TYPES.additive: METHODS.euler,
+                NOISE_TYPES.scalar: METHODS.euler,
+                NOISE_TYPES.general: METHODS.euler,
+            }[sde.noise_type],
+            SDE_TYPES.stratonovich: METHODS.midpoint,
+        }[sde.sde_type]

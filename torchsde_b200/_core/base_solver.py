@@ -1,0 +1,304 @@
+"""Fixed-step SDE solver engine: host-planned time grid + fused CUDA tableau kernels.
+
+Per-step operator contract = the reference's (torchsde/_core/base_solver.py:29-90):
+``BaseSDESolver(sde, bm, dt, adaptive, rtol, atol, dt_min, options)`` with class attributes
+``strong_order, weak_order, sde_type, noise_types, levy_area_approximations``, the constructor
+compatibility checks (:49-58 -> ValueError), ``init_extra_solver_state(t0, y0)`` (:72-73),
+``step(t0, t1, y0, extra0) -> (y1, extra1)`` (:75-90) and ``integrate(y0, ts, extra0)``
+(:92-149).
+
+What changed underneath:
+* ``integrate`` no longer loops over 0-d device tensors.  The grid is planned on the host
+  (schedule.py), the Brownian motion is asked once to *bind* that grid (so each step's increment
+  is a counter lookup regenerated in registers), every step is {user f/g (torch ops) -> one or
+  two fused tableau launches through the C ABI}, ``ys`` is preallocated and each step writes its
+  ``y1`` straight into its output row (no ``torch.stack``, no ``linear_interp`` for aligned
+  rows; reference :147,149).
+* The whole loop — user callables included — can be captured once into a CUDA graph and replayed
+  (``options={'cuda_graph': True}``, see graph.py), removing all per-step host work.
+"""
+import abc
+import ctypes
+import warnings
+
+import torch
+
+from . import schedule as schedule_lib
+from .. import _cabi
+from .._brownian import BaseBrownian, BrownianInterval, ReverseBrownian, GridBinding
+from ..settings import NOISE_TYPES
+
+
+def _contig(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class StepContext:
+    """Everything one step needs besides tensors; built once per solve for every step."""
+    __slots__ = ('k', 't0', 't1', 'ft0', 'ft1', 'dt', 'scalars', 'aux_t', 'solver')
+
+    def __init__(self, solver, k, t0, t1, ft0, ft1, dt, scalars, aux_t):
+        self.solver = solver
+        self.k = k
+        self.t0 = t0          # 0-d device tensors handed to the user's f/g
+        self.t1 = t1
+        self.ft0 = ft0        # python floats (exact values of t0, t1)
+        self.ft1 = ft1
+        self.dt = dt          # float(t1 - t0), computed in ts' dtype
+        self.scalars = scalars  # dict of derived scalars (python floats)
+        self.aux_t = aux_t      # list of 0-d device tensors (stage times)
+
+
+class NoiseFeed:
+    """Hands the tableau kernels their Brownian increment for step k.
+
+    counter mode : the bm bound the solver's grid (GridBinding) -> kernels regenerate dW from the
+                   Philox counter, nothing is materialised (unless a user g_prod needs the tensor).
+    memory mode  : any other BaseBrownian-like object -> bm(ta, tb) is called as the reference does
+                   (base_solver.py:54-57 duck typing) and the kernels read its tensors.
+    """
+
+    def __init__(self, solver, bm, binding):
+        self.solver = solver
+        self.bm = bm
+        self.binding = binding
+        self._nz = _cabi.Noise()
+        self._keep = None
+        self._cached = None
+        if binding is not None:
+            self._key_ptr = binding.interval.key_tensor().data_ptr()
+            self._row_offset = binding.interval._row_offset
+        self._unit = _cabi.Noise()
+        self._unit.source = _cabi.SRC_UNIT
+
+    def unit(self):
+        return ctypes.byref(self._unit)
+
+    def tensors(self, c, want_u=False):
+        """Materialised (W, U) for step c (needed by user-supplied g_prod / f_and_g_prod).
+        Cached per step so that the Brownian motion is queried once per step, as in the reference."""
+        if self._cached is not None and self._cached[0] is c and (self._cached[2] is not None or not want_u):
+            return self._cached[1], self._cached[2]
+        w, u = self._tensors(c, want_u)
+        self._cached = (c, w, u)
+        return w, u
+
+    def _tensors(self, c, want_u):
+        s = self.solver
+        if self.binding is None:
+            if want_u:
+                w, u = self.bm(c.ft0, c.ft1, return_U=True)
+            else:
+                w, u = self.bm(c.ft0, c.ft1), None
+            w = _contig(w)
+            u = _contig(u) if u is not None else None
+            _cabi.require_cuda(w, u)
+            if w.dtype != s.dtype:
+                raise ValueError(f"Brownian motion returned dtype {w.dtype}, expected {s.dtype}.")
+            return w, u
+        nz = self.binding.fill(self._nz, c.k, want_u, self._key_ptr, self._row_offset)
+        w = torch.empty((s.rows, s.m), dtype=s.dtype, device=s.device)
+        u = torch.empty_like(w) if want_u else None
+        _cabi.check(_cabi.lib().tsde_brownian_cells(ctypes.byref(s.launch_bm), ctypes.byref(nz), w.data_ptr(),
+                                                    None if u is None else u.data_ptr(), None),
+                    "tsde_brownian_cells")
+        return w, u
+
+    def get(self, c, want_u=False):
+        """ctypes reference to a filled `tsde_noise` for step c."""
+        if self.binding is not None:
+            self.binding.fill(self._nz, c.k, want_u, self._key_ptr, self._row_offset)
+            return ctypes.byref(self._nz)
+        w, u = self.tensors(c, want_u)
+        return self.from_tensors(w, u)
+
+    def from_tensors(self, w, u=None):
+        nz = self._nz
+        nz.source = _cabi.SRC_MEMORY
+        nz.want_u = 0 if u is None else 1
+        nz.w = w.data_ptr()
+        nz.u = None if u is None else u.data_ptr()
+        nz.key = None
+        nz.n_cells = 1
+        nz.cell_h = None
+        self._keep = (w, u)  # keep alive until the launch that consumes it has been enqueued
+        return ctypes.byref(nz)
+
+
+class BaseSDESolver(metaclass=abc.ABCMeta):
+    """API for fixed-step solvers (adaptive stepping: see DESIGN.md, "next")."""
+
+    strong_order = None
+    weak_order = None
+    sde_type = None
+    noise_types = None
+    levy_area_approximations = None
+    want_u = False  # whether step() needs the space-time Levy area U
+
+    def __init__(self, sde, bm, dt, adaptive, rtol, atol, dt_min, options, **kwargs):
+        super(BaseSDESolver, self).__init__(**kwargs)
+        # base_solver.py:49-58
+        if sde.sde_type != self.sde_type:
+            raise ValueError(f"SDE is of type {sde.sde_type} but solver is for type {self.sde_type}")
+        if sde.noise_type not in self.noise_types:
+            raise ValueError(f"SDE has noise type {sde.noise_type} but solver only supports noise types "
+                             f"{self.noise_types}")
+        if bm.levy_area_approximation not in self.levy_area_approximations:
+            raise ValueError(f"SDE solver requires one of {self.levy_area_approximations} set as the "
+                             f"`levy_area_approximation` on the Brownian motion.")
+        if sde.noise_type == NOISE_TYPES.scalar and torch.Size(bm.shape[1:]).numel() != 1:  # noqa
+            raise ValueError("The Brownian motion for scalar SDEs must of dimension 1.")
+
+        self.sde = sde
+        self.bm = bm
+        self.dt = dt
+        self.adaptive = adaptive
+        self.rtol = rtol
+        self.atol = atol
+        self.dt_min = dt_min
+        self.options = options
+        self._prepared = False
+
+    def __repr__(self):
+        return f"{self.__class__.__name__} of strong order: {self.strong_order}, and weak order: {self.weak_order}"
+
+    # ------------------------------------------------------------------------------------------
+    def init_extra_solver_state(self, t0, y0):
+        return ()
+
+    def aux_times(self, t0, t1, dt):
+        """Stage times other than t0, t1, as 0-d CPU tensors (same expressions as the reference)."""
+        return []
+
+    def scalars(self, dt):
+        """Derived scalars of a step, from the 0-d CPU tensor dt (same expressions as the reference)."""
+        return {}
+
+    @abc.abstractmethod
+    def _step(self, c, y0, extra0, out):
+        """Advance one step.  Writes y1 into `out` (a (rows, d) tensor) and returns extra1."""
+        raise NotImplementedError
+
+    # ------------------------------------------------------------------------------------------
+    def _prepare(self, y0):
+        _cabi.require_cuda(y0)
+        _cabi.lib()  # fail loudly if the CUDA library is missing
+        self.dtype = y0.dtype
+        self.device = y0.device
+        self.rows, self.d = y0.shape
+        self.m = int(torch.Size(self.bm.shape[1:]).numel()) if len(self.bm.shape) > 1 else 1
+        diag = self.sde.noise_type == NOISE_TYPES.diagonal
+        nt = _cabi.NOISE_DIAGONAL if diag else _cabi.NOISE_GENERAL
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self.launch = _cabi.make_launch(self.dtype, nt, self.rows, self.d, self.m, stream)
+        # user-supplied products arrive as (rows, d): element-wise launch with unit noise
+        self.launch_unit = _cabi.make_launch(self.dtype, _cabi.NOISE_DIAGONAL, self.rows, self.d, self.d, stream)
+        # Brownian tensors are (rows, m)
+        self.launch_bm = _cabi.make_launch(self.dtype, _cabi.NOISE_DIAGONAL, self.rows, self.m, self.m, stream)
+        self._L = ctypes.byref(self.launch)
+        self._LU = ctypes.byref(self.launch_unit)
+        self._lib = _cabi.lib()
+        self._prepared = True
+
+    def _refresh_stream(self):
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self.launch.stream = stream
+        self.launch_unit.stream = stream
+        self.launch_bm.stream = stream
+
+    def _bind(self, sched):
+        """Ask the Brownian motion to adopt the solver grid (fast path) if it can."""
+        bm = self.bm
+        binding = None
+        if isinstance(bm, BrownianInterval):
+            binding = bm.bind_grid(sched.bounds)
+        elif isinstance(bm, ReverseBrownian) and isinstance(bm.base_brownian, BrownianInterval):
+            fwd = bm.base_brownian.bind_grid([-b for b in reversed(sched.bounds)])
+            binding = None if fwd is None else fwd.reversed()
+        return binding
+
+    def _contexts(self, sched, ts):
+        """Per-step contexts; all scalar arithmetic in ts' dtype on the host, one H2D copy."""
+        n = sched.n_steps
+        if n == 0:
+            return []
+        cpu_t0 = [s[0] for s in sched.steps]
+        cpu_t1 = [s[1] for s in sched.steps]
+        cpu_dt = [b - a for a, b in sched.steps]
+        aux = [self.aux_times(a, b, h) for a, b, h in zip(cpu_t0, cpu_t1, cpu_dt)]
+        n_aux = len(aux[0])
+        table = torch.stack([torch.stack([a, b] + list(x)) for a, b, x in zip(cpu_t0, cpu_t1, aux)])
+        table = table.to(ts.dtype).to(self.device, non_blocking=False)  # (n, 2 + n_aux)
+        self._time_table = table  # keep alive (static addresses for graph replay)
+        ctxs = []
+        for k in range(n):
+            row = table[k]
+            ctxs.append(StepContext(self, k, row[0], row[1], sched.bounds[k], sched.bounds[k + 1],
+                                    float(cpu_dt[k]), self.scalars(cpu_dt[k]),
+                                    [row[2 + j] for j in range(n_aux)]))
+        return ctxs
+
+    # ------------------------------------------------------------------------------------------
+    def step(self, t0, t1, y0, extra0):
+        """Reference-compatible single step (base_solver.py:75-90): queries ``self.bm(t0, t1)``."""
+        if not self._prepared:
+            self._prepare(y0)
+        self._refresh_stream()
+        t0 = torch.as_tensor(t0)
+        t1 = torch.as_tensor(t1)
+        c0, c1 = t0.detach().cpu(), t1.detach().cpu()
+        dt = c1 - c0
+        aux = [a.to(self.device) for a in self.aux_times(c0, c1, dt)]
+        c = StepContext(self, 0, t0.to(self.device), t1.to(self.device), float(c0), float(c1), float(dt),
+                        self.scalars(dt), aux)
+        self._feed = NoiseFeed(self, self.bm, None)
+        out = torch.empty_like(y0)
+        with torch.no_grad():
+            extra1 = self._step(c, _contig(y0.detach()), extra0, out)
+        return out, extra1
+
+    def integrate(self, y0, ts, extra0):
+        """Integrate along trajectory.  Returns ys (T, batch, d) and the final extra state
+        (base_solver.py:92-149, fixed-step branch)."""
+        if self.adaptive:
+            raise NotImplementedError(
+                "torchsde_b200: adaptive time-stepping is not implemented yet (fixed-step solvers only).")
+        sched = schedule_lib.build_schedule(ts, self.dt)
+        y0 = _contig(y0.detach())
+        self._prepare(y0)
+        binding = self._bind(sched)
+        self._feed = NoiseFeed(self, self.bm, binding)
+        ctxs = self._contexts(sched, ts)
+        T = ts.numel()
+        ys = torch.empty((T, self.rows, self.d), dtype=self.dtype, device=self.device)
+        ys[0].copy_(y0)
+        extra = tuple(extra0)
+        with torch.no_grad():
+            extra = self._run(sched, ctxs, ys, extra)
+        return ys, extra
+
+    def _run(self, sched, ctxs, ys, extra):
+        """The time loop proper: capturable (no syncs, no host-dependent control flow)."""
+        self._refresh_stream()
+        curr = ys[0]
+        prev = curr
+        scratch = [None, None]
+        flip = 0
+        for k, c in enumerate(ctxs):
+            row = sched.aligned_row(k)
+            if row is not None:
+                out = ys[row]
+            else:
+                if scratch[flip] is None:
+                    scratch[flip] = torch.empty_like(ys[0])
+                out = scratch[flip]
+                flip ^= 1
+            extra = self._step(c, curr, extra, out)
+            prev, curr = curr, out
+            for o in sched.outputs_after.get(k, ()):
+                if not o.aligned:
+                    # interp.py:15-18
+                    _cabi.check(self._lib.tsde_linear_interp(self._LU, prev.data_ptr(), curr.data_ptr(),
+                                                             o.w0, o.w1, ys[o.index].data_ptr()),
+                                "tsde_linear_interp")
+        return extra

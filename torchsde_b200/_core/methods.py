@@ -1,0 +1,422 @@
+"""The step tableaus, as host-side drivers of the fused CUDA kernels.
+
+One class per method of the reference (torchsde/_core/methods/*.py), with the same class
+attributes (strong/weak order, sde_type, noise_types, levy_area_approximations) and the same
+constructor-time errors; ``select`` mirrors methods/__init__.py:26-48.  Each ``_step`` issues the
+user's drift/diffusion calls in the reference's order and replaces the ATen arithmetic of the
+reference's ``step`` by one or two launches through the C ABI (include/torchsde_b200.h).
+"""
+import ctypes
+
+import torch
+
+from . import base_solver
+from .base_solver import _contig
+from .. import _cabi
+from ..settings import SDE_TYPES, NOISE_TYPES, LEVY_AREA_APPROXIMATIONS, METHODS, METHOD_OPTIONS
+
+_check = _cabi.check
+
+
+def _p(t):
+    return t.data_ptr()
+
+
+class _ProdMixin:
+    """Shared handling of the reference's `f_and_g_prod` / `g_prod` call sites (base_sde.py:51-56)."""
+
+    def _f_and_g_prod(self, c, t, y, out_fn):
+        """Evaluate drift and diffusion at (t, y) the way ForwardSDE.f_and_g_prod would, then call
+        out_fn(L, nz, f, g) where (L, nz, g) are either (general/diag launch, step noise, g) or
+        (unit launch, unit noise, g_prod)."""
+        sde = self.sde
+        mode = sde.f_and_g_prod_mode
+        if mode == 'fused':
+            f, g = sde.f_and_g(t, y)
+            return out_fn(self._L, self._feed.get(c, self.want_u), _contig(f), _contig(g))
+        w, _ = self._feed.tensors(c)
+        w = w.reshape(self.bm.shape)
+        if mode == 'f_and_g_prod':
+            f, gp = sde.f_and_g_prod(t, y, w)
+        else:
+            f, gp = sde.f(t, y), sde.g_prod(t, y, w)
+        return out_fn(self._LU, self._feed.unit(), _contig(f), _contig(gp))
+
+    def _g_prod(self, c, t, y, out_fn):
+        sde = self.sde
+        if sde.g_prod_mode == 'fused':
+            g = sde.g(t, y)
+            return out_fn(self._L, self._feed.get(c, self.want_u), _contig(g))
+        w, _ = self._feed.tensors(c)
+        gp = sde.g_prod(t, y, w.reshape(self.bm.shape))
+        return out_fn(self._LU, self._feed.unit(), _contig(gp))
+
+
+class Euler(_ProdMixin, base_solver.BaseSDESolver):
+    """methods/euler.py:19-37."""
+    weak_order = 1.0
+    sde_type = SDE_TYPES.ito
+    noise_types = NOISE_TYPES.all()
+    levy_area_approximations = LEVY_AREA_APPROXIMATIONS.all()
+
+    def __init__(self, sde, **kwargs):
+        self.strong_order = 1.0 if sde.noise_type == NOISE_TYPES.additive else 0.5
+        super(Euler, self).__init__(sde=sde, **kwargs)
+
+    def _step(self, c, y0, extra0, out):
+        lib = self._lib
+
+        def fin(L, nz, f, g):
+            _check(lib.tsde_step_euler(L, nz, _p(y0), _p(f), _p(g), c.dt, _p(out)), "tsde_step_euler")
+
+        self._f_and_g_prod(c, c.t0, y0, fin)
+        return ()
+
+
+class BaseMilstein(_ProdMixin, base_solver.BaseSDESolver):
+    """methods/milstein.py:22-74."""
+    strong_order = 1.0
+    weak_order = 1.0
+    noise_types = (NOISE_TYPES.additive, NOISE_TYPES.diagonal, NOISE_TYPES.scalar)
+    levy_area_approximations = LEVY_AREA_APPROXIMATIONS.all()
+    ito = None
+
+    def __init__(self, sde, options, **kwargs):
+        # milstein.py:29-41
+        if METHOD_OPTIONS.grad_free not in options:
+            options[METHOD_OPTIONS.grad_free] = False
+        if options[METHOD_OPTIONS.grad_free]:
+            if sde.noise_type == NOISE_TYPES.additive:
+                options[METHOD_OPTIONS.grad_free] = False
+        if options[METHOD_OPTIONS.grad_free]:
+            if getattr(sde, 'is_adjoint_sde', False):
+                raise ValueError(f"Derivative-free Milstein cannot be used for adjoint SDEs, because it requires "
+                                 f"direct access to the diffusion, whilst adjoint SDEs rely on a more efficient "
+                                 f"diffusion-vector product. Use derivative-using Milstein instead: "
+                                 f"`adjoint_options=dict({METHOD_OPTIONS.grad_free}=False)`")
+        super(BaseMilstein, self).__init__(sde=sde, options=options, **kwargs)
+
+    def scalars(self, dt):
+        sqrt_dt = dt.sqrt()
+        return {'sqrt_dt': float(sqrt_dt), 'two_sqrt_dt': float(2 * sqrt_dt)}
+
+    def _step(self, c, y0, extra0, out):
+        lib, sde = self._lib, self.sde
+        ito = 1 if self.ito else 0
+        if self.options[METHOD_OPTIONS.grad_free]:
+            # milstein.py:58-67
+            f, g = sde.f_and_g(c.t0, y0)
+            f, g = _contig(f), _contig(g)
+            yp = torch.empty_like(y0)
+            _check(lib.tsde_milstein_gf_predict(self._LU, _p(y0), _p(f), _p(g), c.dt, c.scalars['sqrt_dt'], ito,
+                                                _p(yp)), "tsde_milstein_gf_predict")
+            g_prime = _contig(sde.g(c.t0, yp))
+            _check(lib.tsde_step_milstein_gf(self._L, self._feed.get(c), _p(y0), _p(f), _p(g), _p(g_prime), c.dt,
+                                             c.scalars['two_sqrt_dt'], ito, _p(out)), "tsde_step_milstein_gf")
+            return ()
+        f = _contig(sde.f(c.t0, y0))
+        if sde.noise_type == NOISE_TYPES.additive:
+            # g_prod_and_gdg_prod_additive: (g_prod(t, y, v1), 0.)  base_sde.py:157-158
+            def fin(L, nz, g):
+                _check(lib.tsde_step_euler(L, nz, _p(y0), _p(f), _p(g), c.dt, _p(out)), "tsde_step_euler")
+            self._g_prod(c, c.t0, y0, fin)
+            return ()
+        # g_prod_and_gdg_prod_{diagonal,default}: vjp of g wrt y with grad_outputs g * (0.5 v)
+        # base_sde.py:127-155 (always calls self.g, never g_prod)
+        with torch.enable_grad():
+            y = y0.detach().requires_grad_(True)
+            g = sde.g(c.t0, y)
+            gd = _contig(g.detach())
+            go = torch.empty_like(gd)
+            nz = self._feed.get(c)
+            _check(lib.tsde_milstein_vjp_seed(self._L, nz, _p(gd), c.dt, ito, _p(go)), "tsde_milstein_vjp_seed")
+            if g.requires_grad:
+                gdg, = torch.autograd.grad(g, y, grad_outputs=go.view_as(g), allow_unused=True)
+            else:
+                gdg = None
+        if gdg is None:
+            gdg = torch.zeros_like(y0)
+        _check(lib.tsde_step_milstein(self._L, self._feed.get(c), _p(y0), _p(f), _p(gd), _p(_contig(gdg)), c.dt,
+                                      _p(out)), "tsde_step_milstein")
+        return ()
+
+
+class MilsteinIto(BaseMilstein):
+    sde_type = SDE_TYPES.ito
+    ito = True
+
+
+class MilsteinStratonovich(BaseMilstein):
+    sde_type = SDE_TYPES.stratonovich
+    ito = False
+
+
+class Heun(_ProdMixin, base_solver.BaseSDESolver):
+    """methods/heun.py:25-48."""
+    weak_order = 1.0
+    sde_type = SDE_TYPES.stratonovich
+    noise_types = NOISE_TYPES.all()
+    levy_area_approximations = LEVY_AREA_APPROXIMATIONS.all()
+
+    def __init__(self, sde, **kwargs):
+        self.strong_order = 0.5 if sde.noise_type == NOISE_TYPES.general else 1.0
+        super(Heun, self).__init__(sde=sde, **kwargs)
+
+    def _step(self, c, y0, extra0, out):
+        lib = self._lib
+        yp = torch.empty_like(y0)
+        st = {}
+
+        def first(L, nz, f, g):
+            _check(lib.tsde_step_euler(L, nz, _p(y0), _p(f), _p(g), c.dt, _p(yp)), "tsde_step_euler")
+            st['f'], st['g'] = f, g
+
+        self._f_and_g_prod(c, c.t0, y0, first)
+
+        def second(L, nz, fp, gp):
+            _check(lib.tsde_step_heun(L, nz, _p(y0), _p(st['f']), _p(fp), _p(st['g']), _p(gp), c.dt, _p(out)),
+                   "tsde_step_heun")
+
+        self._f_and_g_prod(c, c.t1, yp, second)
+        return ()
+
+
+class Midpoint(_ProdMixin, base_solver.BaseSDESolver):
+    """methods/midpoint.py:19-45."""
+    weak_order = 1.0
+    sde_type = SDE_TYPES.stratonovich
+    noise_types = NOISE_TYPES.all()
+    levy_area_approximations = LEVY_AREA_APPROXIMATIONS.all()
+
+    def __init__(self, sde, **kwargs):
+        self.strong_order = 0.5 if sde.noise_type == NOISE_TYPES.general else 1.0
+        super(Midpoint, self).__init__(sde=sde, **kwargs)
+
+    def aux_times(self, t0, t1, dt):
+        return [t0 + 0.5 * dt]  # t_prime = t0 + half_dt, midpoint.py:35-37
+
+    def scalars(self, dt):
+        return {'half_dt': float(0.5 * dt)}
+
+    def _step(self, c, y0, extra0, out):
+        lib = self._lib
+        yp = torch.empty_like(y0)
+
+        def first(L, nz, f, g):
+            _check(lib.tsde_midpoint_predict(L, nz, _p(y0), _p(f), _p(g), c.scalars['half_dt'], _p(yp)),
+                   "tsde_midpoint_predict")
+
+        self._f_and_g_prod(c, c.t0, y0, first)
+
+        def second(L, nz, fp, gp):
+            _check(lib.tsde_step_euler(L, nz, _p(y0), _p(fp), _p(gp), c.dt, _p(out)), "tsde_step_euler")
+
+        self._f_and_g_prod(c, c.aux_t[0], yp, second)
+        return ()
+
+
+class EulerHeun(_ProdMixin, base_solver.BaseSDESolver):
+    """methods/euler_heun.py:19-42."""
+    weak_order = 1.0
+    sde_type = SDE_TYPES.stratonovich
+    noise_types = NOISE_TYPES.all()
+    levy_area_approximations = LEVY_AREA_APPROXIMATIONS.all()
+
+    def __init__(self, sde, **kwargs):
+        self.strong_order = 0.5 if sde.noise_type == NOISE_TYPES.general else 1.0
+        super(EulerHeun, self).__init__(sde=sde, **kwargs)
+
+    def _step(self, c, y0, extra0, out):
+        lib = self._lib
+        yp = torch.empty_like(y0)
+        st = {}
+
+        def first(L, nz, f, g):
+            _check(lib.tsde_euler_heun_predict(L, nz, _p(y0), _p(g), _p(yp)), "tsde_euler_heun_predict")
+            st['f'], st['g'], st['unit'] = f, g, L is self._LU
+
+        self._f_and_g_prod(c, c.t0, y0, first)
+
+        def second(L, nz, gp):
+            if (L is self._LU) != st['unit']:
+                raise RuntimeError("torchsde_b200: inconsistent g_prod availability in euler_heun.")
+            _check(lib.tsde_step_euler_heun(L, nz, _p(y0), _p(st['f']), _p(st['g']), _p(gp), c.dt, _p(out)),
+                   "tsde_step_euler_heun")
+
+        if st['unit']:
+            # first product came from the user's (f_and_)g_prod; the reference then calls sde.g_prod
+            sde = self.sde
+            w, _ = self._feed.tensors(c)
+            w = w.reshape(self.bm.shape)
+            if sde.user_g_prod:
+                gp = sde.g_prod(c.t1, yp, w)
+            else:  # only f_and_g_prod given: reference's g_prod_default needs g -> RuntimeError there too
+                gp = sde.f_and_g_prod(c.t1, yp, w)[1] if not hasattr(sde._base_sde, 'g') else None
+                if gp is None:
+                    raise RuntimeError("torchsde_b200: euler_heun with f_and_g_prod and g but no g_prod is "
+                                       "not supported; provide g_prod or only f/g.")
+            second(self._LU, self._feed.unit(), _contig(gp))
+        else:
+            self._g_prod(c, c.t1, yp, second)
+        return ()
+
+
+class ReversibleHeun(base_solver.BaseSDESolver):
+    """methods/reversible_heun.py:48-73."""
+    weak_order = 1.0
+    sde_type = SDE_TYPES.stratonovich
+    noise_types = NOISE_TYPES.all()
+    levy_area_approximations = LEVY_AREA_APPROXIMATIONS.all()
+
+    def __init__(self, sde, **kwargs):
+        self.strong_order = 1.0 if sde.noise_type == NOISE_TYPES.additive else 0.5
+        super(ReversibleHeun, self).__init__(sde=sde, **kwargs)
+
+    def scalars(self, dt):
+        return {'half_dt': float(0.5 * dt)}
+
+    def init_extra_solver_state(self, t0, y0):
+        return self.sde.f_and_g(t0, y0) + (y0,)
+
+    def _step(self, c, y0, extra0, out):
+        lib = self._lib
+        f0, g0, z0 = (_contig(x) for x in extra0)
+        z1 = torch.empty_like(y0)
+        _check(lib.tsde_reversible_heun_z(self._L, self._feed.get(c), _p(y0), _p(z0), _p(f0), _p(g0), c.dt, _p(z1)),
+               "tsde_reversible_heun_z")
+        f1, g1 = self.sde.f_and_g(c.t1, z1)
+        f1, g1 = _contig(f1), _contig(g1)
+        _check(lib.tsde_step_reversible_heun(self._L, self._feed.get(c), _p(y0), _p(f0), _p(f1), _p(g0), _p(g1),
+                                             c.scalars['half_dt'], _p(out)), "tsde_step_reversible_heun")
+        return f1, g1, z1
+
+
+class SRK(base_solver.BaseSDESolver):
+    """methods/srk.py:31-111 (srid2 for diagonal/scalar noise, sra1 for additive noise)."""
+    strong_order = 1.5
+    weak_order = 1.5
+    sde_type = SDE_TYPES.ito
+    noise_types = (NOISE_TYPES.additive, NOISE_TYPES.diagonal, NOISE_TYPES.scalar)
+    levy_area_approximations = (LEVY_AREA_APPROXIMATIONS.space_time,
+                                LEVY_AREA_APPROXIMATIONS.davie,
+                                LEVY_AREA_APPROXIMATIONS.foster)
+    want_u = True
+
+    def __init__(self, sde, **kwargs):
+        if getattr(sde, 'is_adjoint_sde', False):
+            raise ValueError("Stochastic Runge–Kutta methods cannot be used for adjoint SDEs, because it requires "
+                             "direct access to the diffusion, whilst adjoint SDEs rely on a more efficient "
+                             "diffusion-vector product. Use a different method instead.")
+        self._additive = sde.noise_type == NOISE_TYPES.additive
+        super(SRK, self).__init__(sde=sde, **kwargs)
+
+    def aux_times(self, t0, t1, dt):
+        if self._additive:
+            # sra1: C0 = (0, 3/4), C1 = (1, 0)                         tableaus/sra1.py:21-22
+            return [t0 + 1 * dt, t0 + (3 / 4) * dt, t0 + 0 * dt]
+        # srid2: C0 = (0, 1, 1/2, 0), C1 = (0, 1/4, 1, 1/4)            tableaus/srid2.py:21-22
+        return [t0 + 0 * dt, t0 + 1 * dt, t0 + (1 / 4) * dt, t0 + (1 / 2) * dt]
+
+    def scalars(self, dt):
+        return {'rdt': float(1 / dt), 'sqrt_dt': float(dt.sqrt()), 'three_dt': float(3 * dt)}
+
+    def _step(self, c, y0, extra0, out):
+        if self._additive:
+            return self._additive_step(c, y0, out)
+        return self._diagonal_or_scalar_step(c, y0, out)
+
+    def _diagonal_or_scalar_step(self, c, y0, out):
+        """srk.py:57-88.  Distinct evaluations only: f0,g0 at (t0,y0); f1 at (t0+dt, H0_1);
+        g1 at (t0+dt/4, H1_1); f2 at (t0+dt/2, H0_2); g2 at (t0+dt, H1_2); g3 at (t0+dt/4, H1_3)."""
+        lib, sde, s = self._lib, self.sde, c.scalars
+        if sde.user_g_prod:
+            raise NotImplementedError("torchsde_b200: srk with a user-supplied g_prod is not supported; "
+                                      "provide g (the fused kernel performs the product).")
+        t_00, t_1, t_q, t_h = c.aux_t  # t0 + 0*dt, t0 + dt, t0 + dt/4, t0 + dt/2
+        LU = self._LU
+        f0 = _contig(sde.f(t_00, y0))
+        g0 = _contig(sde.g(t_00, y0))
+        h0_1, h1_1 = torch.empty_like(y0), torch.empty_like(y0)
+        _check(lib.tsde_srk_diag_stage1(LU, _p(y0), _p(f0), _p(g0), c.dt, s['sqrt_dt'], _p(h0_1), _p(h1_1)),
+               "tsde_srk_diag_stage1")
+        f1 = _contig(sde.f(t_1, h0_1))
+        g1 = _contig(sde.g(t_q, h1_1))
+        h0_2, h1_2 = torch.empty_like(y0), torch.empty_like(y0)
+        _check(lib.tsde_srk_diag_stage2(self._L, self._feed.get(c, True), _p(y0), _p(f0), _p(g0), _p(f1), _p(g1),
+                                        c.dt, s['rdt'], s['sqrt_dt'], _p(h0_2), _p(h1_2)), "tsde_srk_diag_stage2")
+        f2 = _contig(sde.f(t_h, h0_2))
+        g2 = _contig(sde.g(t_1, h1_2))
+        h1_3 = torch.empty_like(y0)
+        _check(lib.tsde_srk_diag_stage3(LU, _p(y0), _p(g0), _p(g1), _p(f2), _p(g2), c.dt, s['sqrt_dt'], _p(h1_3)),
+               "tsde_srk_diag_stage3")
+        g3 = _contig(sde.g(t_q, h1_3))
+        _check(lib.tsde_step_srk_diag(self._L, self._feed.get(c, True), _p(y0), _p(f0), _p(f1), _p(f2), _p(g0),
+                                      _p(g1), _p(g2), _p(g3), c.dt, s['rdt'], s['sqrt_dt'], s['three_dt'],
+                                      _p(out)), "tsde_step_srk_diag")
+        return ()
+
+    def _additive_step(self, c, y0, out):
+        """srk.py:90-111: f0 = f(t0, y0); gA = g(t0+dt, y0); f1 = f(t0+3/4dt, H0_1); gB = g(t0, y0)."""
+        lib, sde, s = self._lib, self.sde, c.scalars
+        if sde.user_g_prod:
+            raise NotImplementedError("torchsde_b200: srk with a user-supplied g_prod is not supported; "
+                                      "provide g (the fused kernel performs the product).")
+        t_1, t_34, t_00 = c.aux_t
+        f0 = _contig(sde.f(t_00, y0))
+        ga = _contig(sde.g(t_1, y0))
+        h0_1 = torch.empty_like(y0)
+        if self.m == 1:
+            raise NotImplementedError("torchsde_b200: additive srk needs m > 1 (use noise_type='scalar' for m == 1).")
+        _check(lib.tsde_srk_additive_stage(self._L, self._feed.get(c, True), _p(y0), _p(f0), _p(ga), c.dt, s['rdt'],
+                                           _p(h0_1)), "tsde_srk_additive_stage")
+        f1 = _contig(sde.f(t_34, h0_1))
+        gb = _contig(sde.g(t_00, y0))
+        _check(lib.tsde_step_srk_additive(self._L, self._feed.get(c, True), _p(y0), _p(f0), _p(f1), _p(ga), _p(gb),
+                                          c.dt, s['rdt'], _p(out)), "tsde_step_srk_additive")
+        return ()
+
+
+class LogODEMidpoint(base_solver.BaseSDESolver):
+    """methods/log_ode.py:25-56 — constructor contract only; the Levy-area step is SURVEY §8(f) 'next'."""
+    weak_order = 1.0
+    sde_type = SDE_TYPES.stratonovich
+    noise_types = NOISE_TYPES.all()
+    levy_area_approximations = (LEVY_AREA_APPROXIMATIONS.davie, LEVY_AREA_APPROXIMATIONS.foster)
+
+    def __init__(self, sde, **kwargs):
+        if getattr(sde, 'is_adjoint_sde', False):
+            raise ValueError("Log-ODE schemes cannot be used for adjoint SDEs, because they require "
+                             "direct access to the diffusion, whilst adjoint SDEs rely on a more efficient "
+                             "diffusion-vector product. Use a different method instead.")
+        self.strong_order = 0.5 if sde.noise_type == NOISE_TYPES.general else 1.0
+        super(LogODEMidpoint, self).__init__(sde=sde, **kwargs)
+
+    def _step(self, c, y0, extra0, out):
+        raise NotImplementedError("torchsde_b200: the log-ODE (Levy area) step is not implemented yet.")
+
+
+def select(method, sde_type):
+    """methods/__init__.py:26-48."""
+    if method == METHODS.euler:
+        return Euler
+    elif method == METHODS.milstein and sde_type == SDE_TYPES.ito:
+        return MilsteinIto
+    elif method == METHODS.srk:
+        return SRK
+    elif method == METHODS.midpoint:
+        return Midpoint
+    elif method == METHODS.reversible_heun:
+        return ReversibleHeun
+    elif method == METHODS.adjoint_reversible_heun:
+        from .adjoint import AdjointReversibleHeun
+        return AdjointReversibleHeun
+    elif method == METHODS.heun:
+        return Heun
+    elif method == METHODS.milstein and sde_type == SDE_TYPES.stratonovich:
+        return MilsteinStratonovich
+    elif method == METHODS.log_ode_midpoint:
+        return LogODEMidpoint
+    elif method == METHODS.euler_heun:
+        return EulerHeun
+    else:
+        raise ValueError(f"Method '{method}' does not match any known method.")

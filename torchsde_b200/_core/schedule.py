@@ -1,0 +1,80 @@
+"""Fixed-step time grid of a solve, computed once on the host.
+
+Restates the control flow of ``BaseSDESolver.integrate`` (reference:
+torchsde/_core/base_solver.py:92-149, fixed-step branch :143-147) *without* running it on the
+device: the reference evaluates ``while curr_t < out_t`` and ``min(curr_t + dt, ts[-1])`` on 0-d
+device tensors, i.e. with two or three host<->device syncs per step.  Here the same expressions
+are evaluated once with 0-d CPU tensors of the same dtype (so rounding — e.g. the accumulation
+of ``curr_t + dt`` in fp32, which gives 1001 steps for dt=1e-3 on [0,1] — is bit-identical), and
+the resulting plan is what the CUDA-graph time loop executes.
+"""
+import torch
+
+
+class Output:
+    """Row `index` of ys is produced after step `step`:
+    aligned -> ys[index] is that step's y1 itself; else the linear interpolation
+    w0 * prev_y + w1 * curr_y of _core/interp.py:15-18 (weights computed in ts' dtype)."""
+    __slots__ = ('index', 'step', 'aligned', 'w0', 'w1')
+
+    def __init__(self, index, step, aligned, w0, w1):
+        self.index = index
+        self.step = step
+        self.aligned = aligned
+        self.w0 = w0
+        self.w1 = w1
+
+
+class Schedule:
+    """steps[k] = (t0, t1) as 0-d CPU tensors in ts' dtype; outputs = list of Output."""
+
+    def __init__(self, ts_cpu, steps, outputs):
+        self.ts = ts_cpu
+        self.steps = steps
+        self.outputs = outputs
+        self.n_steps = len(steps)
+        # python floats (exact) of the step boundaries, used by the Brownian grid binding
+        self.bounds = [float(steps[0][0])] + [float(s[1]) for s in steps] if steps else [float(ts_cpu[0])]
+        outs_after = {}
+        for o in outputs:
+            outs_after.setdefault(o.step, []).append(o)
+        self.outputs_after = outs_after
+
+    def aligned_row(self, k):
+        """Row of ys that coincides with the end of step k (or None)."""
+        for o in self.outputs_after.get(k, ()):
+            if o.aligned:
+                return o.index
+        return None
+
+
+def build_schedule(ts, dt):
+    """ts: 1-D tensor (any device); dt: python float or 0-d tensor.  base_solver.py:107-147."""
+    ts_cpu = ts.detach().to('cpu')
+    step_size = dt.detach().to('cpu') if torch.is_tensor(dt) else dt
+    curr_t = ts_cpu[0]
+    prev_t = curr_t
+    end_t = ts_cpu[-1]
+    steps = []
+    outputs = []
+    for i in range(1, ts_cpu.numel()):
+        out_t = ts_cpu[i]
+        while curr_t < out_t:
+            next_t = min(curr_t + step_size, end_t)
+            if not (next_t > curr_t):
+                raise ValueError("Step size `dt` is too small to advance time in the dtype of `ts`.")
+            prev_t = curr_t
+            steps.append((curr_t, next_t))
+            curr_t = next_t
+        k = len(steps) - 1
+        if k < 0:
+            raise ValueError("Evaluation times `ts` must be strictly increasing.")
+        aligned = bool(curr_t == out_t)
+        if aligned:
+            w0, w1 = 0.0, 1.0
+        else:
+            # interp.py:17 — (t1 - t)/(t1 - t0) * y0 + (t - t0)/(t1 - t0) * y1
+            w0 = float((curr_t - out_t) / (curr_t - prev_t))
+            w1 = float((out_t - prev_t) / (curr_t - prev_t))
+        outputs.append(Output(i, k, aligned, w0, w1))
+    return Schedule(ts_cpu, steps, outputs)

@@ -1,0 +1,239 @@
+"""`sdeint`: public entry point of the forward solve.
+
+Signature, defaults, validation errors and return conventions follow the reference
+(torchsde/_core/sdeint.py: `sdeint` :27-112, `check_contract` :115-281, `parse_return`
+:284-300); the integration itself is done by the CUDA engine (base_solver.py, methods.py).
+
+Known differences, by design:
+* tensors must live on a CUDA device (there is no CPU path);
+* gradients do not flow through `sdeint` (the tableau kernels are not autograd nodes);
+  use `sdeint_adjoint` for training, as the reference recommends for memory reasons anyway;
+* `adaptive=True` raises NotImplementedError ("next").
+"""
+import warnings
+
+import torch
+
+from . import base_sde
+from . import methods
+from .. import _cabi
+from .._brownian import BrownianInterval
+from ..settings import LEVY_AREA_APPROXIMATIONS, METHODS, NOISE_TYPES, SDE_TYPES
+
+
+def handle_unused_kwargs(unused_kwargs, msg=None):
+    # misc.py:26-31
+    if len(unused_kwargs) > 0:
+        if msg is not None:
+            warnings.warn(f"{msg}: Unexpected arguments {unused_kwargs}")
+        else:
+            warnings.warn(f"Unexpected arguments {unused_kwargs}")
+
+
+def assert_no_grad(names, maybe_tensors):
+    # misc.py:20-23
+    for name, maybe_tensor in zip(names, maybe_tensors):
+        if torch.is_tensor(maybe_tensor) and maybe_tensor.requires_grad:
+            raise ValueError(f"Argument {name} must not require gradient.")
+
+
+def sdeint(sde, y0, ts, bm=None, method=None, dt=1e-3, adaptive=False, rtol=1e-5, atol=1e-4, dt_min=1e-5,
+           options=None, names=None, logqp=False, extra=False, extra_solver_state=None, **unused_kwargs):
+    """Numerically integrate an SDE (reference docstring: sdeint.py:43-92).
+
+    Returns ys of size (T, batch_size, d); with `logqp` also the log-ratio increments (T-1, batch);
+    with `extra` also the solver's final extra state.
+    """
+    handle_unused_kwargs(unused_kwargs, msg="`sdeint`")
+    del unused_kwargs
+
+    sde, y0, ts, bm, method, options = check_contract(sde, y0, ts, bm, method, adaptive, options, names, logqp)
+    assert_no_grad(['ts', 'dt', 'rtol', 'atol', 'dt_min'], [ts, dt, rtol, atol, dt_min])
+
+    solver_fn = methods.select(method=method, sde_type=sde.sde_type)
+    solver = solver_fn(sde=sde, bm=bm, dt=dt, adaptive=adaptive, rtol=rtol, atol=atol, dt_min=dt_min,
+                       options=options)
+    _cabi.require_cuda(y0)
+    with torch.no_grad():
+        if extra_solver_state is None:
+            extra_solver_state = solver.init_extra_solver_state(ts[0], y0)
+        ys, extra_solver_state = _integrate(solver, y0, ts, extra_solver_state, options)
+    return parse_return(y0, ys, extra_solver_state, extra, logqp)
+
+
+def _integrate(solver, y0, ts, extra_solver_state, options):
+    if options.get('cuda_graph', False):
+        from . import graph
+        return graph.integrate_captured(solver, y0, ts, extra_solver_state)
+    return solver.integrate(y0, ts, extra_solver_state)
+
+
+class _Sizes:
+    """Collects the batch / state / noise sizes seen while probing the SDE (sdeint.py:168-248)."""
+
+    def __init__(self, noise_type):
+        self.noise_type = noise_type
+        self.batch, self.state, self.noise = [], [], []
+
+    def two_d(self, name, shape):
+        if len(shape) != 2:
+            raise ValueError(f"{name} must be of shape (batch, state_channels), but got {shape}.")
+        self.batch.append(shape[0])
+        self.state.append(shape[1])
+
+    def diffusion(self, name, shape):
+        if self.noise_type == NOISE_TYPES.diagonal:
+            if len(shape) != 2:
+                raise ValueError(f"{name} must be of shape (batch, state_channels), but got {shape}.")
+            self.batch.append(shape[0])
+            self.state.append(shape[1])
+            self.noise.append(shape[1])
+        else:
+            if len(shape) != 3:
+                raise ValueError(f"{name} must be of shape (batch, state_channels, noise_channels), but got {shape}.")
+            self.batch.append(shape[0])
+            self.state.append(shape[1])
+            self.noise.append(shape[2])
+
+    def need_noise_size(self):
+        if len(self.noise) == 0:
+            raise ValueError("Cannot infer noise size (i.e. number of Brownian motion channels). Either pass `bm` "
+                             "explicitly, or specify one of the `g`, `f_and_g` functions.`")
+
+    def consistent(self):
+        if any(b != self.batch[0] for b in self.batch[1:]):
+            raise ValueError("Batch sizes not consistent.")
+        if any(s != self.state[0] for s in self.state[1:]):
+            raise ValueError("State sizes not consistent.")
+        if any(n != self.noise[0] for n in self.noise[1:]):
+            raise ValueError("Noise sizes not consistent.")
+
+
+def _is_strictly_increasing(ts):
+    return all(x < y for x, y in zip(ts[:-1], ts[1:]))
+
+
+def check_contract(sde, y0, ts, bm, method, adaptive, options, names, logqp):
+    """Validate and normalise the arguments of a solve; reference sdeint.py:115-281."""
+    rename = {}
+    if names is not None:
+        rename = {key: names[key] for key in ("drift", "diffusion", "prior_drift", "drift_and_diffusion",
+                                              "drift_and_diffusion_prod") if key in names}
+    if len(rename) > 0:
+        sde = base_sde.RenameMethodsSDE(sde, **rename)
+
+    if not hasattr(sde, "noise_type"):
+        raise ValueError("sde does not have the attribute noise_type.")
+    if sde.noise_type not in NOISE_TYPES:
+        raise ValueError(f"Expected noise type in {NOISE_TYPES}, but found {sde.noise_type}.")
+    if not hasattr(sde, "sde_type"):
+        raise ValueError("sde does not have the attribute sde_type.")
+    if sde.sde_type not in SDE_TYPES:
+        raise ValueError(f"Expected sde type in {SDE_TYPES}, but found {sde.sde_type}.")
+
+    if not torch.is_tensor(y0):
+        raise ValueError("`y0` must be a torch.Tensor.")
+    if y0.dim() != 2:
+        raise ValueError("`y0` must be a 2-dimensional tensor of shape (batch, channels).")
+
+    if logqp:  # backwards compatibility v0.1.1, sdeint.py:141-145
+        sde = base_sde.SDELogqp(sde)
+        y0 = torch.cat((y0, y0.new_zeros(size=(y0.size(0), 1))), dim=1)
+
+    if method is None:
+        if sde.sde_type == SDE_TYPES.stratonovich:
+            method = METHODS.midpoint
+        elif sde.noise_type == NOISE_TYPES.general:
+            method = METHODS.euler
+        else:
+            method = METHODS.srk
+    if method not in METHODS:
+        raise ValueError(f"Expected method in {METHODS}, but found {method}.")
+
+    if not torch.is_tensor(ts):
+        if not isinstance(ts, (tuple, list)) or not all(isinstance(t, (float, int)) for t in ts):
+            raise ValueError("Evaluation times `ts` must be a 1-D Tensor or list/tuple of floats.")
+        ts = torch.tensor(ts, dtype=y0.dtype, device=y0.device)
+    if not _is_strictly_increasing(ts.detach().cpu().tolist() if ts.is_cuda else ts):
+        raise ValueError("Evaluation times `ts` must be strictly increasing.")
+
+    sizes = _Sizes(sde.noise_type)
+    sizes.batch.append(y0.size(0))
+    sizes.state.append(y0.size(1))
+    if bm is not None:
+        if len(bm.shape) != 2:
+            raise ValueError("`bm` must be of shape (batch, noise_channels).")
+        sizes.batch.append(bm.shape[0])
+        sizes.noise.append(bm.shape[1])
+
+    has_f = has_g = False
+    with torch.no_grad():
+        if hasattr(sde, 'f'):
+            has_f = True
+            sizes.two_d('Drift', tuple(sde.f(ts[0], y0).size()))
+        if hasattr(sde, 'g'):
+            has_g = True
+            sizes.diffusion('Diffusion', tuple(sde.g(ts[0], y0).size()))
+        if hasattr(sde, 'f_and_g'):
+            has_f = has_g = True
+            _f, _g = sde.f_and_g(ts[0], y0)
+            sizes.two_d('Drift', tuple(_f.size()))
+            sizes.diffusion('Diffusion', tuple(_g.size()))
+        if hasattr(sde, 'g_prod'):
+            has_g = True
+            sizes.need_noise_size()
+            v = torch.randn(sizes.batch[0], sizes.noise[0], dtype=y0.dtype, device=y0.device)
+            sizes.two_d('Diffusion-vector product', tuple(sde.g_prod(ts[0], y0, v).size()))
+        if hasattr(sde, 'f_and_g_prod'):
+            has_f = has_g = True
+            sizes.need_noise_size()
+            v = torch.randn(sizes.batch[0], sizes.noise[0], dtype=y0.dtype, device=y0.device)
+            _f, _g_prod = sde.f_and_g_prod(ts[0], y0, v)
+            sizes.two_d('Drift', tuple(_f.size()))
+            sizes.two_d('Diffusion-vector product', tuple(_g_prod.size()))
+
+    if not has_f:
+        raise ValueError("sde must define at least one of `f`, `f_and_g`, or `f_and_g_prod`. (Or possibly more "
+                         "depending on the method chosen.)")
+    if not has_g:
+        raise ValueError("sde must define at least one of `g`, `f_and_g`, `g_prod` or `f_and_g_prod`. (Or possibly "
+                         "more depending on the method chosen.)")
+    sizes.consistent()
+
+    if sde.noise_type == NOISE_TYPES.scalar:
+        if sizes.noise[0] != 1:
+            raise ValueError(f"Scalar noise must have only one channel; the diffusion has {sizes.noise[0]} noise "
+                             f"channels.")
+
+    sde = base_sde.ForwardSDE(sde)
+
+    if bm is None:
+        if method == METHODS.srk:
+            levy_area_approximation = LEVY_AREA_APPROXIMATIONS.space_time
+        elif method == METHODS.log_ode_midpoint:
+            levy_area_approximation = LEVY_AREA_APPROXIMATIONS.foster
+        else:
+            levy_area_approximation = LEVY_AREA_APPROXIMATIONS.none
+        bm = BrownianInterval(t0=ts[0], t1=ts[-1], size=(sizes.batch[0], sizes.noise[0]), dtype=y0.dtype,
+                              device=y0.device, levy_area_approximation=levy_area_approximation)
+
+    options = {} if options is None else options.copy()
+
+    if adaptive and method == METHODS.euler and sde.noise_type != NOISE_TYPES.additive:
+        warnings.warn("Numerical solution is not guaranteed to converge to the correct solution when using adaptive "
+                      "time-stepping with the Euler--Maruyama method with non-additive noise.")
+
+    return sde, y0, ts, bm, method, options
+
+
+def parse_return(y0, ys, extra_solver_state, extra, logqp):
+    """sdeint.py:284-300."""
+    if logqp:
+        ys, log_ratio = ys.split(split_size=(y0.size(1) - 1, 1), dim=2)
+        log_ratio_increments = (log_ratio[1:] - log_ratio[:-1]).squeeze(dim=2)
+        if extra:
+            return ys, log_ratio_increments, extra_solver_state
+        return ys, log_ratio_increments
+    if extra:
+        return ys, extra_solver_state
+    return ys

@@ -1,0 +1,432 @@
+// Brownian source kernels: materialise increments of whole cells, Brownian-bridge descent,
+// interval merges, Davie/Foster Levy area.  Replaces the tensor arithmetic of
+// torchsde/_brownian/brownian_interval.py (the interval *tree* stays on the host,
+// torchsde_b200/_brownian/interval.py).
+#include "ew.cuh"
+
+namespace tsde {
+
+// ---- cells -> (W, U, H) ---------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+cells_kernel(NoiseP<T> nz, int64_t rows, int64_t m, int64_t qpr, int vec, T* out_w) {
+  const Key key = load_key(nz.key);
+  const int64_t nquads = rows * qpr;
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t Q = (int64_t)blockIdx.x * kThreads + threadIdx.x; Q < nquads; Q += stride) {
+    const int64_t row = Q / qpr, q = Q - row * qpr;
+    const int64_t base = row * m + 4 * q;
+    const int64_t rem = m - 4 * q;
+    const int nvalid = rem < 4 ? (int)rem : 4;
+    T w[4], u[4];
+    counter_noise<T, false>(nz, key, (uint32_t)(row + nz.row_offset), (uint32_t)q, w, u);
+    store_quad(out_w, base, vec != 0, nvalid, w);
+  }
+}
+
+// Variant that also exposes H itself (the bridge descent consumes it).
+template <typename T>
+__device__ __forceinline__ void counter_wh(const NoiseP<T>& nz, Key key, uint32_t row, uint32_t q,
+                                           T (&w)[4], T (&hh)[4]) {
+  double len0 = nz.cell_h ? nz.cell_h[0] : nz.h;
+  T n[4];
+  normal4(key, nz.cell_id, STREAM_W, row, q, n);
+  const T s = (T)sqrt(len0);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) w[j] = n[j] * s;
+  normal4(key, nz.cell_id, STREAM_H, row, q, n);
+  const T s12 = (T)sqrt(len0 / 12.0);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) hh[j] = n[j] * s12;
+  double elapsed = len0;
+  for (int c = 1; c < nz.n_cells; ++c) {
+    const double len = nz.cell_h ? nz.cell_h[c] : nz.h;
+    T wi[4];
+    normal4(key, nz.cell_id + (uint64_t)c, STREAM_W, row, q, n);
+    const T si = (T)sqrt(len);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) wi[j] = n[j] * si;
+    normal4(key, nz.cell_id + (uint64_t)c, STREAM_H, row, q, n);
+    const T s12i = (T)sqrt(len / 12.0);
+    const T tl = (T)len, te = (T)elapsed, tt = (T)(elapsed + len);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const T hi = n[j] * s12i;
+      const T term1 = tl * (hi + T(0.5) * w[j]);
+      const T term2 = te * (hh[j] - T(0.5) * wi[j]);
+      hh[j] = (term1 + term2) / tt;
+      w[j] = w[j] + wi[j];
+    }
+    elapsed += len;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+cells_wh_kernel(NoiseP<T> nz, int64_t rows, int64_t m, int64_t qpr, int vec, T* out_w, T* out_u,
+                T* out_h) {
+  const Key key = load_key(nz.key);
+  const int64_t nquads = rows * qpr;
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  const T ht = (T)nz.h_total;
+  for (int64_t Q = (int64_t)blockIdx.x * kThreads + threadIdx.x; Q < nquads; Q += stride) {
+    const int64_t row = Q / qpr, q = Q - row * qpr;
+    const int64_t base = row * m + 4 * q;
+    const int64_t rem = m - 4 * q;
+    const int nvalid = rem < 4 ? (int)rem : 4;
+    T w[4], hh[4];
+    counter_wh<T>(nz, key, (uint32_t)(row + nz.row_offset), (uint32_t)q, w, hh);
+    store_quad(out_w, base, vec != 0, nvalid, w);
+    if (out_h) store_quad(out_h, base, vec != 0, nvalid, hh);
+    if (out_u) {
+      T u[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) u[j] = ht * (T(0.5) * w[j] + hh[j]);
+      store_quad(out_u, base, vec != 0, nvalid, u);
+    }
+  }
+}
+
+static inline unsigned grid_for(int64_t nquads) {
+  int64_t blocks = (nquads + kThreads - 1) / kThreads;
+  const int64_t cap = (int64_t)kSMs * kBlocksPerSM;
+  return (unsigned)(blocks > cap ? cap : blocks);
+}
+
+template <typename T>
+static int cells_impl(const tsde_launch* L, const tsde_noise* nz, void* out_w, void* out_u,
+                      void* out_h) {
+  if (!nz || nz->source != TSDE_SRC_COUNTER || !out_w) return TSDE_EINVAL;
+  NoiseP<T> np;
+  if (int e = fill_noise<T>(L, nz, false, np)) return e;
+  const int64_t m = L->m, rows = L->rows, qpr = (m + 3) / 4, nquads = rows * qpr;
+  if (nquads == 0) return 0;
+  if (rows + nz->row_offset > 0xFFFFFFFFll) return TSDE_EINVAL;
+  const bool vec = (m % 4 == 0) && aligned16(out_w) && (!out_u || aligned16(out_u)) &&
+                   (!out_h || aligned16(out_h));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(L->stream);
+  if (out_u || out_h) {
+    cells_wh_kernel<T><<<grid_for(nquads), kThreads, 0, st>>>(np, rows, m, qpr, vec, (T*)out_w,
+                                                             (T*)out_u, (T*)out_h);
+  } else {
+    cells_kernel<T><<<grid_for(nquads), kThreads, 0, st>>>(np, rows, m, qpr, vec, (T*)out_w);
+  }
+  return (int)cudaGetLastError();
+}
+
+// ---- Brownian bridge descent ------------------------------------------------------------------
+constexpr int kMaxBridgeDepth = 24;
+struct BridgeLevel {
+  uint64_t id;
+  double k[6];
+};
+struct BridgeP {
+  BridgeLevel lv[kMaxBridgeDepth];
+  int32_t depth;
+  int32_t have_h;
+};
+
+template <typename T, bool HAVE_H>
+__global__ void __launch_bounds__(kThreads)
+bridge_kernel(const __grid_constant__ BridgeP bp, const void* keyp, int64_t row_offset, int64_t rows,
+              int64_t m, int64_t qpr, int vec, const T* in_w, const T* in_h, T* out_w, T* out_h) {
+  const Key key = load_key(keyp);
+  const int64_t nquads = rows * qpr;
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t Q = (int64_t)blockIdx.x * kThreads + threadIdx.x; Q < nquads; Q += stride) {
+    const int64_t row = Q / qpr, q = Q - row * qpr;
+    const int64_t base = row * m + 4 * q;
+    const int64_t rem = m - 4 * q;
+    const int nvalid = rem < 4 ? (int)rem : 4;
+    const uint32_t grow = (uint32_t)(row + row_offset);
+    T w[4], hh[4];
+    load_quad(in_w, base, vec != 0, nvalid, w);
+    if (HAVE_H) load_quad(in_h, base, vec != 0, nvalid, hh);
+    for (int l = 0; l < bp.depth; ++l) {
+      const BridgeLevel& lv = bp.lv[l];
+      T x1[4];
+      normal4(key, lv.id, STREAM_X1, grow, (uint32_t)q, x1);
+      if (HAVE_H) {
+        // brownian_interval.py:199-225
+        T x2[4];
+        normal4(key, lv.id, STREAM_X2, grow, (uint32_t)q, x2);
+        const T k1 = (T)lv.k[0], k2 = (T)lv.k[1], k3 = (T)lv.k[2], k4 = (T)lv.k[3],
+                k5 = (T)lv.k[4], k6 = (T)lv.k[5];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const T ow = (k1 * w[j] + k2 * hh[j]) + k3 * x1[j];
+          const T oh = (k4 * hh[j] + k5 * x1[j]) + k6 * x2[j];
+          w[j] = ow;
+          hh[j] = oh;
+        }
+      } else {
+        // brownian_interval.py:226-237 ; k0 = left_diff, k1 = h_reciprocal, k2 = sqrt(var),
+        // k3 = 1 for the left child, 0 for the right child
+        const T ld = (T)lv.k[0], hr = (T)lv.k[1], sd = (T)lv.k[2];
+        const bool left = lv.k[3] != 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const T left_w = (ld * w[j]) * hr + sd * x1[j];
+          w[j] = left ? left_w : (w[j] - left_w);
+        }
+      }
+    }
+    store_quad(out_w, base, vec != 0, nvalid, w);
+    if (HAVE_H) store_quad(out_h, base, vec != 0, nvalid, hh);
+  }
+}
+
+template <typename T>
+static int bridge_impl(const tsde_launch* L, const void* key, int64_t row_offset, int32_t depth,
+                       const uint64_t* ids, const int32_t* is_left, const double* times,
+                       const void* in_w, const void* in_h, void* out_w, void* out_h) {
+  if (!key || !in_w || !out_w || depth < 0 || (depth > 0 && (!ids || !is_left || !times)))
+    return TSDE_EINVAL;
+  const bool have_h = in_h != nullptr;
+  if (have_h && !out_h) return TSDE_EINVAL;
+  const int64_t m = L->m, rows = L->rows, qpr = (m + 3) / 4, nquads = rows * qpr;
+  if (nquads == 0) return 0;
+  if (rows + row_offset > 0xFFFFFFFFll) return TSDE_EINVAL;
+  const bool vec = (m % 4 == 0) && aligned16(in_w) && aligned16(out_w) &&
+                   (!have_h || (aligned16(in_h) && aligned16(out_h)));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(L->stream);
+  const void* cur_w = in_w;
+  const void* cur_h = in_h;
+  int done = 0;
+  do {
+    BridgeP bp{};
+    const int n = depth - done < kMaxBridgeDepth ? depth - done : kMaxBridgeDepth;
+    bp.depth = n;
+    bp.have_h = have_h;
+    for (int l = 0; l < n; ++l) {
+      const int i = done + l;
+      const double start = times[3 * i], mid = times[3 * i + 1], end = times[3 * i + 2];
+      const double h_rec = 1.0 / (end - start);
+      const double ld = mid - start, rd = end - mid;
+      BridgeLevel& lv = bp.lv[l];
+      lv.id = ids[i];
+      if (have_h) {
+        const double ld2 = ld * ld, rd2 = rd * rd;
+        const double ld3 = ld * ld2, rd3 = rd * rd2;
+        const double v = 0.5 * sqrt(ld * rd / (ld3 + rd3));
+        const double a = v * ld2 * h_rec;
+        const double b = v * rd2 * h_rec;
+        const double c = v * 0.57735026918962584;  // 1/sqrt(3)
+        const double third = 2 * (a * ld + b * rd) * h_rec;
+        if (is_left[i]) {
+          const double first = ld * h_rec;
+          const double second = 6 * first * rd * h_rec;
+          lv.k[0] = first; lv.k[1] = second; lv.k[2] = third;
+          lv.k[3] = first * first; lv.k[4] = -a; lv.k[5] = c * rd;
+        } else {
+          const double first = rd * h_rec;
+          const double second = 6 * first * ld * h_rec;
+          lv.k[0] = first; lv.k[1] = -second; lv.k[2] = -third;
+          lv.k[3] = first * first; lv.k[4] = -b; lv.k[5] = -(c * ld);
+        }
+      } else {
+        lv.k[0] = ld; lv.k[1] = h_rec; lv.k[2] = sqrt(ld * rd * h_rec);
+        lv.k[3] = is_left[i] ? 1.0 : 0.0;
+      }
+    }
+    if (have_h) {
+      bridge_kernel<T, true><<<grid_for(nquads), kThreads, 0, st>>>(
+          bp, key, row_offset, rows, m, qpr, vec, (const T*)cur_w, (const T*)cur_h, (T*)out_w,
+          (T*)out_h);
+    } else {
+      bridge_kernel<T, false><<<grid_for(nquads), kThreads, 0, st>>>(
+          bp, key, row_offset, rows, m, qpr, vec, (const T*)cur_w, nullptr, (T*)out_w, nullptr);
+    }
+    done += n;
+    cur_w = out_w;  // further chunks continue in place
+    cur_h = out_h;
+  } while (done < depth);
+  return (int)cudaGetLastError();
+}
+
+// ---- merges ------------------------------------------------------------------------------------
+// brownian_interval.py:649-672
+template <typename T>
+struct MergeWHOp {
+  static constexpr int NIN = 4, NOUT = 2;
+  static constexpr bool USES_NOISE = false, WANT_U = false;
+  T len1, len0, tot;
+  __device__ __forceinline__ void operator()(const T (&in)[4], T, T, T (&out)[2]) const {
+    const T w = in[0], h = in[1], wi = in[2], hi = in[3];
+    const T term1 = len1 * (hi + T(0.5) * w);
+    const T term2 = len0 * (h - T(0.5) * wi);
+    out[1] = (term1 + term2) / tot;
+    out[0] = w + wi;
+  }
+};
+template <typename T>
+struct AddOp {
+  static constexpr int NIN = 2, NOUT = 1;
+  static constexpr bool USES_NOISE = false, WANT_U = false;
+  __device__ __forceinline__ void operator()(const T (&in)[2], T, T, T (&out)[1]) const {
+    out[0] = in[0] + in[1];
+  }
+};
+template <typename T>
+struct HToUOp {
+  static constexpr int NIN = 2, NOUT = 1;
+  static constexpr bool USES_NOISE = false, WANT_U = false;
+  T h;
+  __device__ __forceinline__ void operator()(const T (&in)[2], T, T, T (&out)[1]) const {
+    out[0] = h * (T(0.5) * in[0] + in[1]);
+  }
+};
+
+// ---- Davie / Foster Levy area                                   brownian_interval.py:78-99
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+levy_area_kernel(const void* keyp, int64_t row_offset, uint64_t a_id, int64_t rows, int64_t m,
+                 const T* w, const T* hh, T tenth_h, T davie_std, int foster, T* out) {
+  const Key key = load_key(keyp);
+  const int64_t mm = m * m, total = rows * mm;
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x; e < total; e += stride) {
+    const int64_t row = e / mm;
+    const int64_t ij = e - row * mm;
+    const int64_t i = ij / m, j = ij - i * m;
+    const uint32_t grow = (uint32_t)(row + row_offset);
+    const int64_t ji = j * m + i;
+    T n4[4];
+    normal4(key, a_id, STREAM_A, grow, (uint32_t)(ij >> 2), n4);
+    const T nij = n4[ij & 3];
+    normal4(key, a_id, STREAM_A, grow, (uint32_t)(ji >> 2), n4);
+    const T nji = n4[ji & 3];
+    const T wi = w[row * m + i], wj = w[row * m + j];
+    const T hi = hh[row * m + i], hj = hh[row * m + j];
+    T a = hi * wj - wi * hj;
+    const T noise = nij - nji;
+    T std_;
+    if (foster) {
+      std_ = sqrt(tenth_h * ((tenth_h + hi * hi) + hj * hj));
+    } else {
+      std_ = davie_std;
+    }
+    out[e] = a + std_ * noise;
+  }
+}
+
+// A <- A + Ai + 0.5 (W (x) Wi - Wi (x) W)                         brownian_interval.py:671
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+merge_area_kernel(int64_t rows, int64_t m, T* a0, const T* a1, const T* w0, const T* w1) {
+  const int64_t mm = m * m, total = rows * mm;
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x; e < total; e += stride) {
+    const int64_t row = e / mm;
+    const int64_t ij = e - row * mm;
+    const int64_t i = ij / m, j = ij - i * m;
+    const T x = w0[row * m + i] * w1[row * m + j] - w1[row * m + i] * w0[row * m + j];
+    a0[e] = (a0[e] + a1[e]) + T(0.5) * x;
+  }
+}
+
+}  // namespace tsde
+
+using namespace tsde;
+
+template <typename T>
+static int levy_impl(const tsde_launch* L, const void* key, int64_t row_offset, uint64_t a_id,
+                     const void* w, const void* hh, double h, int32_t foster, void* out_a) {
+  if (!key || !w || !hh || !out_a) return TSDE_EINVAL;
+  const int64_t total = L->rows * L->m * L->m;
+  if (total == 0) return 0;
+  if (L->rows + row_offset > 0xFFFFFFFFll) return TSDE_EINVAL;
+  if (L->m * L->m > (1ll << 26)) return TSDE_EINVAL;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(L->stream);
+  const double r12 = 1.0 / 12.0;
+  levy_area_kernel<T><<<grid_for(total), kThreads, 0, st>>>(
+      key, row_offset, a_id, L->rows, L->m, (const T*)w, (const T*)hh, (T)(0.1 * h),
+      (T)sqrt(r12 * h * h), foster, (T*)out_a);
+  return (int)cudaGetLastError();
+}
+
+template <typename T>
+static int merge_area_impl(const tsde_launch* L, void* a0, const void* a1, const void* w0,
+                           const void* w1) {
+  if (!a0 || !a1 || !w0 || !w1) return TSDE_EINVAL;
+  const int64_t total = L->rows * L->m * L->m;
+  if (total == 0) return 0;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(L->stream);
+  merge_area_kernel<T><<<grid_for(total), kThreads, 0, st>>>(L->rows, L->m, (T*)a0, (const T*)a1,
+                                                           (const T*)w0, (const T*)w1);
+  return (int)cudaGetLastError();
+}
+
+
+extern "C" {
+
+int tsde_brownian_cells(const tsde_launch* L, const tsde_noise* nz, void* out_w, void* out_u,
+                        void* out_h) {
+  return TSDE_DISPATCH_DTYPE(L, cells_impl<float>(L, nz, out_w, out_u, out_h),
+                             cells_impl<double>(L, nz, out_w, out_u, out_h));
+}
+
+int tsde_brownian_bridge(const tsde_launch* L, const void* key, int64_t row_offset, int32_t depth,
+                         const uint64_t* ids, const int32_t* is_left, const double* times,
+                         const void* in_w, const void* in_h, void* out_w, void* out_h) {
+  return TSDE_DISPATCH_DTYPE(
+      L,
+      bridge_impl<float>(L, key, row_offset, depth, ids, is_left, times, in_w, in_h, out_w, out_h),
+      bridge_impl<double>(L, key, row_offset, depth, ids, is_left, times, in_w, in_h, out_w,
+                          out_h));
+}
+
+// The Brownian tensors are (rows, m); reuse the row-wise framework with d := m.
+static tsde_launch as_rows_m(const tsde_launch* L) {
+  tsde_launch r = *L;
+  r.d = L->m;
+  r.noise_type = TSDE_NOISE_DIAGONAL;
+  return r;
+}
+
+int tsde_brownian_merge(const tsde_launch* L, void* w0, void* h0, const void* w1, const void* h1,
+                        double len0, double len1, double tot) {
+  const tsde_launch r = as_rows_m(L);
+  if (h0 && h1) {
+    const void* ins[4] = {w0, h0, w1, h1};
+    void* outs[2] = {w0, h0};
+    return TSDE_DISPATCH_DTYPE(
+        L,
+        (launch_ew<float, MergeWHOp<float>>(
+            &r, nullptr, false, ins, outs,
+            MergeWHOp<float>{(float)len1, (float)len0, (float)tot})),
+        (launch_ew<double, MergeWHOp<double>>(&r, nullptr, false, ins, outs,
+                                              MergeWHOp<double>{len1, len0, tot})));
+  }
+  const void* ins[2] = {w0, w1};
+  void* outs[1] = {w0};
+  return TSDE_DISPATCH_DTYPE(
+      L, (launch_ew<float, AddOp<float>>(&r, nullptr, false, ins, outs, AddOp<float>{})),
+      (launch_ew<double, AddOp<double>>(&r, nullptr, false, ins, outs, AddOp<double>{})));
+}
+
+int tsde_brownian_h_to_u(const tsde_launch* L, const void* w, const void* hh, double h,
+                         void* out_u) {
+  const tsde_launch r = as_rows_m(L);
+  const void* ins[2] = {w, hh};
+  void* outs[1] = {out_u};
+  return TSDE_DISPATCH_DTYPE(
+      L, (launch_ew<float, HToUOp<float>>(&r, nullptr, false, ins, outs, HToUOp<float>{(float)h})),
+      (launch_ew<double, HToUOp<double>>(&r, nullptr, false, ins, outs, HToUOp<double>{h})));
+}
+
+int tsde_brownian_levy_area(const tsde_launch* L, const void* key, int64_t row_offset,
+                            uint64_t a_id, const void* w, const void* hh, double h, int32_t foster,
+                            void* out_a) {
+  return TSDE_DISPATCH_DTYPE(
+      L, levy_impl<float>(L, key, row_offset, a_id, w, hh, h, foster, out_a),
+      levy_impl<double>(L, key, row_offset, a_id, w, hh, h, foster, out_a));
+}
+
+int tsde_brownian_merge_area(const tsde_launch* L, void* a0, const void* a1, const void* w0,
+                             const void* w1) {
+  return TSDE_DISPATCH_DTYPE(L, merge_area_impl<float>(L, a0, a1, w0, w1),
+                             merge_area_impl<double>(L, a0, a1, w0, w1));
+}
+
+}  // extern "C"

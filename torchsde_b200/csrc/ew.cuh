@@ -1,0 +1,296 @@
+// Fused row-wise tableau kernel framework (diagonal noise, and every purely element-wise
+// stage).  One thread owns one "quad": 4 consecutive channels of one trajectory, which is
+// exactly what one Philox4x32 call yields in fp32 — so the Brownian increment of the quad is
+// produced in registers and never touches HBM (north star: "dW in registers").
+//
+// HBM plan (B200: 148 SMs, ~6.5 TB/s measured copy bandwidth): each input tensor is read
+// once with 128-bit loads, each output written once with 128-bit stores; every thread issues
+// all of its loads before the first dependent use (NIN independent LDG.128 in flight per
+// thread), the grid is a multiple of the SM count (persistent grid-stride loop).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/torchsde_b200.h"
+#include "philox.cuh"
+
+namespace tsde {
+
+constexpr int kThreads = 256;
+constexpr int kSMs = 148;        // B200
+constexpr int kBlocksPerSM = 8;  // 2048 threads / SM
+
+template <typename T>
+struct NoiseP {
+  const T* w;         // MEMORY
+  const T* u;         // MEMORY
+  const void* key;    // COUNTER
+  uint64_t cell_id;
+  int64_t row_offset;
+  int32_t n_cells;
+  int32_t bcast;      // noise has a single channel shared by all d (scalar noise, squeezed g)
+  double h;           // uniform cell length
+  const double* cell_h;  // device, or nullptr
+  double h_total;     // tb - ta of the whole query (for U)
+  int64_t m;          // channels of the noise tensor
+};
+
+template <int NIN, int NOUT>
+struct EwP {
+  const void* in[NIN > 0 ? NIN : 1];
+  void* out[NOUT];
+  int64_t rows;
+  int64_t d;
+  int64_t qpr;     // quads per row
+  int64_t nquads;  // rows * qpr
+  int32_t vec;     // all pointers 16B-aligned and d % 4 == 0
+};
+
+// ---- vector load / store helpers ---------------------------------------------------------
+__device__ __forceinline__ void ld4(const float* p, float (&v)[4]) {
+  const float4 t = *reinterpret_cast<const float4*>(p);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void ld4(const double* p, double (&v)[4]) {
+  const double2 a = *reinterpret_cast<const double2*>(p);
+  const double2 b = *reinterpret_cast<const double2*>(p + 2);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ void st4(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void st4(double* p, const double (&v)[4]) {
+  *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+  *reinterpret_cast<double2*>(p + 2) = make_double2(v[2], v[3]);
+}
+
+template <typename T>
+__device__ __forceinline__ void load_quad(const T* p, int64_t base, bool vec, int nvalid,
+                                          T (&v)[4]) {
+  if (vec) {
+    ld4(p + base, v);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = j < nvalid ? p[base + j] : T(0);
+  }
+}
+template <typename T>
+__device__ __forceinline__ void store_quad(T* p, int64_t base, bool vec, int nvalid,
+                                           const T (&v)[4]) {
+  if (vec) {
+    st4(p + base, v);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < nvalid) p[base + j] = v[j];
+  }
+}
+
+// ---- Brownian increment of one quad --------------------------------------------------------
+// Counter mode: merge of n_cells primary cells, left to right, with the reference's
+// aggregation rule (brownian_interval.py:643-672):
+//     H <- ( len_i (H_i + W/2) + (start_i - ta)(H - W_i/2) ) / (end_i - ta) ;  W <- W + W_i
+// Lengths are host doubles rounded once to T (python-float * tensor semantics).
+template <typename T, bool WANT_U>
+__device__ __forceinline__ void counter_noise(const NoiseP<T>& nz, Key key, uint32_t row,
+                                              uint32_t q, T (&w)[4], T (&u)[4]) {
+  T hh[4];
+  double len0 = nz.cell_h ? nz.cell_h[0] : nz.h;
+  {
+    T n[4];
+    normal4(key, nz.cell_id, STREAM_W, row, q, n);
+    const T s = (T)sqrt(len0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) w[j] = n[j] * s;
+    if (WANT_U) {
+      normal4(key, nz.cell_id, STREAM_H, row, q, n);
+      const T s12 = (T)sqrt(len0 / 12.0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) hh[j] = n[j] * s12;
+    }
+  }
+  double elapsed = len0;  // start_i - ta
+  for (int c = 1; c < nz.n_cells; ++c) {
+    const double len = nz.cell_h ? nz.cell_h[c] : nz.h;
+    T n[4], wi[4];
+    normal4(key, nz.cell_id + (uint64_t)c, STREAM_W, row, q, n);
+    const T s = (T)sqrt(len);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) wi[j] = n[j] * s;
+    if (WANT_U) {
+      normal4(key, nz.cell_id + (uint64_t)c, STREAM_H, row, q, n);
+      const T s12 = (T)sqrt(len / 12.0);
+      const T tl = (T)len, te = (T)elapsed, tt = (T)(elapsed + len);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const T hi = n[j] * s12;
+        const T term1 = tl * (hi + T(0.5) * w[j]);
+        const T term2 = te * (hh[j] - T(0.5) * wi[j]);
+        hh[j] = (term1 + term2) / tt;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) w[j] = w[j] + wi[j];
+    elapsed += len;
+  }
+  if (WANT_U) {
+    const T ht = (T)nz.h_total;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) u[j] = ht * (T(0.5) * w[j] + hh[j]);  // _H_to_U :102-103
+  }
+}
+
+template <typename T, int SRC, bool WANT_U>
+__device__ __forceinline__ void quad_noise(const NoiseP<T>& nz, Key key, int64_t row, int64_t q,
+                                           bool vec, int nvalid, T (&w)[4], T (&u)[4]) {
+  if (SRC == TSDE_SRC_UNIT) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { w[j] = T(1); u[j] = T(0); }
+  } else if (SRC == TSDE_SRC_MEMORY) {
+    if (nz.bcast) {
+      const T a = nz.w[row];
+      const T b = WANT_U ? nz.u[row] : T(0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { w[j] = a; u[j] = b; }
+    } else {
+      const int64_t base = row * nz.m + 4 * q;
+      load_quad(nz.w, base, vec, nvalid, w);
+      if (WANT_U) load_quad(nz.u, base, vec, nvalid, u);
+    }
+  } else {
+    const uint32_t grow = (uint32_t)(row + nz.row_offset);
+    if (nz.bcast) {
+      T w4[4], u4[4];
+      counter_noise<T, WANT_U>(nz, key, grow, 0u, w4, u4);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { w[j] = w4[0]; u[j] = WANT_U ? u4[0] : T(0); }
+    } else {
+      counter_noise<T, WANT_U>(nz, key, grow, (uint32_t)q, w, u);
+    }
+  }
+}
+
+// ---- the kernel -----------------------------------------------------------------------------
+// Op: struct with  static constexpr int NIN, NOUT; static constexpr bool USES_NOISE, WANT_U;
+//     template<T> __device__ void operator()(const T (&in)[NIN], T w, T u, T (&out)[NOUT]) const
+template <typename T, typename Op, int SRC>
+__global__ void __launch_bounds__(kThreads)
+ew_kernel(const EwP<Op::NIN, Op::NOUT> p, const NoiseP<T> nz, const Op op) {
+  constexpr int NIN = Op::NIN, NOUT = Op::NOUT;
+  Key key{0u, 0u};
+  if (Op::USES_NOISE && SRC == TSDE_SRC_COUNTER) key = load_key(nz.key);
+  const bool vec = p.vec != 0;
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t Q = (int64_t)blockIdx.x * kThreads + threadIdx.x; Q < p.nquads; Q += stride) {
+    const int64_t row = Q / p.qpr;
+    const int64_t q = Q - row * p.qpr;
+    const int64_t base = row * p.d + 4 * q;
+    const int64_t rem = p.d - 4 * q;
+    const int nvalid = rem < 4 ? (int)rem : 4;
+    T in[NIN > 0 ? NIN : 1][4];
+#pragma unroll
+    for (int i = 0; i < NIN; ++i) load_quad(reinterpret_cast<const T*>(p.in[i]), base, vec, nvalid, in[i]);
+    T w[4], u[4];
+    if (Op::USES_NOISE) {
+      quad_noise<T, SRC, Op::WANT_U>(nz, key, row, q, vec, nvalid, w, u);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { w[j] = T(0); u[j] = T(0); }
+    }
+    T out[NOUT][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      T a[NIN > 0 ? NIN : 1], b[NOUT];
+#pragma unroll
+      for (int i = 0; i < NIN; ++i) a[i] = in[i][j];
+      op(a, w[j], u[j], b);
+#pragma unroll
+      for (int i = 0; i < NOUT; ++i) out[i][j] = b[i];
+    }
+#pragma unroll
+    for (int i = 0; i < NOUT; ++i) store_quad(reinterpret_cast<T*>(p.out[i]), base, vec, nvalid, out[i]);
+  }
+}
+
+// ---- host-side launcher -----------------------------------------------------------------------
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+template <typename T>
+inline int fill_noise(const tsde_launch* L, const tsde_noise* nz, bool bcast, NoiseP<T>& out) {
+  out = NoiseP<T>{};
+  out.m = bcast ? 1 : L->m;
+  out.bcast = bcast ? 1 : 0;
+  if (!nz) return 0;
+  out.w = reinterpret_cast<const T*>(nz->w);
+  out.u = reinterpret_cast<const T*>(nz->u);
+  out.key = nz->key;
+  out.cell_id = nz->cell_id;
+  out.row_offset = nz->row_offset;
+  out.n_cells = nz->n_cells < 1 ? 1 : nz->n_cells;
+  out.h = nz->h;
+  out.cell_h = nz->cell_h;
+  out.h_total = nz->h_total;
+  if (nz->source == TSDE_SRC_MEMORY && !nz->w) return TSDE_EINVAL;
+  if (nz->source == TSDE_SRC_MEMORY && nz->want_u && !nz->u) return TSDE_EINVAL;
+  if (nz->source == TSDE_SRC_COUNTER && !nz->key) return TSDE_EINVAL;
+  return 0;
+}
+
+template <typename T, typename Op>
+inline int launch_ew(const tsde_launch* L, const tsde_noise* nz, bool bcast,
+                     const void* const* ins, void* const* outs, const Op& op) {
+  EwP<Op::NIN, Op::NOUT> p{};
+  bool vec = (L->d % 4) == 0;
+  for (int i = 0; i < Op::NIN; ++i) {
+    if (!ins[i]) return TSDE_EINVAL;
+    p.in[i] = ins[i];
+    vec = vec && aligned16(ins[i]);
+  }
+  for (int i = 0; i < Op::NOUT; ++i) {
+    if (!outs[i]) return TSDE_EINVAL;
+    p.out[i] = outs[i];
+    vec = vec && aligned16(outs[i]);
+  }
+  NoiseP<T> np;
+  if (int e = fill_noise<T>(L, Op::USES_NOISE ? nz : nullptr, bcast, np)) return e;
+  const int src = (Op::USES_NOISE && nz) ? nz->source : TSDE_SRC_UNIT;
+  if (Op::USES_NOISE && !nz) return TSDE_EINVAL;
+  if (src == TSDE_SRC_MEMORY && !bcast) {
+    vec = vec && aligned16(np.w) && (!Op::WANT_U || aligned16(np.u));
+    if (L->noise_type == TSDE_NOISE_DIAGONAL && L->m != L->d) return TSDE_EINVAL;
+  }
+  p.rows = L->rows;
+  p.d = L->d;
+  p.qpr = (L->d + 3) / 4;
+  p.nquads = p.rows * p.qpr;
+  p.vec = vec ? 1 : 0;
+  if (p.nquads == 0) return 0;
+  if (L->rows + (nz ? nz->row_offset : 0) > 0xFFFFFFFFll) return TSDE_EINVAL;
+  int64_t blocks = (p.nquads + kThreads - 1) / kThreads;
+  const int64_t cap = (int64_t)kSMs * kBlocksPerSM;
+  if (blocks > cap) blocks = cap;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(L->stream);
+  if constexpr (!Op::USES_NOISE) {
+    ew_kernel<T, Op, TSDE_SRC_UNIT><<<(unsigned)blocks, kThreads, 0, st>>>(p, np, op);
+  } else {
+    switch (src) {
+      case TSDE_SRC_MEMORY:
+        ew_kernel<T, Op, TSDE_SRC_MEMORY><<<(unsigned)blocks, kThreads, 0, st>>>(p, np, op);
+        break;
+      case TSDE_SRC_COUNTER:
+        ew_kernel<T, Op, TSDE_SRC_COUNTER><<<(unsigned)blocks, kThreads, 0, st>>>(p, np, op);
+        break;
+      case TSDE_SRC_UNIT:
+        ew_kernel<T, Op, TSDE_SRC_UNIT><<<(unsigned)blocks, kThreads, 0, st>>>(p, np, op);
+        break;
+      default:
+        return TSDE_EINVAL;
+    }
+  }
+  return (int)cudaGetLastError();
+}
+
+#define TSDE_DISPATCH_DTYPE(L, EXPR_F32, EXPR_F64) \
+  ((L)->dtype == TSDE_F32 ? (EXPR_F32) : (L)->dtype == TSDE_F64 ? (EXPR_F64) : TSDE_EINVAL)
+
+}  // namespace tsde

@@ -1,0 +1,582 @@
+// Step tableaus for general / additive noise: g:(rows,d,m), dW:(rows,m).
+//
+// The batched matrix-vector product of the reference (`misc.batch_mvp` = torch.bmm(g, v[...,None]),
+// torchsde/_core/misc.py:62-63, reached through base_sde.py:101-102) is fused with the tableau's
+// element-wise combination: g — the only large operand, used exactly once (0.5 flop/byte, HBM
+// bound; tensor cores cannot help) — is streamed with fully coalesced 128-bit
+// loads, lanes run along the contiguous (d,m) axis, the m/4 lanes that hold one (row,d) output
+// reduce their partial dot products with warp shuffles, and one of them applies the tableau.
+// The Brownian increments of the block's rows are produced once per block (Philox, or a load
+// of the user's tensor) into shared memory, so they are not regenerated d times.
+//
+// Summation order: within a 4-chunk left to right, chunks combined by a fixed xor-tree; results
+// are bitwise reproducible and independent of batch sharding, and agree with torch.bmm to
+// rounding (bmm's own order is unspecified), which is how the parity tests treat them.
+#include "ew.cuh"
+
+namespace tsde {
+
+constexpr int kMaxRowsPerBlock = 64;
+
+template <int NE, int NG, int NO>
+struct GenP {
+  const void* e[NE > 0 ? NE : 1];
+  const void* g[NG];
+  void* o[NO];
+  int64_t rows, d, m;
+  int32_t mq;    // m / 4 (vector path)
+  int32_t rb;    // rows per block
+  int32_t vec;   // vector path usable
+};
+
+// Op interface:
+//   static constexpr int NE, NG, NP, NO;  static constexpr bool WANT_U;
+//   T gval(int p, const T (&g)[NG]) const;      value contracted in product p
+//   T weight(int p, T w, T u) const;            weight of product p for this Brownian channel
+//   void combine(const T (&e)[NE], const T (&gp)[NP], T (&o)[NO]) const;
+template <typename T, typename Op, int SRC>
+__global__ void __launch_bounds__(kThreads)
+gen_kernel(const GenP<Op::NE, Op::NG, Op::NO> p, const NoiseP<T> nz, const Op op) {
+  constexpr int NE = Op::NE, NG = Op::NG, NP = Op::NP, NO = Op::NO;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* sw = reinterpret_cast<T*>(smem_raw);
+  T* su = sw + (size_t)p.rb * p.m;
+
+  const int64_t row0 = (int64_t)blockIdx.x * p.rb;
+  const int nrows = (int)((p.rows - row0) < p.rb ? (p.rows - row0) : p.rb);
+  const int64_t m = p.m, d = p.d;
+
+  // ---- phase 1: Brownian increments of this block's rows -> shared memory ------------------
+  {
+    Key key{0u, 0u};
+    if (SRC == TSDE_SRC_COUNTER) key = load_key(nz.key);
+    const int qpr = (int)((m + 3) / 4);
+    for (int i = threadIdx.x; i < nrows * qpr; i += kThreads) {
+      const int r = i / qpr, q = i - r * qpr;
+      const int64_t rem = m - 4 * q;
+      const int nvalid = rem < 4 ? (int)rem : 4;
+      T w[4], u[4];
+      if (SRC == TSDE_SRC_COUNTER) {
+        counter_noise<T, Op::WANT_U>(nz, key, (uint32_t)(row0 + r + nz.row_offset), (uint32_t)q, w, u);
+      } else {
+        const int64_t base = (row0 + r) * m + 4 * q;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          w[j] = j < nvalid ? nz.w[base + j] : T(0);
+          u[j] = (Op::WANT_U && j < nvalid) ? nz.u[base + j] : T(0);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < nvalid) {
+          sw[r * m + 4 * q + j] = w[j];
+          if (Op::WANT_U) su[r * m + 4 * q + j] = u[j];
+        }
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2: stream g, contract, combine ----------------------------------------------------
+  if (p.vec) {
+    const int mq = p.mq;
+    const int64_t per_row = d * mq;
+    const int64_t total = (int64_t)nrows * per_row;
+    const int64_t total_pad = (total + 31) & ~(int64_t)31;
+    for (int64_t c = threadIdx.x; c < total_pad; c += kThreads) {
+      const bool valid = c < total;
+      const int64_t cc = valid ? c : 0;
+      const int r = (int)(cc / per_row);
+      const int64_t rem = cc - (int64_t)r * per_row;
+      const int64_t dd = rem / mq;
+      const int mc = (int)(rem - dd * mq);
+      const int64_t goff = ((row0 + r) * d + dd) * m + 4 * mc;
+      T gv[NG][4];
+#pragma unroll
+      for (int i = 0; i < NG; ++i) {
+        if (valid) {
+          ld4(reinterpret_cast<const T*>(p.g[i]) + goff, gv[i]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) gv[i][j] = T(0);
+        }
+      }
+      T part[NP];
+#pragma unroll
+      for (int k = 0; k < NP; ++k) part[k] = T(0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const T w = sw[r * m + 4 * mc + j];
+        const T u = Op::WANT_U ? su[r * m + 4 * mc + j] : T(0);
+        T gj[NG];
+#pragma unroll
+        for (int i = 0; i < NG; ++i) gj[i] = gv[i][j];
+#pragma unroll
+        for (int k = 0; k < NP; ++k) part[k] = part[k] + op.gval(k, gj) * op.weight(k, w, u);
+      }
+      for (int off = 1; off < mq; off <<= 1) {
+#pragma unroll
+        for (int k = 0; k < NP; ++k) part[k] = part[k] + __shfl_xor_sync(0xffffffffu, part[k], off);
+      }
+      if (valid && mc == 0) {
+        const int64_t eoff = (row0 + r) * d + dd;
+        T e[NE > 0 ? NE : 1], o[NO];
+#pragma unroll
+        for (int i = 0; i < NE; ++i) e[i] = reinterpret_cast<const T*>(p.e[i])[eoff];
+        op.combine(e, part, o);
+#pragma unroll
+        for (int i = 0; i < NO; ++i) reinterpret_cast<T*>(p.o[i])[eoff] = o[i];
+      }
+    }
+  } else {
+    const int64_t total = (int64_t)nrows * d;
+    for (int64_t c = threadIdx.x; c < total; c += kThreads) {
+      const int r = (int)(c / d);
+      const int64_t dd = c - (int64_t)r * d;
+      const int64_t goff = ((row0 + r) * d + dd) * m;
+      T part[NP];
+#pragma unroll
+      for (int k = 0; k < NP; ++k) part[k] = T(0);
+      for (int64_t mm = 0; mm < m; ++mm) {
+        const T w = sw[r * m + mm];
+        const T u = Op::WANT_U ? su[r * m + mm] : T(0);
+        T gj[NG];
+#pragma unroll
+        for (int i = 0; i < NG; ++i) gj[i] = reinterpret_cast<const T*>(p.g[i])[goff + mm];
+#pragma unroll
+        for (int k = 0; k < NP; ++k) part[k] = part[k] + op.gval(k, gj) * op.weight(k, w, u);
+      }
+      const int64_t eoff = (row0 + r) * d + dd;
+      T e[NE > 0 ? NE : 1], o[NO];
+#pragma unroll
+      for (int i = 0; i < NE; ++i) e[i] = reinterpret_cast<const T*>(p.e[i])[eoff];
+      op.combine(e, part, o);
+#pragma unroll
+      for (int i = 0; i < NO; ++i) reinterpret_cast<T*>(p.o[i])[eoff] = o[i];
+    }
+  }
+}
+
+template <typename T, typename Op>
+static int launch_gen(const tsde_launch* L, const tsde_noise* nz,
+                      std::initializer_list<const void*> es, std::initializer_list<const void*> gs,
+                      std::initializer_list<void*> os, const Op& op) {
+  if (!nz) return TSDE_EINVAL;
+  if (nz->source == TSDE_SRC_UNIT) return TSDE_EINVAL;  // g_prod given -> diagonal entry points
+  GenP<Op::NE, Op::NG, Op::NO> p{};
+  bool vec = (L->m % 4) == 0;
+  int i = 0;
+  for (const void* q : es) { if (!q) return TSDE_EINVAL; p.e[i++] = q; }
+  i = 0;
+  for (const void* q : gs) { if (!q) return TSDE_EINVAL; p.g[i++] = q; vec = vec && aligned16(q); }
+  i = 0;
+  for (void* q : os) { if (!q) return TSDE_EINVAL; p.o[i++] = q; }
+  NoiseP<T> np;
+  if (int e = fill_noise<T>(L, nz, false, np)) return e;
+  const int64_t mq = L->m / 4;
+  vec = vec && mq >= 1 && mq <= 32 && (mq & (mq - 1)) == 0;
+  p.rows = L->rows; p.d = L->d; p.m = L->m;
+  p.mq = (int32_t)mq;
+  p.vec = vec ? 1 : 0;
+  if (L->rows == 0) return 0;
+  if (L->rows + nz->row_offset > 0xFFFFFFFFll) return TSDE_EINVAL;
+  // rows per block: ~16 work items per thread, bounded by shared memory for the increments
+  const int64_t per_row = vec ? L->d * mq : L->d;
+  int64_t rb = (16 * kThreads + per_row - 1) / per_row;
+  if (rb < 1) rb = 1;
+  if (rb > kMaxRowsPerBlock) rb = kMaxRowsPerBlock;
+  const int64_t smem_per_row = L->m * (int64_t)sizeof(T) * (Op::WANT_U ? 2 : 1);
+  while (rb > 1 && rb * smem_per_row > 40 * 1024) rb >>= 1;
+  if (rb * smem_per_row > 40 * 1024) return TSDE_EINVAL;  // m too large for one row in smem
+  // keep every SM busy on small batches
+  while (rb > 1 && (L->rows + rb - 1) / rb < 2 * kSMs) rb >>= 1;
+  p.rb = (int32_t)rb;
+  const int64_t blocks = (L->rows + rb - 1) / rb;
+  if (blocks > 0x7fffffffll) return TSDE_EINVAL;
+  const size_t smem = (size_t)(rb * smem_per_row);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(L->stream);
+  if (nz->source == TSDE_SRC_MEMORY) {
+    gen_kernel<T, Op, TSDE_SRC_MEMORY><<<(unsigned)blocks, kThreads, smem, st>>>(p, np, op);
+  } else {
+    gen_kernel<T, Op, TSDE_SRC_COUNTER><<<(unsigned)blocks, kThreads, smem, st>>>(p, np, op);
+  }
+  return (int)cudaGetLastError();
+}
+
+// ---- ops ---------------------------------------------------------------------------------------
+// y1 = y0 + f*dt + g.dW                                                         methods/euler.py:36
+template <typename T>
+struct GEulerOp {
+  static constexpr int NE = 2, NG = 1, NP = 1, NO = 1;
+  static constexpr bool WANT_U = false;
+  T dt;
+  __device__ __forceinline__ T gval(int, const T (&g)[1]) const { return g[0]; }
+  __device__ __forceinline__ T weight(int, T w, T) const { return w; }
+  __device__ __forceinline__ void combine(const T (&e)[2], const T (&gp)[1], T (&o)[1]) const {
+    o[0] = (e[0] + e[1] * dt) + gp[0];
+  }
+};
+// y1 = y0 + (dt*(f+f') + g.dW + g'.dW) * 0.5                                     methods/heun.py:46
+template <typename T>
+struct GHeunOp {
+  static constexpr int NE = 3, NG = 2, NP = 2, NO = 1;
+  static constexpr bool WANT_U = false;
+  T dt;
+  __device__ __forceinline__ T gval(int p, const T (&g)[2]) const { return g[p]; }
+  __device__ __forceinline__ T weight(int, T w, T) const { return w; }
+  __device__ __forceinline__ void combine(const T (&e)[3], const T (&gp)[2], T (&o)[1]) const {
+    o[0] = e[0] + ((dt * (e[1] + e[2]) + gp[0]) + gp[1]) * T(0.5);
+  }
+};
+// y' = y0 + half_dt*f + 0.5*(g.dW)                                               methods/midpoint.py:38
+template <typename T>
+struct GMidpointPredictOp {
+  static constexpr int NE = 2, NG = 1, NP = 1, NO = 1;
+  static constexpr bool WANT_U = false;
+  T half_dt;
+  __device__ __forceinline__ T gval(int, const T (&g)[1]) const { return g[0]; }
+  __device__ __forceinline__ T weight(int, T w, T) const { return w; }
+  __device__ __forceinline__ void combine(const T (&e)[2], const T (&gp)[1], T (&o)[1]) const {
+    o[0] = (e[0] + half_dt * e[1]) + T(0.5) * gp[0];
+  }
+};
+// y' = y0 + g.dW                                                                 methods/euler_heun.py:36
+template <typename T>
+struct GEulerHeunPredictOp {
+  static constexpr int NE = 1, NG = 1, NP = 1, NO = 1;
+  static constexpr bool WANT_U = false;
+  __device__ __forceinline__ T gval(int, const T (&g)[1]) const { return g[0]; }
+  __device__ __forceinline__ T weight(int, T w, T) const { return w; }
+  __device__ __forceinline__ void combine(const T (&e)[1], const T (&gp)[1], T (&o)[1]) const {
+    o[0] = e[0] + gp[0];
+  }
+};
+// y1 = y0 + dt*f + (g.dW + g'.dW)*0.5                                            methods/euler_heun.py:40
+template <typename T>
+struct GEulerHeunOp {
+  static constexpr int NE = 2, NG = 2, NP = 2, NO = 1;
+  static constexpr bool WANT_U = false;
+  T dt;
+  __device__ __forceinline__ T gval(int p, const T (&g)[2]) const { return g[p]; }
+  __device__ __forceinline__ T weight(int, T w, T) const { return w; }
+  __device__ __forceinline__ void combine(const T (&e)[2], const T (&gp)[2], T (&o)[1]) const {
+    o[0] = (e[0] + dt * e[1]) + (gp[0] + gp[1]) * T(0.5);
+  }
+};
+// z1 = 2*y0 - z0 + f0*dt + g0.dW                                                 reversible_heun.py:69
+// sign = -1 gives the adjoint's reconstruction z1 = 2*y0 - z0 - f0*dt - g0.dW    reversible_heun.py:109
+template <typename T>
+struct GRevHeunZOp {
+  static constexpr int NE = 3, NG = 1, NP = 1, NO = 1;
+  static constexpr bool WANT_U = false;
+  T dt;
+  int backward;
+  __device__ __forceinline__ T gval(int, const T (&g)[1]) const { return g[0]; }
+  __device__ __forceinline__ T weight(int, T w, T) const { return w; }
+  __device__ __forceinline__ void combine(const T (&e)[3], const T (&gp)[1], T (&o)[1]) const {
+    const T a = T(2) * e[0] - e[1];
+    o[0] = backward ? ((a - e[2] * dt) - gp[0]) : ((a + e[2] * dt) + gp[0]);
+  }
+};
+// y1 = y0 + (f0+f1)*half_dt + (g0+g1).(0.5*dW)                                   reversible_heun.py:71
+// backward: y1 = y0 - (f0+f1)*half_dt - (g0+g1).half_dW                          reversible_heun.py:134-135
+template <typename T>
+struct GRevHeunOp {
+  static constexpr int NE = 3, NG = 2, NP = 1, NO = 1;
+  static constexpr bool WANT_U = false;
+  T half_dt;
+  int backward;
+  __device__ __forceinline__ T gval(int, const T (&g)[2]) const { return g[0] + g[1]; }
+  __device__ __forceinline__ T weight(int, T w, T) const { return T(0.5) * w; }
+  __device__ __forceinline__ void combine(const T (&e)[3], const T (&gp)[1], T (&o)[1]) const {
+    const T fd = (e[1] + e[2]) * half_dt;
+    o[0] = backward ? ((e[0] - fd) - gp[0]) : ((e[0] + fd) + gp[0]);
+  }
+};
+// SRA1 stage: H0_1 = y0 + (3/4 f0) dt + gA.((3/2 U) rdt)             methods/srk.py:100-105, sra1.py:24-36
+template <typename T>
+struct GSraStageOp {
+  static constexpr int NE = 2, NG = 1, NP = 1, NO = 1;
+  static constexpr bool WANT_U = true;
+  T dt, rdt;
+  __device__ __forceinline__ T gval(int, const T (&g)[1]) const { return g[0]; }
+  __device__ __forceinline__ T weight(int, T, T u) const { return (T(1.5) * u) * rdt; }
+  __device__ __forceinline__ void combine(const T (&e)[2], const T (&gp)[1], T (&o)[1]) const {
+    o[0] = (e[0] + (T(0.75) * e[1]) * dt) + gp[0];
+  }
+};
+// SRA1 final: y1 = y0 + (1/3 f0) dt + gA.(W + (-U) rdt) + (2/3 f1) dt + gB.(0*W + U rdt)   srk.py:107-110
+template <typename T>
+struct GSraFinalOp {
+  static constexpr int NE = 3, NG = 2, NP = 2, NO = 1;
+  static constexpr bool WANT_U = true;
+  T dt, rdt, third, two_thirds;
+  __device__ __forceinline__ T gval(int p, const T (&g)[2]) const { return g[p]; }
+  __device__ __forceinline__ T weight(int p, T w, T u) const {
+    return p == 0 ? (T(1) * w + (T(-1) * u) * rdt) : (T(0) * w + (T(1) * u) * rdt);
+  }
+  __device__ __forceinline__ void combine(const T (&e)[3], const T (&gp)[2], T (&o)[1]) const {
+    T y1 = (e[0] + (third * e[1]) * dt) + gp[0];
+    y1 = (y1 + (two_thirds * e[2]) * dt) + gp[1];
+    o[0] = y1;
+  }
+};
+
+// ---- outer-product bookkeeping of the reversible-Heun adjoint (g-shaped element-wise) ----------
+// out[b,dd,mm] = (base ? base[b,dd,mm] : 0) + a1[b,dd]*(c1*w[b,mm]) (+ a2[b,dd]*(c2*w[b,mm]))
+// reversible_heun.py:95-96,105,115 (a) and :114,140 (b)
+template <typename T, int SRC>
+__global__ void __launch_bounds__(kThreads)
+outer_kernel(const NoiseP<T> nz, int64_t rows, int64_t d, int64_t m, const T* base, const T* a1,
+             T c1, const T* a2, T c2, T* out) {
+  Key key{0u, 0u};
+  if (SRC == TSDE_SRC_COUNTER) key = load_key(nz.key);
+  const int64_t qpr = (m + 3) / 4;
+  const int64_t total = rows * d * qpr;
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x; c < total; c += stride) {
+    const int64_t bd = c / qpr;
+    const int64_t q = c - bd * qpr;
+    const int64_t row = bd / d;
+    const int64_t rem = m - 4 * q;
+    const int nvalid = rem < 4 ? (int)rem : 4;
+    T w[4], u[4];
+    if (SRC == TSDE_SRC_COUNTER) {
+      // d-fold redundant Philox work; this g-shaped pass is off the headline path.
+      counter_noise<T, false>(nz, key, (uint32_t)(row + nz.row_offset), (uint32_t)q, w, u);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) w[j] = j < nvalid ? nz.w[row * m + 4 * q + j] : T(0);
+    }
+    const T x1 = a1[bd];
+    const T x2 = a2 ? a2[bd] : T(0);
+    const int64_t off = bd * m + 4 * q;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (j < nvalid) {
+        T v = x1 * (c1 * w[j]);
+        if (base) v = base[off + j] + v;
+        if (a2) v = v + x2 * (c2 * w[j]);
+        out[off + j] = v;
+      }
+    }
+  }
+}
+
+template <typename T>
+static int launch_outer(const tsde_launch* L, const tsde_noise* nz, const void* base,
+                        const void* a1, double c1, const void* a2, double c2, void* out) {
+  if (!nz || !a1 || !out) return TSDE_EINVAL;
+  NoiseP<T> np;
+  if (int e = fill_noise<T>(L, nz, false, np)) return e;
+  const int64_t total = L->rows * L->d * ((L->m + 3) / 4);
+  if (total == 0) return 0;
+  int64_t blocks = (total + kThreads - 1) / kThreads;
+  const int64_t cap = (int64_t)kSMs * kBlocksPerSM;
+  if (blocks > cap) blocks = cap;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(L->stream);
+  if (nz->source == TSDE_SRC_MEMORY) {
+    outer_kernel<T, TSDE_SRC_MEMORY><<<(unsigned)blocks, kThreads, 0, st>>>(
+        np, L->rows, L->d, L->m, (const T*)base, (const T*)a1, (T)c1, (const T*)a2, (T)c2, (T*)out);
+  } else if (nz->source == TSDE_SRC_COUNTER) {
+    outer_kernel<T, TSDE_SRC_COUNTER><<<(unsigned)blocks, kThreads, 0, st>>>(
+        np, L->rows, L->d, L->m, (const T*)base, (const T*)a1, (T)c1, (const T*)a2, (T)c2, (T*)out);
+  } else {
+    return TSDE_EINVAL;
+  }
+  return (int)cudaGetLastError();
+}
+
+// element-wise (rows,d) parts of the adjoint
+template <typename T>
+struct AdjAElemOp {  // adj_f0' = adj_f0 + adj_y0*half_dt
+  static constexpr int NIN = 2, NOUT = 1;
+  static constexpr bool USES_NOISE = false, WANT_U = false;
+  T half_dt;
+  __device__ __forceinline__ void operator()(const T (&in)[2], T, T, T (&out)[1]) const {
+    out[0] = in[1] + in[0] * half_dt;
+  }
+};
+template <typename T>
+struct AdjBElemOp {  // in: adj_y0, adj_z0, vjp_z -> adj_y1, adj_z1, adj_f1
+  static constexpr int NIN = 3, NOUT = 3;
+  static constexpr bool USES_NOISE = false, WANT_U = false;
+  T dt, half_dt;
+  __device__ __forceinline__ void operator()(const T (&in)[3], T, T, T (&out)[3]) const {
+    const T adj_y0 = in[0];
+    const T adj_z0 = in[1] + in[2];                  // :130
+    out[0] = adj_y0 + T(2) * adj_z0;                 // :137
+    out[1] = -adj_z0;                                // :138
+    out[2] = adj_y0 * half_dt + adj_z0 * dt;         // :112,139
+  }
+};
+
+}  // namespace tsde
+
+using namespace tsde;
+
+extern "C" {
+
+int tsde_general_step_euler(const tsde_launch* L, const tsde_noise* nz, const void* y0,
+                            const void* f, const void* g, double dt, void* y1) {
+  return TSDE_DISPATCH_DTYPE(
+      L, (launch_gen<float, GEulerOp<float>>(L, nz, {y0, f}, {g}, {y1}, GEulerOp<float>{(float)dt})),
+      (launch_gen<double, GEulerOp<double>>(L, nz, {y0, f}, {g}, {y1}, GEulerOp<double>{dt})));
+}
+
+int tsde_general_step_heun(const tsde_launch* L, const tsde_noise* nz, const void* y0,
+                           const void* f, const void* fp, const void* g, const void* gp, double dt,
+                           void* y1) {
+  return TSDE_DISPATCH_DTYPE(
+      L,
+      (launch_gen<float, GHeunOp<float>>(L, nz, {y0, f, fp}, {g, gp}, {y1}, GHeunOp<float>{(float)dt})),
+      (launch_gen<double, GHeunOp<double>>(L, nz, {y0, f, fp}, {g, gp}, {y1}, GHeunOp<double>{dt})));
+}
+
+int tsde_general_midpoint_predict(const tsde_launch* L, const tsde_noise* nz, const void* y0,
+                                  const void* f, const void* g, double half_dt, void* yp) {
+  return TSDE_DISPATCH_DTYPE(
+      L,
+      (launch_gen<float, GMidpointPredictOp<float>>(L, nz, {y0, f}, {g}, {yp},
+                                                    GMidpointPredictOp<float>{(float)half_dt})),
+      (launch_gen<double, GMidpointPredictOp<double>>(L, nz, {y0, f}, {g}, {yp},
+                                                      GMidpointPredictOp<double>{half_dt})));
+}
+
+int tsde_general_euler_heun_predict(const tsde_launch* L, const tsde_noise* nz, const void* y0,
+                                    const void* g, void* yp) {
+  return TSDE_DISPATCH_DTYPE(
+      L,
+      (launch_gen<float, GEulerHeunPredictOp<float>>(L, nz, {y0}, {g}, {yp},
+                                                     GEulerHeunPredictOp<float>{})),
+      (launch_gen<double, GEulerHeunPredictOp<double>>(L, nz, {y0}, {g}, {yp},
+                                                       GEulerHeunPredictOp<double>{})));
+}
+
+int tsde_general_step_euler_heun(const tsde_launch* L, const tsde_noise* nz, const void* y0,
+                                 const void* f, const void* g, const void* gp, double dt,
+                                 void* y1) {
+  return TSDE_DISPATCH_DTYPE(
+      L,
+      (launch_gen<float, GEulerHeunOp<float>>(L, nz, {y0, f}, {g, gp}, {y1},
+                                              GEulerHeunOp<float>{(float)dt})),
+      (launch_gen<double, GEulerHeunOp<double>>(L, nz, {y0, f}, {g, gp}, {y1},
+                                                GEulerHeunOp<double>{dt})));
+}
+
+int tsde_general_reversible_heun_z(const tsde_launch* L, const tsde_noise* nz, const void* y0,
+                                   const void* z0, const void* f0, const void* g0, double dt,
+                                   void* z1) {
+  return TSDE_DISPATCH_DTYPE(
+      L,
+      (launch_gen<float, GRevHeunZOp<float>>(L, nz, {y0, z0, f0}, {g0}, {z1},
+                                             GRevHeunZOp<float>{(float)dt, 0})),
+      (launch_gen<double, GRevHeunZOp<double>>(L, nz, {y0, z0, f0}, {g0}, {z1},
+                                               GRevHeunZOp<double>{dt, 0})));
+}
+
+int tsde_general_step_reversible_heun(const tsde_launch* L, const tsde_noise* nz, const void* y0,
+                                      const void* f0, const void* f1, const void* g0,
+                                      const void* g1, double half_dt, void* y1) {
+  return TSDE_DISPATCH_DTYPE(
+      L,
+      (launch_gen<float, GRevHeunOp<float>>(L, nz, {y0, f0, f1}, {g0, g1}, {y1},
+                                            GRevHeunOp<float>{(float)half_dt, 0})),
+      (launch_gen<double, GRevHeunOp<double>>(L, nz, {y0, f0, f1}, {g0, g1}, {y1},
+                                              GRevHeunOp<double>{half_dt, 0})));
+}
+
+int tsde_srk_additive_stage(const tsde_launch* L, const tsde_noise* nz, const void* y0,
+                            const void* f0, const void* ga, double dt, double rdt, void* h0_1) {
+  if (!L || L->noise_type != TSDE_NOISE_GENERAL) return TSDE_EINVAL;
+  return TSDE_DISPATCH_DTYPE(
+      L,
+      (launch_gen<float, GSraStageOp<float>>(L, nz, {y0, f0}, {ga}, {h0_1},
+                                             GSraStageOp<float>{(float)dt, (float)rdt})),
+      (launch_gen<double, GSraStageOp<double>>(L, nz, {y0, f0}, {ga}, {h0_1},
+                                               GSraStageOp<double>{dt, rdt})));
+}
+
+int tsde_step_srk_additive(const tsde_launch* L, const tsde_noise* nz, const void* y0,
+                           const void* f0, const void* f1, const void* ga, const void* gb,
+                           double dt, double rdt, void* y1) {
+  if (!L || L->noise_type != TSDE_NOISE_GENERAL) return TSDE_EINVAL;
+  return TSDE_DISPATCH_DTYPE(
+      L,
+      (launch_gen<float, GSraFinalOp<float>>(
+          L, nz, {y0, f0, f1}, {ga, gb}, {y1},
+          GSraFinalOp<float>{(float)dt, (float)rdt, (float)(1.0 / 3), (float)(2.0 / 3)})),
+      (launch_gen<double, GSraFinalOp<double>>(
+          L, nz, {y0, f0, f1}, {ga, gb}, {y1},
+          GSraFinalOp<double>{dt, rdt, 1.0 / 3, 2.0 / 3})));
+}
+
+int tsde_general_adjoint_reversible_heun_a(const tsde_launch* L, const tsde_noise* nz,
+                                           const void* y0, const void* z0, const void* f0,
+                                           const void* g0, const void* adj_y0, const void* adj_f0,
+                                           const void* adj_g0, double dt, double half_dt, void* z1,
+                                           void* adj_f0_out, void* adj_g0_out) {
+  // z1 = 2*y0 - z0 - f0*dt - g0.dW                                              :109
+  int e = TSDE_DISPATCH_DTYPE(
+      L,
+      (launch_gen<float, GRevHeunZOp<float>>(L, nz, {y0, z0, f0}, {g0}, {z1},
+                                             GRevHeunZOp<float>{(float)dt, 1})),
+      (launch_gen<double, GRevHeunZOp<double>>(L, nz, {y0, z0, f0}, {g0}, {z1},
+                                               GRevHeunZOp<double>{dt, 1})));
+  if (e) return e;
+  // adj_f0' = adj_f0 + adj_y0*half_dt                                            :104,113
+  {
+    const void* ins[2] = {adj_y0, adj_f0};
+    void* outs[1] = {adj_f0_out};
+    tsde_launch r = *L;
+    r.noise_type = TSDE_NOISE_DIAGONAL;
+    r.m = r.d;
+    e = TSDE_DISPATCH_DTYPE(
+        L,
+        (launch_ew<float, AdjAElemOp<float>>(&r, nullptr, false, ins, outs,
+                                             AdjAElemOp<float>{(float)half_dt})),
+        (launch_ew<double, AdjAElemOp<double>>(&r, nullptr, false, ins, outs,
+                                               AdjAElemOp<double>{half_dt})));
+    if (e) return e;
+  }
+  // adj_g0' = adj_g0 + adj_y0 (x) half_dW                                        :105,115
+  return TSDE_DISPATCH_DTYPE(
+      L, (launch_outer<float>(L, nz, adj_g0, adj_y0, 0.5, nullptr, 0.0, adj_g0_out)),
+      (launch_outer<double>(L, nz, adj_g0, adj_y0, 0.5, nullptr, 0.0, adj_g0_out)));
+}
+
+int tsde_general_adjoint_reversible_heun_b(const tsde_launch* L, const tsde_noise* nz,
+                                           const void* y0, const void* f0, const void* f1,
+                                           const void* g0, const void* g1, const void* adj_y0,
+                                           const void* adj_z0, const void* vjp_z, double dt,
+                                           double half_dt, void* y1, void* adj_y1, void* adj_z1,
+                                           void* adj_f1, void* adj_g1) {
+  // y1 = y0 - (f0+f1)*half_dt - (g0+g1).half_dW                                   :134-135
+  int e = TSDE_DISPATCH_DTYPE(
+      L,
+      (launch_gen<float, GRevHeunOp<float>>(L, nz, {y0, f0, f1}, {g0, g1}, {y1},
+                                            GRevHeunOp<float>{(float)half_dt, 1})),
+      (launch_gen<double, GRevHeunOp<double>>(L, nz, {y0, f0, f1}, {g0, g1}, {y1},
+                                              GRevHeunOp<double>{half_dt, 1})));
+  if (e) return e;
+  // element-wise part: adj_y1, adj_z1 = -(adj_z0 + vjp_z), adj_f1
+  {
+    const void* ins[3] = {adj_y0, adj_z0, vjp_z};
+    void* outs[3] = {adj_y1, adj_z1, adj_f1};
+    tsde_launch r = *L;
+    r.noise_type = TSDE_NOISE_DIAGONAL;
+    r.m = r.d;
+    e = TSDE_DISPATCH_DTYPE(
+        L,
+        (launch_ew<float, AdjBElemOp<float>>(&r, nullptr, false, ins, outs,
+                                             AdjBElemOp<float>{(float)dt, (float)half_dt})),
+        (launch_ew<double, AdjBElemOp<double>>(&r, nullptr, false, ins, outs,
+                                               AdjBElemOp<double>{dt, half_dt})));
+    if (e) return e;
+  }
+  // adj_g1 = adj_y0 (x) half_dW + adj_z0' (x) dW = adj_y0 (x) (0.5 dW) + adj_z1 (x) (-1 dW)   :114,140
+  return TSDE_DISPATCH_DTYPE(
+      L, (launch_outer<float>(L, nz, nullptr, adj_y0, 0.5, adj_z1, -1.0, adj_g1)),
+      (launch_outer<double>(L, nz, nullptr, adj_y0, 0.5, adj_z1, -1.0, adj_g1)));
+}
+
+}  // extern "C"
