@@ -1,0 +1,90 @@
+"""sdeint_adjoint (reversible_heun / adjoint_reversible_heun) on the GPU."""
+import numpy as np
+import pytest
+import torch
+
+from . import helpers, problems
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def _tsde():
+    import torchsde_b200
+    return torchsde_b200
+
+
+@pytest.mark.parametrize('path', helpers.golden_files('adjoint_'), ids=helpers.case_id)
+def test_adjoint_golden_replay(path):
+    """Gradients of the reference's sdeint_adjoint on identical increments."""
+    tsde = _tsde()
+    case = helpers.load(path)
+    sde = problems.make(str(case['kind']), int(case['d']), int(case['m']), 'stratonovich', dtype=torch.float64,
+                        seed=3).to(DEV)
+    y0 = torch.from_numpy(case['y0']).to(DEV).requires_grad_(True)
+    ts = torch.from_numpy(case['ts']).to(DEV)
+    Ws = [torch.from_numpy(w).to(DEV) for w in case['W']]
+    bm = problems.ReplayBM(case['ta'], case['tb'], Ws)
+    ys = tsde.sdeint_adjoint(sde, y0, ts, bm=bm, method='reversible_heun',
+                             adjoint_method='adjoint_reversible_heun', dt=float(case['dt']))
+    np.testing.assert_allclose(ys.detach().cpu().numpy(), case['ys'], rtol=1e-12, atol=1e-13)
+    (ys * torch.from_numpy(case['weights']).to(DEV)).sum().backward()
+    np.testing.assert_allclose(y0.grad.cpu().numpy(), case['grad_y0'], rtol=1e-9, atol=1e-11)
+    for n, p in sde.named_parameters():
+        np.testing.assert_allclose(p.grad.cpu().numpy(), case['grad.' + n], rtol=1e-8, atol=1e-10)
+
+
+@pytest.mark.parametrize('kind,d,m', [('gbm', 16, 16), ('general', 4, 8)])
+def test_adjoint_counter_path_matches_replay(kind, d, m):
+    """Backward regenerates the forward's Brownian cells from the counter, in reverse: gradients
+    equal those obtained when the same increments are served from memory."""
+    tsde = _tsde()
+    B = 24
+    sde = problems.make(kind, d, m, 'stratonovich', dtype=torch.float64, seed=6).to(DEV)
+    bm_m = d if kind == 'gbm' else m
+    ts = torch.tensor([0.0, 0.25, 0.5], dtype=torch.float64, device=DEV)
+    dt = 2.0 ** -4
+    y_a = torch.full((B, d), 0.4, dtype=torch.float64, device=DEV).requires_grad_(True)
+    bm = tsde.BrownianInterval(0.0, 0.5, size=(B, bm_m), dtype=torch.float64, device=DEV, entropy=17)
+    ys = tsde.sdeint_adjoint(sde, y_a, ts, bm=bm, method='reversible_heun', dt=dt)
+    ys.pow(2).sum().backward()
+    g_fast = [y_a.grad.clone()] + [p.grad.clone() for p in sde.parameters()]
+    for p in sde.parameters():
+        p.grad = None
+
+    class Mat:
+        shape = bm.shape
+        levy_area_approximation = 'none'
+
+        def __call__(self, ta, tb=None, return_U=False, return_A=False):
+            return bm(ta, tb)
+
+    y_b = torch.full((B, d), 0.4, dtype=torch.float64, device=DEV).requires_grad_(True)
+    ys2 = tsde.sdeint_adjoint(sde, y_b, ts, bm=Mat(), method='reversible_heun', dt=dt)
+    assert torch.equal(ys, ys2)
+    ys2.pow(2).sum().backward()
+    g_slow = [y_b.grad] + [p.grad for p in sde.parameters()]
+    for a, b in zip(g_fast, g_slow):
+        torch.testing.assert_close(a, b, rtol=1e-12, atol=1e-13)
+
+
+def test_reversibility():
+    """Reference tests/test_sdeint.py:219-252: forward with reversible Heun, then the forward solver
+    again on the reversed Brownian motion with negated extras reconstructs ys."""
+    tsde = _tsde()
+    B, d = 8, 6
+    sde = problems.GBMDiagonal(d, 'stratonovich', seed=2, dtype=torch.float64).to(DEV)
+    y0 = torch.full((B, d), 0.3, dtype=torch.float64, device=DEV)
+    ts = torch.linspace(0.0, 1.0, 5, dtype=torch.float64, device=DEV)
+    bm = tsde.BrownianInterval(0.0, 1.0, size=(B, d), dtype=torch.float64, device=DEV, entropy=5)
+    ys, (f, g, z) = tsde.sdeint(sde, y0, ts, bm=bm, method='reversible_heun', dt=0.125, extra=True)
+
+    class Neg(torch.nn.Module):
+        noise_type, sde_type = 'diagonal', 'stratonovich'
+
+        def f_and_g(self, t, y):
+            return -sde.f(-t, y), -sde.g(-t, y)
+
+    back, _ = tsde.sdeint(Neg(), ys[-1], -ts.flip(0), bm=tsde.ReverseBrownian(bm), method='reversible_heun',
+                          dt=0.125, extra=True, extra_solver_state=(-f, -g, z))
+    torch.testing.assert_close(back.flip(0), ys, rtol=1e-6, atol=1e-6)

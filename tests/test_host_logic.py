@@ -1,0 +1,238 @@
+"""CPU-only tests: host logic of the package (no kernel is launched) and the C-ABI surface."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import torchsde_b200 as tsde
+from torchsde_b200 import _cabi
+from torchsde_b200._brownian import interval as bi
+from torchsde_b200._core import schedule
+from . import problems
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---- C ABI ---------------------------------------------------------------------------------
+def _declared_symbols():
+    text = open(os.path.join(ROOT, 'include', 'torchsde_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(tsde_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_cabi_loads_and_exports_every_declared_symbol():
+    if not os.path.exists(_cabi.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    lib = ctypes.CDLL(_cabi.LIB_PATH)
+    names = _declared_symbols()
+    assert len(names) >= 28
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/torchsde_b200.h but not exported"
+    # the ctypes binding covers every declared compute entry point, with matching arity
+    assert set(_cabi.SIGNATURES) == set(names) - {'tsde_abi_version', 'tsde_error_string'}
+    assert _cabi.lib().tsde_abi_version() == 1
+
+
+def test_struct_layout_matches_header():
+    assert ctypes.sizeof(_cabi.Launch) == 40
+    assert ctypes.sizeof(_cabi.Noise) == 80
+    assert _cabi.Noise.cell_id.offset == 32 and _cabi.Noise.h.offset == 56
+
+
+def test_no_cpu_fallback():
+    sde = problems.GBMDiagonal(4, 'ito', dtype=torch.float32)
+    y0 = torch.ones(3, 4)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        tsde.sdeint(sde, y0, [0.0, 0.1], dt=0.05, method='euler',
+                    bm=problems.ReplayBM([0.0], [0.05], [torch.zeros(3, 4)]))
+    with pytest.raises(RuntimeError, match='CUDA'):
+        tsde.BrownianInterval(0.0, 1.0, size=(2, 2))(0.0, 0.5)
+
+
+def test_product_does_not_import_oracle():
+    import subprocess, sys
+    code = "import sys, torchsde_b200; assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules)"
+    subprocess.run([sys.executable, '-c', code], check=True, cwd=ROOT)
+    for dirpath, _, files in os.walk(os.path.join(ROOT, 'torchsde_b200')):
+        for f in files:
+            if f.endswith('.py'):
+                assert 'oracle' not in open(os.path.join(dirpath, f)).read().replace('oracle/', '')
+
+
+# ---- schedule (base_solver.py:107-147) ----------------------------------------------------------
+def _reference_grid(ts, dt):
+    """The reference's loop on 0-d tensors, verbatim control flow."""
+    curr_t = ts[0]
+    steps, outs = [], []
+    prev_t = curr_t
+    for out_t in ts[1:]:
+        while curr_t < out_t:
+            next_t = min(curr_t + dt, ts[-1])
+            prev_t = curr_t
+            steps.append((float(curr_t), float(next_t)))
+            curr_t = next_t
+        outs.append((len(steps) - 1, float(prev_t), float(curr_t), float(out_t)))
+    return steps, outs
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float64])
+@pytest.mark.parametrize('ts,dt', [([0.0, 1.0], 1e-3), ([0.0, 0.075, 0.15, 0.225, 0.3], 0.05),
+                                   ([0.0, 0.25, 1.0], 2.0 ** -4), ([0.0, 0.01, 0.02], 0.05), ([1.0, 2.5], 0.7)])
+def test_schedule_matches_reference_loop(dtype, ts, dt):
+    t = torch.tensor(ts, dtype=dtype)
+    s = schedule.build_schedule(t, dt)
+    steps, outs = _reference_grid(t, dt)
+    assert [(float(a), float(b)) for a, b in s.steps] == steps
+    assert s.bounds == [steps[0][0]] + [b for _, b in steps]
+    for o, (k, prev_t, curr_t, out_t) in zip(s.outputs, outs):
+        assert o.step == k and o.aligned == (curr_t == out_t)
+    if dtype == torch.float32 and ts == [0.0, 1.0]:
+        assert s.n_steps == 1001  # fp32 accumulation leaves a sliver step
+
+
+def test_schedule_rejects_stalled_time():
+    with pytest.raises(ValueError):
+        schedule.build_schedule(torch.tensor([1e8, 1e8 + 16], dtype=torch.float32), 1e-3)
+
+
+# ---- contract errors (sdeint.py:115-281, base_solver.py:49-58, test_sdeint.py:124-136) ---------
+def _bm(levy, m=3):
+    return tsde.BrownianInterval(0.0, 0.3, size=(4, m), dtype=torch.float64, device='cuda',
+                                 levy_area_approximation=levy)
+
+
+@pytest.mark.parametrize('sde_type', ['ito', 'stratonovich'])
+@pytest.mark.parametrize('method', ['blah', 'euler', 'milstein', 'srk', 'euler_heun', 'heun', 'midpoint', 'log_ode',
+                                    'reversible_heun'])
+@pytest.mark.parametrize('kind', ['gbm', 'scalar', 'additive', 'general'])
+@pytest.mark.parametrize('levy', [None, 'none', 'space-time', 'davie', 'foster'])
+def test_error_matrix(sde_type, method, kind, levy):
+    """Which (sde_type, noise_type, method, levy) combinations must raise ValueError; evaluated on
+    CPU tensors: a legal combination gets past all checks and then stops at the CUDA requirement."""
+    d, m = 3, {'gbm': 3, 'scalar': 1}.get(kind, 2)
+    sde = problems.make(kind, d, m, sde_type, dtype=torch.float64)
+    should_fail = False
+    if sde_type == 'ito':
+        should_fail |= method not in ('euler', 'srk', 'milstein')
+    else:
+        should_fail |= method not in ('euler_heun', 'heun', 'midpoint', 'log_ode', 'milstein', 'reversible_heun')
+    if method in ('milstein', 'srk') and kind == 'general':
+        should_fail = True
+    if method == 'srk' and levy == 'none':
+        should_fail = True
+    if method == 'log_ode' and levy in ('none', 'space-time'):
+        should_fail = True
+    y0 = torch.ones(4, d, dtype=torch.float64)
+    bm = None if levy is None else _bm(levy, m)
+    if should_fail:
+        with pytest.raises(ValueError):
+            tsde.sdeint(sde, y0, [0.0, 0.3], bm=bm, method=method, dt=0.05)
+    else:
+        with pytest.raises((RuntimeError, NotImplementedError), match='CUDA|not implemented'):
+            tsde.sdeint(sde, y0, [0.0, 0.3], bm=bm, method=method, dt=0.05)
+
+
+def test_contract_messages():
+    sde = problems.GBMDiagonal(3, 'ito')
+    y0 = torch.ones(4, 3, dtype=torch.float64)
+    with pytest.raises(ValueError, match='2-dimensional'):
+        tsde.sdeint(sde, y0[0], [0.0, 1.0])
+    with pytest.raises(ValueError, match='strictly increasing'):
+        tsde.sdeint(sde, y0, [0.0, 0.0])
+    with pytest.raises(ValueError, match='torch.Tensor'):
+        tsde.sdeint(sde, [1.0], [0.0, 1.0])
+    with pytest.raises(ValueError, match='Batch sizes'):
+        tsde.sdeint(sde, y0, [0.0, 1.0], bm=tsde.BrownianInterval(0., 1., size=(5, 3), device='cuda'))
+    with pytest.raises(ValueError, match='must not require gradient'):
+        tsde.sdeint(sde, y0, torch.tensor([0.0, 1.0], dtype=torch.float64, requires_grad=True))
+    with pytest.warns(UserWarning, match='Unexpected arguments'):
+        with pytest.raises(RuntimeError):
+            tsde.sdeint(sde, y0, [0.0, 1.0], method='euler', bogus=1)
+
+    class NoNoise(torch.nn.Module):
+        sde_type = 'ito'
+    with pytest.raises(ValueError, match='noise_type'):
+        tsde.sdeint(NoNoise(), y0, [0.0, 1.0])
+    with pytest.raises(ValueError, match='adjoint parameters'):
+        tsde.sdeint_adjoint(object(), y0, [0.0, 1.0])
+    with pytest.raises(ValueError, match='only be used for adjoint_method'):
+        tsde.sdeint(problems.GBMDiagonal(3, 'stratonovich'), y0, [0.0, 1.0], method='adjoint_reversible_heun')
+
+
+# ---- interval tree (pure host logic) ----------------------------------------------------------
+def _pieces(bm, ta, tb):
+    out = []
+    for p in bm._locate(ta, tb):
+        if isinstance(p, bi._Node):
+            out.append((p.start, p.end))
+        else:
+            g, i, j = p
+            out.append((g.bounds[i], g.bounds[j], j - i))
+    return out
+
+
+def test_locate_binary_tree_like_reference():
+    bm = tsde.BrownianInterval(0.0, 1.0, size=(2, 2), device='cuda')
+    assert _pieces(bm, 0.0, 1.0) == [(0.0, 1.0)]
+    assert _pieces(bm, 0.3, 0.6) == [(0.3, 0.6)]
+    # root split at 0.3, right child split at 0.6
+    assert bm._root.mid == 0.3 and bm._root.right.mid == 0.6
+    assert _pieces(bm, 0.1, 0.8) == [(0.1, 0.3), (0.3, 0.6), (0.6, 0.8)]
+    assert _pieces(bm, 0.0, 0.3) == [(0.0, 0.3)]      # an existing node answers as a whole
+    assert _pieces(bm, 0.0, 0.2) == [(0.0, 0.1), (0.1, 0.2)]
+    ids = set()
+    stack = [bm._root]
+    while stack:
+        n = stack.pop()
+        ids.add(n.id)
+        if n.kind == bi._BINARY:
+            stack += [n.left, n.right]
+    assert len(ids) == 11  # all node ids distinct
+
+
+def test_locate_grid_cells():
+    bm = tsde.BrownianInterval(0.0, 1.0, size=(2, 2), device='cuda', dt=0.125)
+    bm._bind_uniform(0.125)
+    assert bm._root.kind == bi._GRID and len(bm._root.bounds) == 9
+    assert _pieces(bm, 0.25, 0.75) == [(0.25, 0.75, 4)]
+    assert _pieces(bm, 0.0, 1.0) == [(0.0, 1.0)]
+    assert _pieces(bm, 0.125, 0.25) == [(0.125, 0.25, 1)]
+    assert _pieces(bm, 0.3, 0.6) == [(0.3, 0.375), (0.375, 0.5, 1), (0.5, 0.6)]
+    assert _pieces(bm, 0.26, 0.3) == [(0.26, 0.3)]
+    assert _pieces(bm, 0.25, 0.3) == [(0.25, 0.3)]
+    assert _pieces(bm, 0.25, 0.28) == [(0.25, 0.26), (0.26, 0.28)]
+    assert _pieces(bm, 0.3, 0.5) == [(0.3, 0.375), (0.375, 0.5, 1)]
+
+
+def test_bind_grid_rules():
+    mk = lambda **kw: tsde.BrownianInterval(0.0, 1.0, size=(2, 2), device='cuda', **kw)  # noqa
+    bounds = [0.0, 0.25, 0.5, 1.0]
+    b = mk().bind_grid(bounds)
+    assert b is not None and b.first == [0, 1, 2] and b.count == [1, 1, 1]
+    bm = mk()
+    assert bm.bind_grid([k / 8 for k in range(9)]) is not None
+    nested = bm.bind_grid([0.0, 0.5, 0.625, 1.0])           # coarser, nested: runs of cells
+    assert nested.first == [0, 4, 5] and nested.count == [4, 1, 3]
+    assert bm.bind_grid([0.0, 0.3, 1.0]) is None            # not nested -> ordinary queries
+    sub = bm.bind_grid([0.25, 0.5])                          # sub-range of an existing grid
+    assert sub.first == [2] and sub.count == [2]
+    assert mk(halfway_tree=True, tol=1e-6).bind_grid(bounds) is None
+    assert tsde.BrownianInterval(0.0, 1.0, W=torch.zeros(2, 2)).bind_grid(bounds) is None
+    rev = b.reversed()
+    nz = _cabi.Noise()
+    rev.fill(nz, 0, False, 0)
+    assert nz.cell_id == (b.node.cell_base + 2) & ((1 << 64) - 1) and nz.h == 0.5
+    assert bi.key_from_entropy(5) != bi.key_from_entropy(6) and bi.key_from_entropy(2 ** 70 + 5) != bi.key_from_entropy(5)
+
+
+def test_halfway_tree_structure_is_query_order_independent():
+    a = tsde.BrownianInterval(0.0, 1.0, size=(2,), device='cuda', halfway_tree=True, tol=1e-3)
+    b = tsde.BrownianInterval(0.0, 1.0, size=(2,), device='cuda', halfway_tree=True, tol=1e-3)
+    qs = [(0.125, 0.5), (0.3, 0.7), (0.0, 0.06)]
+    pa = [[(p.start, p.end, p.id) for p in a._locate(a._round(x), a._round(y))] for x, y in qs]
+    pb = [[(p.start, p.end, p.id) for p in b._locate(b._round(x), b._round(y))] for x, y in reversed(qs)][::-1]
+    assert pa == pb

@@ -101,7 +101,12 @@ def lib():
     return _lib
 
 
+LAUNCHES = 0  # number of C-ABI launch calls issued by this process (bench.py reports it)
+
+
 def check(code, what):
+    global LAUNCHES
+    LAUNCHES += 1
     if code != 0:
         msg = lib().tsde_error_string(code).decode()
         raise RuntimeError(f"torchsde_b200: {what} failed: {msg} (code {code})")

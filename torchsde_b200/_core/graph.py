@@ -1,0 +1,122 @@
+"""CUDA-graph time loop.
+
+The reference's `integrate` (torchsde/_core/base_solver.py:107-147) is a Python loop with two or
+three host<->device syncs per step.  Here the *whole solve* — for every step {user f/g as ordinary
+torch ops (and Milstein's autograd vjp) -> fused tableau kernels} — is captured once into a CUDA
+graph and replayed per call, so a solve costs one graph launch: no Python, no launch gaps beyond
+the graph's own dependencies, `ys[i]` written in place by the step that produces it.
+
+What makes this possible (and what it requires):
+* the time grid is planned on the host (schedule.py) and all per-step scalars are launch arguments;
+* the Brownian increments come from the Philox counter: per call only the 8-byte key changes, and
+  the kernels read it from a static device buffer that is refreshed before each replay;
+* `y0` (and a solver's extra state) are copied into static buffers before each replay;
+* `f`/`g` must be pure functions of (t, y) and of tensors that are updated *in place*
+  (nn.Parameters, buffers): their addresses are baked into the graph.  Host-side control flow on
+  tensor values (`.item()`, `float(t)`) inside f/g cannot be captured; such SDEs run with the
+  default eager loop.
+
+Enable with ``options={'cuda_graph': True}``.  The returned `ys` is the plan's static output buffer:
+it is overwritten by the next solve that reuses the plan (standard CUDA-graph output semantics).
+Plans are cached per (sde object, method, shapes, dtype, grid, dt, Brownian structure).
+"""
+import weakref
+
+import torch
+
+from . import base_solver
+from . import schedule as schedule_lib
+from .._brownian import BrownianInterval, ReverseBrownian
+
+_PLANS = weakref.WeakKeyDictionary()
+
+
+class _Plan:
+    pass
+
+
+def _plan_key(solver, y0, ts, extra0, binding):
+    node = binding.node
+    return (type(solver).__name__, tuple(y0.shape), y0.dtype, str(y0.device),
+            tuple(ts.detach().cpu().tolist()), str(ts.dtype),
+            float(solver.dt) if not torch.is_tensor(solver.dt) else float(solver.dt),
+            tuple(sorted((k, repr(v)) for k, v in solver.options.items())),
+            solver.bm.levy_area_approximation, tuple(solver.bm.shape),
+            node.cell_base, tuple(binding.first), tuple(binding.count), binding.reverse,
+            binding.interval._row_offset,
+            tuple((tuple(e.shape), e.dtype) for e in extra0))
+
+
+def integrate_captured(solver, y0, ts, extra0):
+    sde_obj = solver.sde._base_sde
+    sched = schedule_lib.build_schedule(ts, solver.dt)
+    y0 = base_solver._contig(y0.detach())
+    solver._prepare(y0)
+    binding = solver._bind(sched)
+    if binding is None or solver.adaptive:
+        # arbitrary Brownian objects keep host-side state per query: not replayable
+        return solver.integrate(y0, ts, extra0)
+    extra0 = tuple(base_solver._contig(e.detach()) for e in extra0)
+    key = _plan_key(solver, y0, ts, extra0, binding)
+    plans = _PLANS.setdefault(sde_obj, {})
+    plan = plans.get(key)
+    if plan is None:
+        plan = _capture(solver, sched, binding, y0, ts, extra0)
+        plans[key] = plan
+    plan.y0.copy_(y0)
+    plan.key.copy_(binding.interval.key_tensor())
+    for dst, src in zip(plan.extra_in, extra0):
+        dst.copy_(src)
+    plan.graph.replay()
+    return plan.ys, plan.extra_out
+
+
+def _capture(solver, sched, binding, y0, ts, extra0):
+    plan = _Plan()
+    dev = y0.device
+    plan.solver = solver  # keeps launch descriptors / time table alive
+    plan.binding = binding  # keeps the grid node (and its device-side cell lengths) alive
+    plan.y0 = torch.empty_like(y0)
+    plan.key = torch.empty(1, dtype=torch.int64, device=dev)
+    plan.extra_in = tuple(torch.empty_like(e) for e in extra0)
+    T = ts.numel()
+    plan.ys = torch.empty((T, solver.rows, solver.d), dtype=solver.dtype, device=dev)
+    plan.y0.copy_(y0)
+    plan.key.copy_(binding.interval.key_tensor())
+    for dst, src in zip(plan.extra_in, extra0):
+        dst.copy_(src)
+
+    feed = base_solver.NoiseFeed(solver, solver.bm, binding)
+    feed._key_ptr = plan.key.data_ptr()  # kernels read the key from the static buffer
+    solver._feed = feed
+    ctxs = solver._contexts(sched, ts)
+    plan.ctxs = ctxs
+    plan.sched = sched
+
+    def body():
+        plan.ys[0].copy_(plan.y0)
+        return solver._run(sched, ctxs, plan.ys, plan.extra_in)
+
+    # Warm-up on a side stream (lazy initialisations: cuBLAS handles, autograd, allocator)
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side), torch.no_grad():
+        plan.ys[0].copy_(plan.y0)
+        n_warm = min(3, sched.n_steps)
+        if n_warm:
+            class _Few:
+                pass
+            few = _Few()
+            few.aligned_row = lambda k: None
+            few.outputs_after = {}
+            ys_tmp = plan.ys
+            solver._run(few, ctxs[:n_warm], ys_tmp, plan.extra_in)
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize(dev)
+
+    graph = torch.cuda.CUDAGraph()
+    with torch.no_grad(), torch.cuda.graph(graph):
+        extra_out = body()
+    plan.graph = graph
+    plan.extra_out = tuple(extra_out)
+    return plan
