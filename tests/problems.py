@@ -214,7 +214,13 @@ class ReplayBM:
         self.device = None
 
     def __call__(self, ta, tb=None, return_U=False, return_A=False):
-        W, U = self.table[(float(ta), float(tb))]
+        key = (float(ta), float(tb))
+        if key not in self.table:  # e.g. an fp32 time grid replaying increments recorded on an fp64 grid
+            near = min(self.table, key=lambda k: abs(k[0] - key[0]) + abs(k[1] - key[1]))
+            if abs(near[0] - key[0]) + abs(near[1] - key[1]) > 1e-5:
+                raise KeyError(key)
+            key = near
+        W, U = self.table[key]
         if self.to_torch is not None:
             W = self.to_torch(W)
             U = None if U is None else self.to_torch(U)

@@ -67,7 +67,7 @@ def test_ito_diagonal_fixture(path, dtype):
     Us = [torch.from_numpy(u).to(tdt).to(dev) for u in case['U']]
     bm = problems.ReplayBM(case['ta'], case['tb'], Ws, Us, levy='space-time')
     y0 = torch.from_numpy(case['y0']).to(tdt).to(dev)
-    ts = torch.from_numpy(case['ts']).to(dev)  # float64 grid in both runs, as in the reference fixture
+    ts = torch.from_numpy(case['ts']).to(tdt).to(dev)  # linspace(0, 2, 10), dt = 0.1 (diagnostics/ito_diagonal.py:31-33)
     ys = tsde.sdeint(mod, y0, ts, bm=bm, method=str(case['method']), dt=float(case['dt']),
                      options={'grad_free': True} if bool(case['grad_free']) else None)
     ys = ys.double().cpu().numpy()
@@ -124,13 +124,14 @@ def test_counter_path_vs_oracle(kind, sde_type, method, opts, d, m, dtype):
     levy = 'space-time' if method == 'srk' else 'none'
     bm = tsde.BrownianInterval(0.0, 0.375, size=(B, bm_m), dtype=tdt, device=dev, entropy=4242,
                                levy_area_approximation=levy)
-    ys = tsde.sdeint(sde.to(dev), y0.to(dev), torch.from_numpy(ts).to(dev), bm=bm, method=method, dt=dt,
+    sde_dev = problems.make(kind, d, m, sde_type, dtype=tdt, seed=2).to(dev)
+    ys = tsde.sdeint(sde_dev, y0.to(dev), torch.from_numpy(ts).to(dev), bm=bm, method=method, dt=dt,
                      options=opts)
     assert bm._root.kind == 2, "solver did not bind its grid (fast path not taken)"
     sde_cpu = problems.make(kind, d, m, sde_type, dtype=tdt, seed=2)
     oracle_bm = _oracle_bm_from(bm, B, bm_m, npdt, levy != 'none')
     ref, _ = solvers.make(method, problems.NumpySDE(sde_cpu), oracle_bm, dt, opts).integrate(y0.numpy(), ts)
-    tol = dict(rtol=1e-11, atol=1e-12) if dtype == 'f64' else dict(rtol=3e-5, atol=3e-6)
+    tol = dict(rtol=1e-11, atol=1e-12) if dtype == 'f64' else dict(rtol=5e-5, atol=1e-5)
     np.testing.assert_allclose(ys.cpu().numpy(), ref, **tol)
 
 

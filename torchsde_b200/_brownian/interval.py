@@ -105,7 +105,12 @@ def _check_tensor_info(*tensors, size, dtype, device):
         raise ValueError("Multiple sizes found. Make sure `size` and `W` or `H` are consistent.")
     if not all(i == dtypes[0] for i in dtypes):
         raise ValueError("Multiple dtypes found. Make sure `dtype` and `W` or `H` are consistent.")
-    if not all(torch.device(i) == torch.device(devices[0]) for i in devices):
+    def _norm(dv):
+        dv = torch.device(dv)
+        if dv.type == 'cuda' and dv.index is None and torch.cuda.is_available():
+            dv = torch.device('cuda', torch.cuda.current_device())
+        return dv
+    if not all(_norm(i) == _norm(devices[0]) for i in devices):
         raise ValueError("Multiple devices found. Make sure `device` and `W` or `H` are consistent.")
     return tuple(sizes[0]), dtypes[0], devices[0]
 
@@ -563,7 +568,8 @@ class BrownianInterval(brownian_base.BaseBrownian):
                 U = U.reshape(self._size)
             W = W.reshape(self._size)
             if A is not None:
-                A = A.reshape((*self._size, *self._size[-1:]))
+                # rank 0/1: zero Levy area with the shape of W (brownian_interval.py:81-84)
+                A = A.reshape(self._size if len(self._size) < 2 else (*self._size, *self._size[-1:]))
 
         if return_U:
             if return_A:

@@ -20,6 +20,16 @@ constexpr int kThreads = 256;
 constexpr int kSMs = 148;        // B200
 constexpr int kBlocksPerSM = 8;  // 2048 threads / SM
 
+inline int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = kSMs;
+  }
+  return n;
+}
+
 template <typename T>
 struct NoiseP {
   const T* w;         // MEMORY
@@ -33,6 +43,9 @@ struct NoiseP {
   const double* cell_h;  // device, or nullptr
   double h_total;     // tb - ta of the whole query (for U)
   int64_t m;          // channels of the noise tensor
+  T sqrt_h;           // (T)sqrt(h), (T)sqrt(h/12), (T)h_total: host-rounded once (single-cell path)
+  T sqrt_h12;
+  T ht;
 };
 
 template <int NIN, int NOUT>
@@ -44,6 +57,8 @@ struct EwP {
   int64_t qpr;     // quads per row
   int64_t nquads;  // rows * qpr
   int32_t vec;     // all pointers 16B-aligned and d % 4 == 0
+  int32_t qshift;  // log2(qpr) if qpr is a power of two, else -1
+  int32_t small;   // nquads < 2^31: 32-bit index arithmetic
 };
 
 // ---- vector load / store helpers ---------------------------------------------------------
@@ -95,6 +110,22 @@ template <typename T, bool WANT_U>
 __device__ __forceinline__ void counter_noise(const NoiseP<T>& nz, Key key, uint32_t row,
                                               uint32_t q, T (&w)[4], T (&u)[4]) {
   T hh[4];
+  if (nz.n_cells == 1) {
+    // the solver's own grid: one primary cell per step, scales rounded once on the host
+    T n[4];
+    normal4(key, nz.cell_id, STREAM_W, row, q, n);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) w[j] = n[j] * nz.sqrt_h;
+    if (WANT_U) {
+      normal4(key, nz.cell_id, STREAM_H, row, q, n);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        hh[j] = n[j] * nz.sqrt_h12;
+        u[j] = nz.ht * (T(0.5) * w[j] + hh[j]);  // _H_to_U :102-103
+      }
+    }
+    return;
+  }
   double len0 = nz.cell_h ? nz.cell_h[0] : nz.h;
   {
     T n[4];
@@ -182,8 +213,18 @@ ew_kernel(const EwP<Op::NIN, Op::NOUT> p, const NoiseP<T> nz, const Op op) {
   const bool vec = p.vec != 0;
   const int64_t stride = (int64_t)gridDim.x * kThreads;
   for (int64_t Q = (int64_t)blockIdx.x * kThreads + threadIdx.x; Q < p.nquads; Q += stride) {
-    const int64_t row = Q / p.qpr;
-    const int64_t q = Q - row * p.qpr;
+    int64_t row, q;
+    if (p.qshift >= 0) {
+      row = Q >> p.qshift;
+      q = Q & ((1 << p.qshift) - 1);
+    } else if (p.small) {
+      const uint32_t r32 = (uint32_t)Q / (uint32_t)p.qpr;
+      row = r32;
+      q = (uint32_t)Q - r32 * (uint32_t)p.qpr;
+    } else {
+      row = Q / p.qpr;
+      q = Q - row * p.qpr;
+    }
     const int64_t base = row * p.d + 4 * q;
     const int64_t rem = p.d - 4 * q;
     const int nvalid = rem < 4 ? (int)rem : 4;
@@ -230,6 +271,9 @@ inline int fill_noise(const tsde_launch* L, const tsde_noise* nz, bool bcast, No
   out.h = nz->h;
   out.cell_h = nz->cell_h;
   out.h_total = nz->h_total;
+  out.sqrt_h = (T)sqrt(nz->h);
+  out.sqrt_h12 = (T)sqrt(nz->h / 12.0);
+  out.ht = (T)nz->h_total;
   if (nz->source == TSDE_SRC_MEMORY && !nz->w) return TSDE_EINVAL;
   if (nz->source == TSDE_SRC_MEMORY && nz->want_u && !nz->u) return TSDE_EINVAL;
   if (nz->source == TSDE_SRC_COUNTER && !nz->key) return TSDE_EINVAL;
@@ -266,28 +310,45 @@ inline int launch_ew(const tsde_launch* L, const tsde_noise* nz, bool bcast,
   p.vec = vec ? 1 : 0;
   if (p.nquads == 0) return 0;
   if (L->rows + (nz ? nz->row_offset : 0) > 0xFFFFFFFFll) return TSDE_EINVAL;
-  int64_t blocks = (p.nquads + kThreads - 1) / kThreads;
-  const int64_t cap = (int64_t)kSMs * kBlocksPerSM;
-  if (blocks > cap) blocks = cap;
+  p.qshift = -1;
+  if ((p.qpr & (p.qpr - 1)) == 0 && p.qpr < (1ll << 30)) {
+    int sh = 0;
+    while ((1ll << sh) < p.qpr) ++sh;
+    p.qshift = sh;
+  }
+  p.small = p.nquads < (1ll << 31) ? 1 : 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(L->stream);
+  auto go = [&](auto kernel) -> int {
+    // Persistent, balanced grid: one wave of resident CTAs, every thread the same trip count.
+    static int resident = 0;  // CTAs per SM of this instantiation (queried once)
+    if (resident == 0) {
+      int n = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kThreads, 0) != cudaSuccess || n < 1) n = 1;
+      resident = n;
+    }
+    const int64_t cap = (int64_t)sm_count() * resident;
+    const int64_t per_cta = kThreads;
+    int64_t iters = (p.nquads + cap * per_cta - 1) / (cap * per_cta);
+    if (iters < 1) iters = 1;
+    int64_t blocks = (p.nquads + per_cta * iters - 1) / (per_cta * iters);
+    if (blocks < 1) blocks = 1;
+    kernel<<<(unsigned)blocks, kThreads, 0, st>>>(p, np, op);
+    return (int)cudaGetLastError();
+  };
   if constexpr (!Op::USES_NOISE) {
-    ew_kernel<T, Op, TSDE_SRC_UNIT><<<(unsigned)blocks, kThreads, 0, st>>>(p, np, op);
+    return go(ew_kernel<T, Op, TSDE_SRC_UNIT>);
   } else {
     switch (src) {
       case TSDE_SRC_MEMORY:
-        ew_kernel<T, Op, TSDE_SRC_MEMORY><<<(unsigned)blocks, kThreads, 0, st>>>(p, np, op);
-        break;
+        return go(ew_kernel<T, Op, TSDE_SRC_MEMORY>);
       case TSDE_SRC_COUNTER:
-        ew_kernel<T, Op, TSDE_SRC_COUNTER><<<(unsigned)blocks, kThreads, 0, st>>>(p, np, op);
-        break;
+        return go(ew_kernel<T, Op, TSDE_SRC_COUNTER>);
       case TSDE_SRC_UNIT:
-        ew_kernel<T, Op, TSDE_SRC_UNIT><<<(unsigned)blocks, kThreads, 0, st>>>(p, np, op);
-        break;
+        return go(ew_kernel<T, Op, TSDE_SRC_UNIT>);
       default:
         return TSDE_EINVAL;
     }
   }
-  return (int)cudaGetLastError();
 }
 
 #define TSDE_DISPATCH_DTYPE(L, EXPR_F32, EXPR_F64) \

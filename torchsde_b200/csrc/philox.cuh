@@ -14,6 +14,8 @@
 //     x[4] = Philox4x32-10(ctr, K)
 //   fp32:  u_j = fma(float(x_j), 2^-32, 2^-33)            (round-to-nearest conversion)
 //          n0,n1 = BoxMuller(u_0, u_1) ; n2,n3 = BoxMuller(u_2, u_3);  normal = n[lane]
+//          (evaluated with SFU approximations, see below; the oracle evaluates the same
+//           formula in float64 — agreement ~1e-6 absolute per normal)
 //   fp64:  two calls (call = 0,1); call k serves lanes 2k, 2k+1:
 //          u_a = ((x_0 * 2^32 + x_1) >> 11 + 0.5) * 2^-53 ; u_b likewise from x_2,x_3
 //          n_{2k}, n_{2k+1} = BoxMuller(u_a, u_b)
@@ -52,16 +54,50 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1
 }
 
 // ---- fp32 -------------------------------------------------------------------------------
+// The Brownian kernels are HBM-bound only if the normals are cheap, so the fp32 path uses the
+// SFU (MUFU.LG2 / MUFU.SQRT / MUFU.SIN / MUFU.COS) instead of libm:
+//   * radius:  r^2 = -2 ln u.  MUFU.LG2 has ~2^-22 *absolute* error, which would hurt only for
+//     u -> 1 (tiny r); there u = 1 - v with v = (~x + 0.5) 2^-32 exact, and
+//     -ln(1 - v) = v (1 + v/2 + v^2/3 + ...) is used instead (x >= 0xFF000000, v < 2^-8).
+//   * angle:   theta = 2 pi b - pi in (-pi, pi] where sin/cos.approx are accurate (~5e-7 abs);
+//     cos(2 pi b) = -cos(theta), sin(2 pi b) = -sin(theta).
+// Agreement with the float64 oracle: a few 1e-7 relative on r, <= ~1e-6 absolute on a normal.
 __device__ __forceinline__ float u01(uint32_t x) {
   return fmaf(__uint2float_rn(x), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
 }
 
-__device__ __forceinline__ void box_muller(float a, float b, float& n0, float& n1) {
-  const float r = sqrtf(-2.0f * logf(a));
-  float s, c;
-  sincospif(2.0f * b, &s, &c);
-  n0 = r * c;
-  n1 = r * s;
+__device__ __forceinline__ float mufu_lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float mufu_sqrt(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float mufu_sin(float x) {
+  float y;
+  asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float mufu_cos(float x) {
+  float y;
+  asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// a = u01(xa) drives the radius, b = u01(xb) the angle
+__device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, float& n0, float& n1) {
+  const float a = u01(xa);
+  const float v = fmaf(__uint2float_rn(~xa), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+  const float series = 2.0f * v * fmaf(v, fmaf(v, 0.33333334f, 0.5f), 1.0f);
+  const float viaLog = -1.3862943611198906f * mufu_lg2(a);  // -2 ln2 log2(a)
+  const float r2 = xa >= 0xFF000000u ? series : viaLog;
+  const float r = mufu_sqrt(r2);
+  const float th = fmaf(u01(xb), 6.2831853071795865f, -3.1415926535897932f);
+  n0 = -r * mufu_cos(th);
+  n1 = -r * mufu_sin(th);
 }
 
 // four normals for channels 4q..4q+3 of (row, id, stream)
@@ -69,8 +105,8 @@ __device__ __forceinline__ void normal4(Key k, uint64_t id, uint32_t stream, uin
                                         uint32_t q, float (&n)[4]) {
   const uint4 x = philox4x32_10(
       make_uint4(q | (stream << 24), row, (uint32_t)id, (uint32_t)(id >> 32)), k.lo, k.hi);
-  box_muller(u01(x.x), u01(x.y), n[0], n[1]);
-  box_muller(u01(x.z), u01(x.w), n[2], n[3]);
+  box_muller(x.x, x.y, n[0], n[1]);
+  box_muller(x.z, x.w, n[2], n[3]);
 }
 
 // ---- fp64 -------------------------------------------------------------------------------
