@@ -211,8 +211,12 @@ ew_kernel(const EwP<Op::NIN, Op::NOUT> p, const NoiseP<T> nz, const Op op) {
   Key key{0u, 0u};
   if (Op::USES_NOISE && SRC == TSDE_SRC_COUNTER) key = load_key(nz.key);
   const bool vec = p.vec != 0;
-  const int64_t stride = (int64_t)gridDim.x * kThreads;
-  for (int64_t Q = (int64_t)blockIdx.x * kThreads + threadIdx.x; Q < p.nquads; Q += stride) {
+  // Each CTA owns one contiguous slice of the quads, slices differ by at most one quad: with
+  // gridDim = SMs x resident CTAs every SM gets the same amount of work (no tail wave, no
+  // ceil(trip count) imbalance between SMs).
+  const int64_t q_begin = (p.nquads * (int64_t)blockIdx.x) / gridDim.x;
+  const int64_t q_end = (p.nquads * ((int64_t)blockIdx.x + 1)) / gridDim.x;
+  for (int64_t Q = q_begin + threadIdx.x; Q < q_end; Q += kThreads) {
     int64_t row, q;
     if (p.qshift >= 0) {
       row = Q >> p.qshift;
@@ -319,7 +323,7 @@ inline int launch_ew(const tsde_launch* L, const tsde_noise* nz, bool bcast,
   p.small = p.nquads < (1ll << 31) ? 1 : 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(L->stream);
   auto go = [&](auto kernel) -> int {
-    // Persistent, balanced grid: one wave of resident CTAs, every thread the same trip count.
+    // Persistent, balanced grid: one wave of resident CTAs, each owning an equal contiguous slice.
     static int resident = 0;  // CTAs per SM of this instantiation (queried once)
     if (resident == 0) {
       int n = 0;
@@ -327,11 +331,8 @@ inline int launch_ew(const tsde_launch* L, const tsde_noise* nz, bool bcast,
       resident = n;
     }
     const int64_t cap = (int64_t)sm_count() * resident;
-    const int64_t per_cta = kThreads;
-    int64_t iters = (p.nquads + cap * per_cta - 1) / (cap * per_cta);
-    if (iters < 1) iters = 1;
-    int64_t blocks = (p.nquads + per_cta * iters - 1) / (per_cta * iters);
-    if (blocks < 1) blocks = 1;
+    int64_t blocks = (p.nquads + kThreads - 1) / kThreads;  // small problems: one quad per thread
+    if (blocks > cap) blocks = cap;                          // large: one resident wave, sliced evenly
     kernel<<<(unsigned)blocks, kThreads, 0, st>>>(p, np, op);
     return (int)cudaGetLastError();
   };
