@@ -158,6 +158,7 @@ class BaseSDESolver(metaclass=abc.ABCMeta):
         self.dt_min = dt_min
         self.options = options
         self._prepared = False
+        self._side_stream = None
 
     def __repr__(self):
         return f"{self.__class__.__name__} of strong order: {self.strong_order}, and weak order: {self.weak_order}"
@@ -199,6 +200,32 @@ class BaseSDESolver(metaclass=abc.ABCMeta):
         self._LU = ctypes.byref(self.launch_unit)
         self._lib = _cabi.lib()
         self._prepared = True
+
+    # -- drift on a parallel branch --------------------------------------------------------------
+    # f(t, y) and the diffusion chain g -> (vjp) are independent given y.  Issuing the drift on a
+    # side stream makes them parallel branches of the captured graph (fork/join), so PyTorch's
+    # latency-bound element-wise kernels of the user's f overlap with the g chain instead of
+    # queueing behind it.  Evaluation *order* of f and g is not observable for pure callables.
+    def _drift_async(self, fn):
+        if not self.options.get('overlap_drift', True):
+            return fn(), None
+        main = torch.cuda.current_stream(self.device)
+        side = self._side_stream
+        if side is None:
+            side = self._side_stream = torch.cuda.Stream(device=self.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            out = fn()
+        return out, side
+
+    def _drift_join(self, out, side):
+        if side is not None:
+            main = torch.cuda.current_stream(self.device)
+            main.wait_stream(side)
+            for t in (out if isinstance(out, (tuple, list)) else (out,)):
+                if torch.is_tensor(t):
+                    t.record_stream(main)
+        return out
 
     def _refresh_stream(self):
         stream = torch.cuda.current_stream(self.device).cuda_stream

@@ -114,13 +114,14 @@ class BaseMilstein(_ProdMixin, base_solver.BaseSDESolver):
             _check(lib.tsde_step_milstein_gf(self._L, self._feed.get(c), _p(y0), _p(f), _p(g), _p(g_prime), c.dt,
                                              c.scalars['two_sqrt_dt'], ito, _p(out)), "tsde_step_milstein_gf")
             return ()
-        f = _contig(sde.f(c.t0, y0))
         if sde.noise_type == NOISE_TYPES.additive:
+            f = _contig(sde.f(c.t0, y0))
             # g_prod_and_gdg_prod_additive: (g_prod(t, y, v1), 0.)  base_sde.py:157-158
             def fin(L, nz, g):
                 _check(lib.tsde_step_euler(L, nz, _p(y0), _p(f), _p(g), c.dt, _p(out)), "tsde_step_euler")
             self._g_prod(c, c.t0, y0, fin)
             return ()
+        f, side = self._drift_async(lambda: _contig(sde.f(c.t0, y0)))
         # g_prod_and_gdg_prod_{diagonal,default}: vjp of g wrt y with grad_outputs g * (0.5 v)
         # base_sde.py:127-155 (always calls self.g, never g_prod)
         with torch.enable_grad():
@@ -136,6 +137,7 @@ class BaseMilstein(_ProdMixin, base_solver.BaseSDESolver):
                 gdg = None
         if gdg is None:
             gdg = torch.zeros_like(y0)
+        self._drift_join(f, side)
         _check(lib.tsde_step_milstein(self._L, self._feed.get(c), _p(y0), _p(f), _p(gd), _p(_contig(gdg)), c.dt,
                                       _p(out)), "tsde_step_milstein")
         return ()
