@@ -260,3 +260,27 @@ def test_ragged_ts_interpolation_and_reuse():
     assert torch.isfinite(coarse).all()
     s = sum(bm(k / 8, (k + 1) / 8) for k in range(8))
     torch.testing.assert_close(s, w_all, rtol=1e-12, atol=1e-13)
+
+
+@pytest.mark.parametrize('kind,sde_type,method,d,m', [('gbm', 'ito', 'milstein', 64, 64), ('gbm', 'ito', 'srk', 8, 8),
+                                                      ('general', 'stratonovich', 'heun', 8, 16),
+                                                      ('gbm', 'stratonovich', 'reversible_heun', 8, 8)])
+def test_cuda_graph_equals_eager(kind, sde_type, method, d, m):
+    """options={'cuda_graph': True}: replayed solves are bit-identical to the eager loop, including
+    replays with a new Brownian key / new y0 (only static buffers are refreshed)."""
+    tsde = _tsde()
+    dev = torch.device('cuda')
+    B = 64
+    sde = problems.make(kind, d, m, sde_type, dtype=torch.float32, seed=1).to(dev)
+    bm_m = d if kind == 'gbm' else m
+    ts = torch.tensor([0.0, 0.125, 0.25, 0.5], device=dev)
+    levy = 'space-time' if method == 'srk' else 'none'
+    for entropy, fill in ((11, 0.3), (12, 0.6), (11, 0.3)):
+        y0 = torch.full((B, d), fill, device=dev)
+        outs = []
+        for graph in (False, True):
+            bm = tsde.BrownianInterval(0.0, 0.5, size=(B, bm_m), dtype=torch.float32, device=dev, entropy=entropy,
+                                       levy_area_approximation=levy)
+            outs.append(tsde.sdeint(sde, y0, ts, bm=bm, method=method, dt=2.0 ** -4,
+                                    options={'cuda_graph': graph}).clone())
+        assert torch.equal(outs[0], outs[1])

@@ -85,37 +85,64 @@ class _BackwardEngine(base_solver.BaseSDESolver):
     def _step(self, c, y0, extra0, out):
         raise RuntimeError("internal")
 
-    def run(self, ys, ts, grad_ys, extras, grad_extras):
-        """Backward sweep over all output intervals (adjoint.py:97-119).  Returns
-        adj_y0, (adj_f, adj_g, adj_z), adj_params."""
-        lib = _cabi.lib()
+    def plan(self, ys, ts):
+        """Host-side plan of the backward sweep: one schedule per interval [-ts[i], -ts[i-1]], exactly
+        as the reference re-enters integrate() (adjoint.py:97-113), merged into one step list."""
         T = ts.numel()
         y = _contig(ys[-1])
         self._prepare(y)
-        L = self._L
         neg_ts = -ts
-        # One schedule per interval [-ts[i], -ts[i-1]], exactly as the reference re-enters integrate().
-        scheds = [schedule_lib.build_schedule(torch.stack([neg_ts[i], neg_ts[i - 1]]), self.dt)
-                  for i in range(T - 1, 0, -1)]
-        bounds = [scheds[0].bounds[0]]
-        for s in scheds:
+        self.scheds = [schedule_lib.build_schedule(torch.stack([neg_ts[i], neg_ts[i - 1]]), self.dt)
+                       for i in range(T - 1, 0, -1)]
+        bounds = [self.scheds[0].bounds[0]]
+        for s in self.scheds:
             bounds.extend(s.bounds[1:])
-        merged = schedule_lib.Schedule(None, [st for s in scheds for st in s.steps], [])
+        merged = schedule_lib.Schedule(None, [st for s in self.scheds for st in s.steps], [])
         merged.bounds = bounds
-        binding = self._bind(merged)
-        self._feed = base_solver.NoiseFeed(self, self.bm, binding)
-        ctxs = self._contexts(merged, ts)
+        self.binding = self._bind(merged)
+        self._feed = base_solver.NoiseFeed(self, self.bm, self.binding)
+        self.ctxs = self._contexts(merged, ts)
+        self.T = T
 
+    def param_names(self):
+        """Names of the adjoint parameters inside the SDE module tree (None if some are foreign tensors)."""
+        by_id = {id(p): n for n, p in self.sde.named_parameters()}
+        names = [by_id.get(id(p)) for p in self.params]
+        return None if any(n is None for n in names) else names
+
+    def sweep(self, ys, grad_ys, extras, grad_extras, alias_names=None):
+        """Backward sweep over all output intervals (adjoint.py:97-119).  Capturable: no host syncs.
+        Returns adj_y0, (adj_f, adj_g, adj_z), adj_params.
+
+        alias_names (graph capture only): differentiate w.r.t. fresh detached aliases of the parameters,
+        swapped into the module for the duration of the call.  A parameter's cached AccumulateGrad node
+        remembers the stream it was created on (usually the legacy default stream); when a parameter
+        receives gradient from two paths autograd synchronises *that* stream with the producer, which is
+        illegal while another stream is capturing.  Aliases created under capture do not have this problem
+        and give bit-identical gradients."""
+        if alias_names is not None:
+            from torch.nn.utils import stateless
+            aliases = {n: p.detach().requires_grad_() for n, p in zip(alias_names, self.params)}
+            with stateless._reparametrize_module(self.sde, aliases):
+                return self._sweep(ys, grad_ys, extras, grad_extras, [aliases[n] for n in alias_names])
+        return self._sweep(ys, grad_ys, extras, grad_extras, self.params)
+
+    def _sweep(self, ys, grad_ys, extras, grad_extras, params):
+        lib = _cabi.lib()
+        self._refresh_stream()
+        L = self._L
+        T = self.T
+        y = _contig(ys[-1])
         f0, g0, z0 = (_contig(x.detach()) for x in extras)
         adj_y = _contig(grad_ys[-1]).clone()
         adj_f, adj_g, adj_z = (_contig(x).clone() for x in grad_extras)
-        adj_params = [torch.zeros_like(p) for p in self.params]
+        adj_params = [torch.zeros_like(p) for p in params]
         sde = self.sde
         k = 0
-        for n, sched in enumerate(scheds):
+        for n, sched in enumerate(self.scheds):
             i = T - 1 - n
             for _ in range(sched.n_steps):
-                c = ctxs[k]
+                c = self.ctxs[k]
                 k += 1
                 t_fwd0, t_fwd1 = c.aux_t
                 half_dt = c.scalars['half_dt']
@@ -134,9 +161,9 @@ class _BackwardEngine(base_solver.BaseSDESolver):
                             outs.append(o)
                             gouts.append(go.view_as(o))
                     if outs:
-                        vjps = torch.autograd.grad(outs, [z0r] + self.params, gouts, allow_unused=True)
+                        vjps = torch.autograd.grad(outs, [z0r] + list(params), gouts, allow_unused=True)
                     else:
-                        vjps = [None] * (1 + len(self.params))
+                        vjps = [None] * (1 + len(params))
                 vjp_z = vjps[0] if vjps[0] is not None else torch.zeros_like(z0)
                 for ap, v in zip(adj_params, vjps[1:]):
                     if v is not None:
@@ -159,6 +186,71 @@ class _BackwardEngine(base_solver.BaseSDESolver):
             adj_y = adj_y + grad_ys[i - 1]
         return adj_y, (adj_f, adj_g, adj_z), adj_params
 
+    def run(self, ys, ts, grad_ys, extras, grad_extras):
+        self.plan(ys, ts)
+        return self.sweep(ys, grad_ys, extras, grad_extras)
+
+
+_BWD_PLANS = __import__('weakref').WeakKeyDictionary()
+
+
+def _backward_plan(engine, ys, ts, extras):
+    """Capture (once) the backward sweep as a CUDA graph.  Called from the *forward* pass, i.e. from
+    the user's thread: stream capture cannot be started from inside the autograd engine's worker
+    thread (its stream bookkeeping touches the legacy stream).  Same design as graph.py: static
+    inputs refreshed by copies, Philox key read from a static 8-byte buffer."""
+    from . import graph as graph_mod
+    engine.plan(ys, ts)
+    binding = engine.binding
+    names = engine.param_names()
+    if binding is None or names is None:
+        return None
+    sde_obj = engine.sde._base_sde
+    key = ('bwd',) + graph_mod._plan_key(engine, ys[0], ts, tuple(extras), binding) + (
+        tuple(tuple(p.shape) for p in engine.params),)
+    plans = _BWD_PLANS.setdefault(sde_obj, {})
+    plan = plans.get(key)
+    if plan is not None:
+        return plan
+    plan = graph_mod._Plan()
+    plan.engine, plan.binding = engine, binding
+    plan.ys = ys.detach().clone()
+    plan.grad_ys = torch.zeros_like(plan.ys)
+    plan.extras = tuple(_contig(e.detach()).clone() for e in extras)
+    plan.grad_extras = tuple(torch.zeros_like(e) for e in plan.extras)
+    plan.key = binding.interval.key_tensor().clone()
+    engine._feed._key_ptr = plan.key.data_ptr()
+    dev = ys.device
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):  # warm-up (cuBLAS handles, autograd, allocator): first interval only
+        saved = engine.scheds, engine.T
+        engine.scheds, engine.T = [engine.scheds[0]], 2
+        engine.sweep(plan.ys[-2:], plan.grad_ys[-2:], plan.extras, plan.grad_extras, alias_names=names)
+        engine.scheds, engine.T = saved
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize(dev)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        plan.out = engine.sweep(plan.ys, plan.grad_ys, plan.extras, plan.grad_extras, alias_names=names)
+    plan.graph = g
+    plans[key] = plan
+    return plan
+
+
+def _replay_backward(plan, bm, ys, grad_ys, extras, grad_extras):
+    plan.ys.copy_(ys)
+    plan.grad_ys.copy_(grad_ys)
+    for d, s_ in zip(plan.extras, extras):
+        d.copy_(s_)
+    for d, s_ in zip(plan.grad_extras, grad_extras):
+        d.copy_(s_)
+    plan.key.copy_(bm.key_tensor())
+    plan.graph.replay()
+    adj_y, adj_extras, adj_params = plan.out
+    # hand out copies: the static outputs are overwritten by the next replay
+    return adj_y.clone(), tuple(a.clone() for a in adj_extras), [a.clone() for a in adj_params]
+
 
 class _AdjointMarker:
     """Stands in for the reference's AdjointSDE where only its type/attributes are inspected."""
@@ -179,11 +271,20 @@ class _AdjointMarker:
 class _SdeintAdjointMethod(torch.autograd.Function):
 
     @staticmethod
-    def forward(ctx, sde, ts, dt, bm, solver, options, n_extras, y0, *extras_and_params):
+    def forward(ctx, sde, ts, dt, bm, solver, options, adjoint_options, n_extras, y0, *extras_and_params):
         ctx.sde, ctx.dt, ctx.bm, ctx.n_extras = sde, dt, bm, n_extras
+        ctx.adjoint_options = adjoint_options
         extras = tuple(x.detach() for x in extras_and_params[:n_extras])
         params = extras_and_params[n_extras:]
         ys, extras_out = sdeint_mod._integrate(solver, y0.detach(), ts, extras, options)
+        if options.get('cuda_graph', False):
+            # the graph's static output buffers are reused by the next solve; what autograd saves must not be
+            ys = ys.clone()
+            extras_out = tuple(e.clone() for e in extras_out)
+        ctx.bwd_plan = None
+        if adjoint_options.get('cuda_graph', False) and isinstance(bm, BrownianInterval):
+            engine = _BackwardEngine(sde, ReverseBrownian(bm), dt, params)
+            ctx.bwd_plan = _backward_plan(engine, ys, ts, extras_out)
         ctx.save_for_backward(ys, ts, *extras_out, *params)
         return (ys, *extras_out)
 
@@ -194,9 +295,13 @@ class _SdeintAdjointMethod(torch.autograd.Function):
         params = rest[ctx.n_extras:]
         grad_extras = [torch.zeros_like(e) if g is None else g for g, e in zip(grad_extras, extras)]
         with torch.no_grad():
-            engine = _BackwardEngine(ctx.sde, ReverseBrownian(ctx.bm), ctx.dt, params)
-            adj_y, adj_extras, adj_params = engine.run(ys, ts, grad_ys, extras, grad_extras)
-        return (None, None, None, None, None, None, None, adj_y, *adj_extras, *adj_params)
+            if ctx.bwd_plan is not None:
+                adj_y, adj_extras, adj_params = _replay_backward(ctx.bwd_plan, ctx.bm, ys, grad_ys, extras,
+                                                                 grad_extras)
+            else:
+                engine = _BackwardEngine(ctx.sde, ReverseBrownian(ctx.bm), ctx.dt, params)
+                adj_y, adj_extras, adj_params = engine.run(ys, ts, grad_ys, extras, grad_extras)
+        return (None, None, None, None, None, None, None, None, adj_y, *adj_extras, *adj_params)
 
 
 def sdeint_adjoint(sde, y0, ts, bm=None, method=None, adjoint_method=None, dt=1e-3, adaptive=False,
@@ -260,7 +365,8 @@ def sdeint_adjoint(sde, y0, ts, bm=None, method=None, adjoint_method=None, dt=1e
         extra_solver_state = solver.init_extra_solver_state(ts[0], y0)
 
     ys, *extra_solver_state = _SdeintAdjointMethod.apply(
-        sde, ts, dt, bm, solver, options, len(extra_solver_state), y0, *extra_solver_state, *adjoint_params)
+        sde, ts, dt, bm, solver, options, adjoint_options, len(extra_solver_state), y0, *extra_solver_state,
+        *adjoint_params)
     return sdeint_mod.parse_return(y0, ys, extra_solver_state, extra, logqp)
 
 
