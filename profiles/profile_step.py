@@ -20,8 +20,10 @@ dev = torch.device('cuda')
 sde = bench.build_sde(w, dev)
 ts = (torch.arange(n + 1, dtype=torch.float32) * w['dt']).to(dev)
 y0 = torch.full((w['B'], w['D']), 0.1, device=dev)
-bm = tsde.BrownianInterval(0.0, n * w['dt'], size=(w['B'], w['D']), dtype=torch.float32, device=dev, entropy=1)
+M = w['D'] if w.get('kind', 'gbm') == 'gbm' else w['M']
+bm = tsde.BrownianInterval(0.0, n * w['dt'], size=(w['B'], M), dtype=torch.float32, device=dev, entropy=1,
+                           levy_area_approximation=w.get('levy', 'none'))
 with torch.no_grad():
-    ys = tsde.sdeint(sde, y0, ts, bm=bm, method=w['method'], dt=w['dt'])
+    ys = tsde.sdeint(sde, y0, ts, bm=bm, method=w['method'], dt=w['dt'], options=w.get('options'))
 torch.cuda.synchronize()
 print('ok', float(ys[-1].mean()))

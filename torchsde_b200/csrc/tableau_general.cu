@@ -156,6 +156,109 @@ gen_kernel(const GenP<Op::NE, Op::NG, Op::NO> p, const NoiseP<T> nz, const Op op
   }
 }
 
+// ---- fast path (m % 4 == 0, m/4 a power of two <= 32) ------------------------------------------
+// One small CTA (128 threads) per group of RW = 32 / (m/4) consecutive rows: the first warp
+// produces the group's RW x m increments (one Philox quad per lane) into shared memory, then
+// all four warps stream the group's g tile (RW x d x m contiguous floats) with kGenUnroll
+// independent 128-bit loads per thread in flight.  Many small CTAs keep the whole tile set in
+// flight at once, which is what matters at the batch sizes of general-noise SDEs (tens of MiB).
+constexpr int kGenUnroll = 4;
+constexpr int kGenThreads = 128;
+
+template <typename T, typename Op, int SRC>
+__global__ void __launch_bounds__(kGenThreads)
+gen_cta_kernel(const GenP<Op::NE, Op::NG, Op::NO> p, const NoiseP<T> nz, const Op op) {
+  constexpr int NE = Op::NE, NG = Op::NG, NP = Op::NP, NO = Op::NO;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x;
+  const int m = (int)p.m, mq = p.mq, rw = p.rb;  // rb = rows per group here
+  const int mq_shift = __ffs(mq) - 1;
+  T* sw = reinterpret_cast<T*>(smem_raw);
+  T* su = sw + rw * m;
+  const int per_row = (int)p.d * mq;
+  const int64_t row0 = (int64_t)blockIdx.x * rw;
+  const int nrows = (int)((p.rows - row0) < rw ? (p.rows - row0) : rw);
+  // phase 1: increments of the group's rows (<= 32 quads)
+  if (tid < nrows * mq) {
+    Key key{0u, 0u};
+    if (SRC == TSDE_SRC_COUNTER) key = load_key(nz.key);
+    const int r = tid >> mq_shift, q = tid & (mq - 1);
+    T w[4], u[4];
+    if (SRC == TSDE_SRC_COUNTER) {
+      counter_noise<T, Op::WANT_U>(nz, key, (uint32_t)(row0 + r + nz.row_offset), (uint32_t)q, w, u);
+    } else {
+      const int64_t base = (row0 + r) * m + 4 * q;
+      ld4(nz.w + base, w);
+      if (Op::WANT_U) ld4(nz.u + base, u);
+    }
+    st4(sw + r * m + 4 * q, w);
+    if (Op::WANT_U) st4(su + r * m + 4 * q, u);
+  }
+  // issue the first batch of g loads before waiting for the increments
+  const int total = nrows * per_row;
+  for (int c0 = 0; c0 < total; c0 += kGenThreads * kGenUnroll) {
+    T gv[kGenUnroll][NG][4];
+    int rr[kGenUnroll], mcs[kGenUnroll];
+    int64_t eoffs[kGenUnroll];
+    bool valid[kGenUnroll];
+#pragma unroll
+    for (int un = 0; un < kGenUnroll; ++un) {
+      const int c = c0 + un * kGenThreads + tid;
+      valid[un] = c < total;
+      const int cc = valid[un] ? c : 0;
+      const int r = cc / per_row;
+      const int rem = cc - r * per_row;
+      const int dd = rem >> mq_shift;
+      const int mc = rem & (mq - 1);
+      rr[un] = r;
+      mcs[un] = mc;
+      eoffs[un] = (row0 + r) * p.d + dd;
+      const int64_t goff = eoffs[un] * m + 4 * mc;
+#pragma unroll
+      for (int i = 0; i < NG; ++i) {
+        if (valid[un]) {
+          ld4(reinterpret_cast<const T*>(p.g[i]) + goff, gv[un][i]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) gv[un][i][j] = T(0);
+        }
+      }
+    }
+    if (c0 == 0) __syncthreads();  // increments visible (uniform: every thread runs iteration 0)
+#pragma unroll
+    for (int un = 0; un < kGenUnroll; ++un) {
+      T part[NP];
+#pragma unroll
+      for (int k = 0; k < NP; ++k) part[k] = T(0);
+      T w4[4], u4[4];
+      ld4(sw + rr[un] * m + 4 * mcs[un], w4);
+      if (Op::WANT_U) ld4(su + rr[un] * m + 4 * mcs[un], u4);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        T gj[NG];
+#pragma unroll
+        for (int i = 0; i < NG; ++i) gj[i] = gv[un][i][j];
+#pragma unroll
+        for (int k = 0; k < NP; ++k)
+          part[k] = part[k] + op.gval(k, gj) * op.weight(k, w4[j], Op::WANT_U ? u4[j] : T(0));
+      }
+      for (int off = 1; off < mq; off <<= 1) {
+#pragma unroll
+        for (int k = 0; k < NP; ++k) part[k] = part[k] + __shfl_xor_sync(0xffffffffu, part[k], off);
+      }
+      if (valid[un] && mcs[un] == 0) {
+        T e[NE > 0 ? NE : 1], o[NO];
+#pragma unroll
+        for (int i = 0; i < NE; ++i) e[i] = reinterpret_cast<const T*>(p.e[i])[eoffs[un]];
+        op.combine(e, part, o);
+#pragma unroll
+        for (int i = 0; i < NO; ++i) reinterpret_cast<T*>(p.o[i])[eoffs[un]] = o[i];
+      }
+    }
+  }
+  if (total == 0) __syncthreads();
+}
+
 template <typename T, typename Op>
 static int launch_gen(const tsde_launch* L, const tsde_noise* nz,
                       std::initializer_list<const void*> es, std::initializer_list<const void*> gs,
@@ -174,13 +277,29 @@ static int launch_gen(const tsde_launch* L, const tsde_noise* nz,
   if (int e = fill_noise<T>(L, nz, false, np)) return e;
   const int64_t mq = L->m / 4;
   vec = vec && mq >= 1 && mq <= 32 && (mq & (mq - 1)) == 0;
+  if (nz->source == TSDE_SRC_MEMORY) vec = vec && aligned16(np.w) && (!Op::WANT_U || aligned16(np.u));
   p.rows = L->rows; p.d = L->d; p.m = L->m;
   p.mq = (int32_t)mq;
   p.vec = vec ? 1 : 0;
   if (L->rows == 0) return 0;
   if (L->rows + nz->row_offset > 0xFFFFFFFFll) return TSDE_EINVAL;
-  // rows per block: ~16 work items per thread, bounded by shared memory for the increments
-  const int64_t per_row = vec ? L->d * mq : L->d;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(L->stream);
+  if (vec) {
+    // one 128-thread CTA per group of rw rows
+    const int64_t rw = 32 / mq;
+    p.rb = (int32_t)rw;
+    const int64_t ngroups = (L->rows + rw - 1) / rw;
+    if (ngroups > 0x7fffffffll) return TSDE_EINVAL;
+    const size_t smem = (size_t)rw * L->m * sizeof(T) * (Op::WANT_U ? 2 : 1);
+    if (nz->source == TSDE_SRC_MEMORY) {
+      gen_cta_kernel<T, Op, TSDE_SRC_MEMORY><<<(unsigned)ngroups, kGenThreads, smem, st>>>(p, np, op);
+    } else {
+      gen_cta_kernel<T, Op, TSDE_SRC_COUNTER><<<(unsigned)ngroups, kGenThreads, smem, st>>>(p, np, op);
+    }
+    return (int)cudaGetLastError();
+  }
+  // generic path: rows per block ~16 work items per thread, bounded by shared memory for the increments
+  const int64_t per_row = L->d;
   int64_t rb = (16 * kThreads + per_row - 1) / per_row;
   if (rb < 1) rb = 1;
   if (rb > kMaxRowsPerBlock) rb = kMaxRowsPerBlock;
@@ -193,7 +312,6 @@ static int launch_gen(const tsde_launch* L, const tsde_noise* nz,
   const int64_t blocks = (L->rows + rb - 1) / rb;
   if (blocks > 0x7fffffffll) return TSDE_EINVAL;
   const size_t smem = (size_t)(rb * smem_per_row);
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(L->stream);
   if (nz->source == TSDE_SRC_MEMORY) {
     gen_kernel<T, Op, TSDE_SRC_MEMORY><<<(unsigned)blocks, kThreads, smem, st>>>(p, np, op);
   } else {
