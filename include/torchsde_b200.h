@@ -250,6 +250,12 @@ int tsde_step_srk_additive(const tsde_launch* L, const tsde_noise* nz, const voi
 int tsde_linear_interp(const tsde_launch* L, const void* y0, const void* y1, double w0,
                        double w1, void* out);
 
+/* Adaptive stepping: out[0] (double) = sum over all (rows*d) elements of ((y11 - y12)/tol)^2 with
+ * tol = clamp_min(rtol*max(|y11|,|y12|) + atol, eps)   _core/adaptive_stepping.py:42-76 (compute_error, _rms).
+ * scratch: device buffer of >= 592 doubles.  The host finishes with sqrt(out/numel).clamp_min(eps). */
+int tsde_adaptive_error_sumsq(const tsde_launch* L, const void* y11, const void* y12, double rtol,
+                              double atol, double eps, void* scratch, void* out);
+
 /* ------------------------------------------------------------------------ */
 /* Reversible-Heun adjoint  (methods/reversible_heun.py:98-144)              */
 /* ------------------------------------------------------------------------ */

@@ -50,6 +50,63 @@ class Solver:
         return np.stack(ys, axis=0), extra
 
 
+def update_step_size(error_estimate, prev_step_size, safety=0.9, facmin=0.2, facmax=1.4, prev_error_ratio=None):
+    # adaptive_stepping.py:21-39
+    if error_estimate > 1:
+        pfactor = 0
+        ifactor = 1 / 1.5
+    else:
+        pfactor = 0.13
+        ifactor = 1 / 4.5
+    error_ratio = safety / error_estimate
+    if prev_error_ratio is None:
+        prev_error_ratio = error_ratio
+    factor = error_ratio ** ifactor * (error_ratio / prev_error_ratio) ** pfactor
+    if error_estimate <= 1:
+        prev_error_ratio = error_ratio
+        facmin = 1.0
+    factor = min(facmax, max(facmin, factor))
+    return prev_step_size * factor, prev_error_ratio
+
+
+def compute_error(y11, y12, rtol, atol, eps=1e-7):
+    # adaptive_stepping.py:42-76
+    tol = np.maximum(_sc(rtol, y11) * np.maximum(np.abs(y11), np.abs(y12)) + _sc(atol, y11), _sc(eps, y11))
+    x = (y11 - y12) / tol
+    return float(max(np.sqrt((x ** 2).sum() / x.size), eps))
+
+
+def integrate_adaptive(solver, y0, ts, rtol, atol, dt_min, extra0=None):
+    """base_solver.py:107-149 with the adaptive branch (:117-142)."""
+    ts = np.asarray(ts)
+    step_size = solver.dt
+    prev_t = curr_t = ts[0]
+    prev_y = curr_y = y0
+    curr_extra = solver.init_extra(ts[0], y0) if extra0 is None else extra0
+    ys = [y0]
+    prev_error_ratio = None
+    n_proposals = 0
+    for out_t in ts[1:]:
+        while curr_t < out_t:
+            next_t = min(curr_t + step_size, ts[-1])
+            next_y_full, _ = solver.step(curr_t, next_t, curr_y, curr_extra)
+            midpoint_t = 0.5 * (curr_t + next_t)
+            midpoint_y, midpoint_extra = solver.step(curr_t, midpoint_t, curr_y, curr_extra)
+            next_y, next_extra = solver.step(midpoint_t, next_t, midpoint_y, midpoint_extra)
+            error_estimate = compute_error(next_y_full, next_y, rtol, atol)
+            step_size, prev_error_ratio = update_step_size(error_estimate, step_size,
+                                                           prev_error_ratio=prev_error_ratio)
+            n_proposals += 1
+            if step_size < dt_min:
+                step_size = dt_min
+                prev_error_ratio = None
+            if error_estimate <= 1 or step_size <= dt_min:
+                prev_t, prev_y = curr_t, curr_y
+                curr_t, curr_y, curr_extra = next_t, next_y, next_extra
+        ys.append(linear_interp(prev_t, prev_y, curr_t, curr_y, out_t))
+    return np.stack(ys, axis=0), curr_extra, n_proposals
+
+
 def linear_interp(t0, y0, t1, y1, t):
     # interp.py:15-18
     w0 = (t1 - t) / (t1 - t0)

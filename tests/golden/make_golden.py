@@ -245,8 +245,47 @@ def adjoint_cases():
         print('wrote adjoint', name)
 
 
+def adaptive_cases():
+    """Adaptive stepping (base_solver.py:117-142) on identical increments: the recorder logs every proposal's
+    three queries; rtol/atol chosen so that proposals get rejected."""
+    cases = [('gbm_ito_euler', 'gbm', 'euler', 'ito', 6, 6), ('gbm_ito_srk', 'gbm', 'srk', 'ito', 8, 8),
+             ('gbm_ito_milstein', 'gbm', 'milstein', 'ito', 6, 6),
+             ('general_strat_heun', 'general', 'heun', 'stratonovich', 4, 8),
+             ('additive_strat_midpoint', 'additive', 'midpoint', 'stratonovich', 3, 2),
+             ('scalar_strat_reversible_heun', 'scalar', 'reversible_heun', 'stratonovich', 5, 1)]
+    import warnings
+    for i, (name, kind, method, sde_type, d, m) in enumerate(cases):
+        torch.manual_seed(4321 + i)
+        tdt = torch.float64
+        sde = problems.make(kind, d, m, sde_type, dtype=tdt, seed=i)
+        B = 4
+        y0 = (0.1 + 0.5 * torch.rand(B, d, dtype=tdt))
+        ts = torch.tensor([0.0, 0.4, 1.0], dtype=tdt)
+        levy = 'space-time' if method == 'srk' else 'none'
+        bm_m = d if kind == 'gbm' else m
+        bm = torchsde.BrownianInterval(0.0, 1.0, size=(B, bm_m), dtype=tdt, entropy=500 + i, levy_area_approximation=levy)
+        rec = Recorder(bm)
+        rtol, atol = 1e-3, 1e-3
+        with torch.no_grad(), warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            ys = torchsde.sdeint(sde, y0, ts, bm=rec, method=method, dt=0.2, adaptive=True, rtol=rtol, atol=atol,
+                                 dt_min=1e-4)
+        save = dict(y0=y0.numpy(), ts=ts.numpy(), dt=np.float64(0.2), ys=ys.numpy(), rtol=rtol, atol=atol, dt_min=1e-4,
+                    ta=np.array([r[0] for r in rec.log]), tb=np.array([r[1] for r in rec.log]),
+                    W=np.stack([r[2] for r in rec.log]), kind=kind, method=method, sde_type=sde_type, d=d, m=m,
+                    dtype='f64', seed=i, grad_free=False, n_queries=len(rec.log))
+        if rec.log[0][3] is not None:
+            save['U'] = np.stack([r[3] for r in rec.log])
+        np.savez_compressed(os.path.join(HERE, f'adaptive_{name}.npz'), **save)
+        print('wrote adaptive', name, len(rec.log) // 3, 'proposals')
+
+
 if __name__ == '__main__':
+    if 'adaptive' in sys.argv:
+        adaptive_cases()
+        sys.exit(0)
     all_solver_cases()
     ito_diagonal_fixture()
     bridge_cases()
     adjoint_cases()
+    adaptive_cases()

@@ -284,3 +284,32 @@ def test_cuda_graph_equals_eager(kind, sde_type, method, d, m):
             outs.append(tsde.sdeint(sde, y0, ts, bm=bm, method=method, dt=2.0 ** -4,
                                     options={'cuda_graph': graph}).clone())
         assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize('path', helpers.golden_files('adaptive_'), ids=helpers.case_id)
+def test_adaptive_golden_replay(path):
+    """adaptive=True on the reference's increments: same accept/reject history, same ys."""
+    import warnings
+    tsde = _tsde()
+    case = helpers.load(path)
+    dev = torch.device('cuda')
+    sde = helpers.build_problem(case, device=dev)
+    bm = helpers.replay_torch(case, dev)
+    calls = []
+    inner = bm.__call__
+
+    class Counting:
+        shape, levy_area_approximation = bm.shape, bm.levy_area_approximation
+
+        def __call__(self, ta, tb=None, return_U=False, return_A=False):
+            calls.append((float(ta), float(tb)))
+            return bm(ta, tb, return_U=return_U)
+
+    y0 = torch.from_numpy(case['y0']).to(dev)
+    ts = torch.from_numpy(case['ts']).to(dev)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        ys = tsde.sdeint(sde, y0, ts, bm=Counting(), method=str(case['method']), dt=float(case['dt']), adaptive=True,
+                         rtol=float(case['rtol']), atol=float(case['atol']), dt_min=float(case['dt_min']))
+    assert len(calls) == int(case['n_queries'])
+    np.testing.assert_allclose(ys.cpu().numpy(), case['ys'], rtol=1e-9, atol=1e-11)

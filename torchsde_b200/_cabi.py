@@ -70,6 +70,7 @@ SIGNATURES = {
     'tsde_srk_additive_stage': [_L, _N, _P, _P, _P, _D, _D, _P],
     'tsde_step_srk_additive': [_L, _N, _P, _P, _P, _P, _P, _D, _D, _P],
     'tsde_linear_interp': [_L, _P, _P, _D, _D, _P],
+    'tsde_adaptive_error_sumsq': [_L, _P, _P, _D, _D, _D, _P, _P],
     'tsde_adjoint_reversible_heun_a': [_L, _N, _P, _P, _P, _P, _P, _P, _P, _D, _D, _P, _P, _P],
     'tsde_adjoint_reversible_heun_b': [_L, _N, _P, _P, _P, _P, _P, _P, _P, _P, _D, _D, _P, _P, _P, _P, _P],
 }

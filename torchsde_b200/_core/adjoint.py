@@ -356,7 +356,9 @@ def sdeint_adjoint(sde, y0, ts, bm=None, method=None, adjoint_method=None, dt=1e
             "method='reversible_heun', adjoint_method='adjoint_reversible_heun'; the generic AdjointSDE "
             "path is not implemented yet.")
     if adaptive or adjoint_adaptive:
-        raise NotImplementedError("torchsde_b200: adaptive time-stepping is not implemented yet.")
+        raise NotImplementedError("torchsde_b200: adaptive time-stepping is not implemented for sdeint_adjoint "
+                                  "(the reversible pair does not record its step sizes; reference warning "
+                                  "adjoint.py:246-249).")
 
     _cabi.require_cuda(y0)
     if extra_solver_state is None:

@@ -159,6 +159,7 @@ class BaseSDESolver(metaclass=abc.ABCMeta):
         self.options = options
         self._prepared = False
         self._side_stream = None
+        self._err_buf = None
 
     def __repr__(self):
         return f"{self.__class__.__name__} of strong order: {self.strong_order}, and weak order: {self.weak_order}"
@@ -288,8 +289,7 @@ class BaseSDESolver(metaclass=abc.ABCMeta):
         """Integrate along trajectory.  Returns ys (T, batch, d) and the final extra state
         (base_solver.py:92-149, fixed-step branch)."""
         if self.adaptive:
-            raise NotImplementedError(
-                "torchsde_b200: adaptive time-stepping is not implemented yet (fixed-step solvers only).")
+            return self._integrate_adaptive(y0, ts, extra0)
         sched = schedule_lib.build_schedule(ts, self.dt)
         y0 = _contig(y0.detach())
         self._prepare(y0)
@@ -303,6 +303,89 @@ class BaseSDESolver(metaclass=abc.ABCMeta):
         with torch.no_grad():
             extra = self._run(sched, ctxs, ys, extra)
         return ys, extra
+
+    # ------------------------------------------------------------------------------------------
+    # adaptive time-stepping (base_solver.py:117-142, adaptive_stepping.py:21-76)
+    # ------------------------------------------------------------------------------------------
+    def _error_estimate(self, y_full, y_half):
+        """compute_error of adaptive_stepping.py:42-69: RMS of (y11 - y12) / tol, reduced on the GPU."""
+        eps = 1e-7
+        if self._err_buf is None:
+            self._err_buf = torch.empty(1024, dtype=torch.float64, device=self.device)
+        buf = self._err_buf
+        _cabi.check(self._lib.tsde_adaptive_error_sumsq(self._LU, y_full.data_ptr(), y_half.data_ptr(),
+                                                        float(self.rtol), float(self.atol), eps,
+                                                        buf[1:].data_ptr(), buf.data_ptr()),
+                    "tsde_adaptive_error_sumsq")
+        total = float(buf[0].item())  # the one host sync per step, as in the reference (:69)
+        err = (total / y_full.numel()) ** 0.5
+        assert err == err, ('Found nans in the error estimate. Try increasing the tolerance or regularizing '
+                            'the dynamics.')
+        return max(err, eps)
+
+    @staticmethod
+    def _update_step_size(error_estimate, prev_step_size, safety=0.9, facmin=0.2, facmax=1.4,
+                          prev_error_ratio=None):
+        """PI step-size controller, adaptive_stepping.py:21-39."""
+        if error_estimate > 1:
+            pfactor, ifactor = 0, 1 / 1.5
+        else:
+            pfactor, ifactor = 0.13, 1 / 4.5
+        error_ratio = safety / error_estimate
+        if prev_error_ratio is None:
+            prev_error_ratio = error_ratio
+        factor = error_ratio ** ifactor * (error_ratio / prev_error_ratio) ** pfactor
+        if error_estimate <= 1:
+            prev_error_ratio = error_ratio
+            facmin = 1.0
+        factor = min(facmax, max(facmin, factor))
+        return prev_step_size * factor, prev_error_ratio
+
+    def _integrate_adaptive(self, y0, ts, extra0):
+        """One full step vs two half steps per proposal; accept / reject on the host.  Step sizes are
+        data dependent, so this branch is an eager loop (one device->host scalar per proposal, exactly
+        the reference's sync count) and the Brownian motion is queried at arbitrary times through
+        ``bm(ta, tb)``; every step still runs the fused tableau kernels."""
+        y0 = _contig(y0.detach())
+        self._prepare(y0)
+        self._err_buf = None
+        ts_cpu = ts.detach().to('cpu')
+        step_size = self.dt.detach().to('cpu') if torch.is_tensor(self.dt) else self.dt
+        prev_t = curr_t = ts_cpu[0]
+        prev_y = curr_y = y0
+        curr_extra = tuple(extra0)
+        T = ts.numel()
+        ys = torch.empty((T, self.rows, self.d), dtype=self.dtype, device=self.device)
+        ys[0].copy_(y0)
+        prev_error_ratio = None
+        with torch.no_grad():
+            for i in range(1, T):
+                out_t = ts_cpu[i]
+                while curr_t < out_t:
+                    next_t = min(curr_t + step_size, ts_cpu[-1])
+                    next_y_full, _ = self.step(curr_t, next_t, curr_y, curr_extra)
+                    midpoint_t = 0.5 * (curr_t + next_t)
+                    midpoint_y, midpoint_extra = self.step(curr_t, midpoint_t, curr_y, curr_extra)
+                    next_y, next_extra = self.step(midpoint_t, next_t, midpoint_y, midpoint_extra)
+                    error_estimate = self._error_estimate(next_y_full, next_y)
+                    step_size, prev_error_ratio = self._update_step_size(
+                        error_estimate=error_estimate, prev_step_size=step_size, prev_error_ratio=prev_error_ratio)
+                    if step_size < self.dt_min:
+                        warnings.warn("Hitting minimum allowed step size in adaptive time-stepping.")
+                        step_size = self.dt_min
+                        prev_error_ratio = None
+                    if error_estimate <= 1 or step_size <= self.dt_min:
+                        prev_t, prev_y = curr_t, curr_y
+                        curr_t, curr_y, curr_extra = next_t, next_y, next_extra
+                # interp.py:15-18
+                if bool(curr_t == out_t):
+                    ys[i].copy_(curr_y)
+                else:
+                    w0 = float((curr_t - out_t) / (curr_t - prev_t))
+                    w1 = float((out_t - prev_t) / (curr_t - prev_t))
+                    _cabi.check(self._lib.tsde_linear_interp(self._LU, prev_y.data_ptr(), curr_y.data_ptr(), w0, w1,
+                                                             ys[i].data_ptr()), "tsde_linear_interp")
+        return ys, curr_extra
 
     def _run(self, sched, ctxs, ys, extra):
         """The time loop proper: capturable (no syncs, no host-dependent control flow)."""

@@ -8,7 +8,8 @@ Known differences, by design:
 * tensors must live on a CUDA device (there is no CPU path);
 * gradients do not flow through `sdeint` (the tableau kernels are not autograd nodes);
   use `sdeint_adjoint` for training, as the reference recommends for memory reasons anyway;
-* `adaptive=True` raises NotImplementedError ("next").
+* `adaptive=True` runs the reference's controller as an eager loop (data-dependent step sizes cannot be
+  graph-captured); every proposal still uses the fused kernels.
 """
 import warnings
 
@@ -62,7 +63,7 @@ def sdeint(sde, y0, ts, bm=None, method=None, dt=1e-3, adaptive=False, rtol=1e-5
 
 
 def _integrate(solver, y0, ts, extra_solver_state, options):
-    if options.get('cuda_graph', False):
+    if options.get('cuda_graph', False) and not solver.adaptive:
         from . import graph
         return graph.integrate_captured(solver, y0, ts, extra_solver_state)
     return solver.integrate(y0, ts, extra_solver_state)

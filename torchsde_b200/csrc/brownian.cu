@@ -430,3 +430,66 @@ int tsde_brownian_merge_area(const tsde_launch* L, void* a0, const void* a1, con
 }
 
 }  // extern "C"
+
+// ---- adaptive step-size control: error estimate --------------------------------------------------
+// Sum over all elements of ((y11 - y12) / tol)^2 with tol = clamp_min(rtol*max(|y11|,|y12|) + atol, eps):
+// the reduction inside compute_error / _rms of torchsde/_core/adaptive_stepping.py:42-76 (the host
+// finishes with sqrt(sum / numel).clamp_min(eps)).  Two deterministic stages, double accumulation.
+namespace tsde {
+
+constexpr int kErrBlocks = 592;  // 4 x 148
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+err_partial_kernel(const T* __restrict__ a, const T* __restrict__ b, int64_t n, T rtol, T atol, T eps,
+                   double* __restrict__ partial) {
+  double acc = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+    const T x = a[i], y = b[i];
+    const T ax = x < T(0) ? -x : x, ay = y < T(0) ? -y : y;
+    T tol = rtol * (ax > ay ? ax : ay) + atol;
+    tol = tol < eps ? eps : tol;
+    const T r = (x - y) / tol;
+    acc += (double)(r * r);
+  }
+  __shared__ double sh[kThreads / 32];
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = threadIdx.x < kThreads / 32 ? sh[threadIdx.x] : 0.0;
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    if (threadIdx.x == 0) partial[blockIdx.x] = v;
+  }
+}
+
+__global__ void err_final_kernel(const double* __restrict__ partial, int nb, double* __restrict__ out) {
+  double v = 0.0;
+  for (int i = threadIdx.x; i < nb; i += 32) v += partial[i];
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+  if (threadIdx.x == 0) out[0] = v;
+}
+
+template <typename T>
+static int err_impl(const tsde_launch* L, const void* y11, const void* y12, double rtol, double atol,
+                    double eps, void* scratch, void* out) {
+  if (!y11 || !y12 || !scratch || !out) return TSDE_EINVAL;
+  const int64_t n = L->rows * L->d;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(L->stream);
+  int nb = (int)((n + kThreads - 1) / kThreads);
+  if (nb > kErrBlocks) nb = kErrBlocks;
+  if (nb < 1) nb = 1;
+  err_partial_kernel<T><<<nb, kThreads, 0, st>>>((const T*)y11, (const T*)y12, n, (T)rtol, (T)atol, (T)eps,
+                                               (double*)scratch);
+  err_final_kernel<<<1, 32, 0, st>>>((const double*)scratch, nb, (double*)out);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace tsde
+
+extern "C" int tsde_adaptive_error_sumsq(const tsde_launch* L, const void* y11, const void* y12, double rtol,
+                                         double atol, double eps, void* scratch, void* out) {
+  return TSDE_DISPATCH_DTYPE(L, tsde::err_impl<float>(L, y11, y12, rtol, atol, eps, scratch, out),
+                             tsde::err_impl<double>(L, y11, y12, rtol, atol, eps, scratch, out));
+}
