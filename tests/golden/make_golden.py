@@ -245,6 +245,44 @@ def adjoint_cases():
         print('wrote adjoint', name)
 
 
+def generic_adjoint_cases():
+    """sdeint_adjoint through the augmented AdjointSDE (adjoint_sde.py) with the default adjoint methods
+    (adjoint.py:281-296)."""
+    cases = [('gbm_ito_euler', 'gbm', 'ito', 'euler', None, 6, 6), ('gbm_ito_srk', 'gbm', 'ito', 'srk', None, 5, 5),
+             ('general_ito_euler', 'general', 'ito', 'euler', None, 4, 3),
+             ('scalar_ito_milstein', 'scalar', 'ito', 'milstein', None, 5, 1),
+             ('additive_ito_srk', 'additive', 'ito', 'srk', None, 3, 2),
+             ('general_strat_midpoint', 'general', 'stratonovich', 'midpoint', None, 4, 3),
+             ('gbm_strat_heun', 'gbm', 'stratonovich', 'heun', None, 6, 6),
+             ('additive_strat_euler_heun', 'additive', 'stratonovich', 'euler_heun', 'heun', 3, 2),
+             ('scalar_strat_midpoint_eh', 'scalar', 'stratonovich', 'midpoint', 'euler_heun', 5, 1)]
+    for i, (name, kind, sde_type, method, adjoint_method, d, m) in enumerate(cases):
+        torch.manual_seed(77 + i)
+        tdt = torch.float64
+        sde = problems.make(kind, d, m, sde_type, dtype=tdt, seed=i + 1)
+        B = 3
+        y0 = (0.1 + 0.5 * torch.rand(B, d, dtype=tdt)).requires_grad_(True)
+        ts = torch.tensor([0.0, 0.1, 0.2, 0.3], dtype=tdt)
+        levy = 'space-time' if method == 'srk' else 'none'
+        bm_m = d if kind == 'gbm' else m
+        bm = torchsde.BrownianInterval(0.0, 0.3, size=(B, bm_m), dtype=tdt, entropy=900 + i, levy_area_approximation=levy)
+        rec = Recorder(bm)
+        ys = torchsde.sdeint_adjoint(sde, y0, ts, bm=rec, method=method, adjoint_method=adjoint_method, dt=0.05)
+        weights = torch.linspace(0.5, 1.5, ys.numel(), dtype=tdt).reshape(ys.shape)
+        (ys * weights).sum().backward()
+        save = dict(y0=y0.detach().numpy(), ts=ts.numpy(), dt=np.float64(0.05), ys=ys.detach().numpy(),
+                    weights=weights.numpy(), grad_y0=y0.grad.numpy(), kind=kind, d=d, m=m, sde_type=sde_type,
+                    method=method, adjoint_method='' if adjoint_method is None else adjoint_method, seed=i + 1,
+                    ta=np.array([r[0] for r in rec.log]), tb=np.array([r[1] for r in rec.log]),
+                    W=np.stack([r[2] for r in rec.log]))
+        if rec.log[0][3] is not None:
+            save['U'] = np.stack([r[3] for r in rec.log])
+        for n, p in sde.named_parameters():
+            save['grad.' + n] = p.grad.numpy()
+        np.savez_compressed(os.path.join(HERE, f'genadj_{name}.npz'), **save)
+        print('wrote generic adjoint', name)
+
+
 def adaptive_cases():
     """Adaptive stepping (base_solver.py:117-142) on identical increments: the recorder logs every proposal's
     three queries; rtol/atol chosen so that proposals get rejected."""
@@ -284,8 +322,12 @@ if __name__ == '__main__':
     if 'adaptive' in sys.argv:
         adaptive_cases()
         sys.exit(0)
+    if 'genadj' in sys.argv:
+        generic_adjoint_cases()
+        sys.exit(0)
     all_solver_cases()
     ito_diagonal_fixture()
     bridge_cases()
     adjoint_cases()
     adaptive_cases()
+    generic_adjoint_cases()

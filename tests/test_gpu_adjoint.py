@@ -117,3 +117,25 @@ def test_adjoint_cuda_graph_equals_eager(kind, d, m):
         assert torch.equal(e[0], g[0]) and torch.equal(e[1], g[1])
         for a, b in zip(e[2], g[2]):
             assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize('path', helpers.golden_files('genadj_'), ids=helpers.case_id)
+def test_generic_adjoint_golden_replay(path):
+    """sdeint_adjoint through AdjointSDE (default adjoint methods): gradients of the reference on identical
+    increments."""
+    tsde = _tsde()
+    case = helpers.load(path)
+    sde = problems.make(str(case['kind']), int(case['d']), int(case['m']), str(case['sde_type']),
+                        dtype=torch.float64, seed=int(case['seed'])).to(DEV)
+    y0 = torch.from_numpy(case['y0']).to(DEV).requires_grad_(True)
+    ts = torch.from_numpy(case['ts']).to(DEV)
+    Ws = [torch.from_numpy(w).to(DEV) for w in case['W']]
+    Us = [torch.from_numpy(u).to(DEV) for u in case['U']] if 'U' in case else None
+    bm = problems.ReplayBM(case['ta'], case['tb'], Ws, Us, levy='space-time' if Us is not None else 'none')
+    ys = tsde.sdeint_adjoint(sde, y0, ts, bm=bm, method=str(case['method']),
+                             adjoint_method=str(case['adjoint_method']) or None, dt=float(case['dt']))
+    np.testing.assert_allclose(ys.detach().cpu().numpy(), case['ys'], rtol=1e-11, atol=1e-13)
+    (ys * torch.from_numpy(case['weights']).to(DEV)).sum().backward()
+    np.testing.assert_allclose(y0.grad.cpu().numpy(), case['grad_y0'], rtol=1e-8, atol=1e-10)
+    for n, p in sde.named_parameters():
+        np.testing.assert_allclose(p.grad.cpu().numpy(), case['grad.' + n], rtol=1e-7, atol=1e-9)

@@ -268,6 +268,30 @@ class _AdjointMarker:
         }[forward_sde.noise_type]
 
 
+def _generic_backward(sde, bm, dt, ys, ts, grad_ys, params, cfg):
+    """Backward pass through the augmented adjoint SDE (adjoint.py:65-127) for non-reversible pairs:
+    integrate (y, adj_y, adj_params) from -ts[i] to -ts[i-1] with `adjoint_method`, newest interval
+    first, resetting y to the stored ys[i-1] and adding grad_ys[i-1] in between."""
+    from .adjoint_sde import AdjointSDE
+    aug = [ys[-1], grad_ys[-1]] + [torch.zeros_like(p) for p in params]
+    shapes = [t.size() for t in aug]
+    numels = [t.numel() for t in aug]
+    adjoint_sde = AdjointSDE(sde, params, shapes)
+    reverse_bm = ReverseBrownian(bm)
+    solver_fn = methods.select(method=cfg['adjoint_method'], sde_type=adjoint_sde.sde_type)
+    solver = solver_fn(sde=adjoint_sde, bm=reverse_bm, dt=dt, adaptive=cfg['adjoint_adaptive'],
+                       rtol=cfg['adjoint_rtol'], atol=cfg['adjoint_atol'], dt_min=cfg['dt_min'],
+                       options=cfg['adjoint_options'])
+    flat = torch.cat([t.reshape(-1) for t in aug]).unsqueeze(0)
+    for i in range(ys.size(0) - 1, 0, -1):
+        out, _ = solver.integrate(flat, torch.stack([-ts[i], -ts[i - 1]]), ())
+        parts = [p.reshape(s) for p, s in zip(out[-1].squeeze(0).split(numels), shapes)]
+        parts[0] = ys[i - 1]
+        parts[1] = parts[1] + grad_ys[i - 1]
+        flat = torch.cat([t.reshape(-1) for t in parts]).unsqueeze(0)
+    return parts[1], parts[2:]
+
+
 class _SdeintAdjointMethod(torch.autograd.Function):
 
     @staticmethod
@@ -282,7 +306,8 @@ class _SdeintAdjointMethod(torch.autograd.Function):
             ys = ys.clone()
             extras_out = tuple(e.clone() for e in extras_out)
         ctx.bwd_plan = None
-        if adjoint_options.get('cuda_graph', False) and isinstance(bm, BrownianInterval):
+        if adjoint_options.get('cuda_graph', False) and isinstance(bm, BrownianInterval) \
+                and adjoint_options_reversible(adjoint_options):
             engine = _BackwardEngine(sde, ReverseBrownian(bm), dt, params)
             ctx.bwd_plan = _backward_plan(engine, ys, ts, extras_out)
         ctx.save_for_backward(ys, ts, *extras_out, *params)
@@ -293,6 +318,12 @@ class _SdeintAdjointMethod(torch.autograd.Function):
         ys, ts, *rest = ctx.saved_tensors
         extras = rest[:ctx.n_extras]
         params = rest[ctx.n_extras:]
+        if not adjoint_options_reversible(ctx.adjoint_options):
+            # generic adjoint: the solver's extra state is not part of the augmented system (adjoint.py:57-60)
+            with torch.no_grad():
+                adj_y, adj_params = _generic_backward(ctx.sde, ctx.bm, ctx.dt, ys, ts, grad_ys, list(params),
+                                                      ctx.adjoint_options['_cfg'])
+            return (None, None, None, None, None, None, None, None, adj_y, *([None] * ctx.n_extras), *adj_params)
         grad_extras = [torch.zeros_like(e) if g is None else g for g, e in zip(grad_extras, extras)]
         with torch.no_grad():
             if ctx.bwd_plan is not None:
@@ -350,15 +381,17 @@ def sdeint_adjoint(sde, y0, ts, bm=None, method=None, adjoint_method=None, dt=1e
     adjoint_solver_fn = methods.select(method=adjoint_method, sde_type=sde.sde_type)
     adjoint_solver_fn(sde=_AdjointMarker(sde), bm=ReverseBrownian(bm), dt=dt, adaptive=adjoint_adaptive,
                       rtol=adjoint_rtol, atol=adjoint_atol, dt_min=dt_min, options=adjoint_options)
-    if not (method == METHODS.reversible_heun and adjoint_method == METHODS.adjoint_reversible_heun):
-        raise NotImplementedError(
-            "torchsde_b200: sdeint_adjoint currently implements the reversible pair "
-            "method='reversible_heun', adjoint_method='adjoint_reversible_heun'; the generic AdjointSDE "
-            "path is not implemented yet.")
-    if adaptive or adjoint_adaptive:
-        raise NotImplementedError("torchsde_b200: adaptive time-stepping is not implemented for sdeint_adjoint "
-                                  "(the reversible pair does not record its step sizes; reference warning "
-                                  "adjoint.py:246-249).")
+    reversible = method == METHODS.reversible_heun and adjoint_method == METHODS.adjoint_reversible_heun
+    if adjoint_method == METHODS.adjoint_reversible_heun and not reversible:
+        raise ValueError(f"adjoint_method={repr(adjoint_method)} requires method={repr(METHODS.reversible_heun)}.")
+    if reversible and adjoint_adaptive:
+        raise NotImplementedError("torchsde_b200: adjoint_adaptive is not supported for the reversible pair (it "
+                                  "does not record its step sizes; reference warning adjoint.py:246-249).")
+    if not reversible:
+        # generic AdjointSDE path: remember the adjoint solver's configuration for backward()
+        adjoint_options['_cfg'] = dict(adjoint_method=adjoint_method, adjoint_adaptive=adjoint_adaptive,
+                                       adjoint_rtol=adjoint_rtol, adjoint_atol=adjoint_atol, dt_min=dt_min,
+                                       adjoint_options={k: v for k, v in adjoint_options.items() if k != '_cfg'})
 
     _cabi.require_cuda(y0)
     if extra_solver_state is None:
@@ -370,6 +403,10 @@ def sdeint_adjoint(sde, y0, ts, bm=None, method=None, adjoint_method=None, dt=1e
         sde, ts, dt, bm, solver, options, adjoint_options, len(extra_solver_state), y0, *extra_solver_state,
         *adjoint_params)
     return sdeint_mod.parse_return(y0, ys, extra_solver_state, extra, logqp)
+
+
+def adjoint_options_reversible(adjoint_options):
+    return adjoint_options.get('_cfg') is None
 
 
 def _select_default_adjoint_method(sde, method, adjoint_method):

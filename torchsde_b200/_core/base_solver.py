@@ -97,7 +97,7 @@ class NoiseFeed:
                 raise ValueError(f"Brownian motion returned dtype {w.dtype}, expected {s.dtype}.")
             return w, u
         nz = self.binding.fill(self._nz, c.k, want_u, self._key_ptr, self._row_offset)
-        w = torch.empty((s.rows, s.m), dtype=s.dtype, device=s.device)
+        w = torch.empty((s.bm_rows, s.m), dtype=s.dtype, device=s.device)
         u = torch.empty_like(w) if want_u else None
         _cabi.check(_cabi.lib().tsde_brownian_cells(ctypes.byref(s.launch_bm), ctypes.byref(nz), w.data_ptr(),
                                                     None if u is None else u.data_ptr(), None),
@@ -189,6 +189,9 @@ class BaseSDESolver(metaclass=abc.ABCMeta):
         self.device = y0.device
         self.rows, self.d = y0.shape
         self.m = int(torch.Size(self.bm.shape[1:]).numel()) if len(self.bm.shape) > 1 else 1
+        # rows of the Brownian tensors; differs from the state's rows only for the flat (1, N) augmented
+        # state of the generic adjoint, whose products are formed by AdjointSDE itself
+        self.bm_rows = int(self.bm.shape[0]) if len(self.bm.shape) > 1 else 1
         diag = self.sde.noise_type == NOISE_TYPES.diagonal
         nt = _cabi.NOISE_DIAGONAL if diag else _cabi.NOISE_GENERAL
         stream = torch.cuda.current_stream(self.device).cuda_stream
@@ -196,7 +199,7 @@ class BaseSDESolver(metaclass=abc.ABCMeta):
         # user-supplied products arrive as (rows, d): element-wise launch with unit noise
         self.launch_unit = _cabi.make_launch(self.dtype, _cabi.NOISE_DIAGONAL, self.rows, self.d, self.d, stream)
         # Brownian tensors are (rows, m)
-        self.launch_bm = _cabi.make_launch(self.dtype, _cabi.NOISE_DIAGONAL, self.rows, self.m, self.m, stream)
+        self.launch_bm = _cabi.make_launch(self.dtype, _cabi.NOISE_DIAGONAL, self.bm_rows, self.m, self.m, stream)
         self._L = ctypes.byref(self.launch)
         self._LU = ctypes.byref(self.launch_unit)
         self._lib = _cabi.lib()

@@ -95,6 +95,7 @@ class BaseMilstein(_ProdMixin, base_solver.BaseSDESolver):
                                  f"diffusion-vector product. Use derivative-using Milstein instead: "
                                  f"`adjoint_options=dict({METHOD_OPTIONS.grad_free}=False)`")
         super(BaseMilstein, self).__init__(sde=sde, options=options, **kwargs)
+        self._ones = None
 
     def scalars(self, dt):
         sqrt_dt = dt.sqrt()
@@ -113,6 +114,20 @@ class BaseMilstein(_ProdMixin, base_solver.BaseSDESolver):
             g_prime = _contig(sde.g(c.t0, yp))
             _check(lib.tsde_step_milstein_gf(self._L, self._feed.get(c), _p(y0), _p(f), _p(g), _p(g_prime), c.dt,
                                              c.scalars['two_sqrt_dt'], ito, _p(out)), "tsde_step_milstein_gf")
+            return ()
+        if getattr(sde, 'is_adjoint_sde', False):
+            # adjoint SDE: it forms g.v and Milstein's correction itself (adjoint_sde.py:332-377);
+            # v2 = 0.5 v is produced by the seed kernel applied to a tensor of ones
+            f = _contig(sde.f(c.t0, y0))
+            w, _ = self._feed.tensors(c)
+            if self._ones is None or self._ones.shape != w.shape:
+                self._ones = torch.ones_like(w)
+            v2 = torch.empty_like(w)
+            _check(lib.tsde_milstein_vjp_seed(ctypes.byref(self.launch_bm), self._feed.from_tensors(w), _p(self._ones),
+                                              c.dt, ito, _p(v2)), "tsde_milstein_vjp_seed")
+            gp, gdg = sde.g_prod_and_gdg_prod(c.t0, y0, w.reshape(self.bm.shape), v2.reshape(self.bm.shape))
+            _check(lib.tsde_step_milstein(self._LU, self._feed.unit(), _p(y0), _p(f), _p(_contig(gp)),
+                                          _p(_contig(gdg)), c.dt, _p(out)), "tsde_step_milstein")
             return ()
         if sde.noise_type == NOISE_TYPES.additive:
             f = _contig(sde.f(c.t0, y0))
