@@ -43,10 +43,18 @@ class Recorder:
         self.log = []
 
     def __call__(self, ta, tb=None, return_U=False, return_A=False):
-        out = self.bm(ta, tb, return_U=True) if self.bm._have_H else (self.bm(ta, tb), None)
-        W, U = out
-        self.log.append((float(ta), float(tb), W.numpy().copy(), None if U is None else U.numpy().copy()))
-        return (W, U) if return_U else W
+        A = None
+        if self.bm._have_A:
+            W, U, A = self.bm(ta, tb, return_U=True, return_A=True)
+        elif self.bm._have_H:
+            W, U = self.bm(ta, tb, return_U=True)
+        else:
+            W, U = self.bm(ta, tb), None
+        self.log.append((float(ta), float(tb), W.numpy().copy(), None if U is None else U.numpy().copy(),
+                         None if A is None else A.numpy().copy()))
+        if return_U:
+            return (W, U, A) if return_A else (W, U)
+        return (W, A) if return_A else W
 
 
 def solver_case(name, kind, method, sde_type, d, m, dtype, B=4, ts=None, dt=0.05, options=None, seed=0):
@@ -283,6 +291,31 @@ def generic_adjoint_cases():
         print('wrote generic adjoint', name)
 
 
+def log_ode_cases():
+    """methods/log_ode.py with davie / foster Levy area (the recorder also logs A)."""
+    for i, (name, kind, d, m, levy) in enumerate((('general_foster', 'general', 4, 3, 'foster'),
+                                                  ('general_davie', 'general', 3, 4, 'davie'),
+                                                  ('gbm_foster', 'gbm', 5, 5, 'foster'),
+                                                  ('additive_davie', 'additive', 3, 2, 'davie'))):
+        torch.manual_seed(55 + i)
+        tdt = torch.float64
+        sde = problems.make(kind, d, m, 'stratonovich', dtype=tdt, seed=i)
+        B = 4
+        y0 = (0.1 + 0.5 * torch.rand(B, d, dtype=tdt))
+        ts = torch.tensor([0.0, 0.1, 0.2, 0.3], dtype=tdt)
+        bm_m = d if kind == 'gbm' else m
+        bm = torchsde.BrownianInterval(0.0, 0.3, size=(B, bm_m), dtype=tdt, entropy=300 + i, levy_area_approximation=levy)
+        rec = Recorder(bm)
+        ys = torchsde.sdeint(sde, y0, ts, bm=rec, method='log_ode', dt=0.05)
+        save = dict(y0=y0.numpy(), ts=ts.numpy(), dt=np.float64(0.05), ys=ys.detach().numpy(), kind=kind, d=d, m=m,
+                    sde_type='stratonovich', method='log_ode', dtype='f64', seed=i, grad_free=False, levy=levy,
+                    ta=np.array([r[0] for r in rec.log]), tb=np.array([r[1] for r in rec.log]),
+                    W=np.stack([r[2] for r in rec.log]), U=np.stack([r[3] for r in rec.log]),
+                    A=np.stack([r[4] for r in rec.log]))
+        np.savez_compressed(os.path.join(HERE, f'logode_{name}.npz'), **save)
+        print('wrote log_ode', name)
+
+
 def adaptive_cases():
     """Adaptive stepping (base_solver.py:117-142) on identical increments: the recorder logs every proposal's
     three queries; rtol/atol chosen so that proposals get rejected."""
@@ -322,6 +355,9 @@ if __name__ == '__main__':
     if 'adaptive' in sys.argv:
         adaptive_cases()
         sys.exit(0)
+    if 'logode' in sys.argv:
+        log_ode_cases()
+        sys.exit(0)
     if 'genadj' in sys.argv:
         generic_adjoint_cases()
         sys.exit(0)
@@ -331,3 +367,4 @@ if __name__ == '__main__':
     adjoint_cases()
     adaptive_cases()
     generic_adjoint_cases()
+    log_ode_cases()

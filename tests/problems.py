@@ -203,10 +203,13 @@ class ReplayBM:
     'same-increment replay' parity device of SURVEY.md fact 3 (the reference solver accepts any
     object with .shape, .levy_area_approximation and __call__, base_solver.py:54-57)."""
 
-    def __init__(self, tas, tbs, Ws, Us=None, levy='none', to_torch=None):
+    def __init__(self, tas, tbs, Ws, Us=None, levy='none', to_torch=None, As=None):
         self.table = {}
+        self.areas = {}
         for i, (a, b) in enumerate(zip(tas, tbs)):
             self.table[(float(a), float(b))] = (Ws[i], None if Us is None else Us[i])
+            if As is not None:
+                self.areas[(float(a), float(b))] = As[i]
         self.shape = tuple(Ws[0].shape)
         self.levy_area_approximation = levy
         self.to_torch = to_torch
@@ -225,5 +228,8 @@ class ReplayBM:
             W = self.to_torch(W)
             U = None if U is None else self.to_torch(U)
         if return_A:
-            raise NotImplementedError
+            A = self.areas[key]
+            if self.to_torch is not None:
+                A = self.to_torch(A)
+            return (W, U, A) if return_U else (W, A)
         return (W, U) if return_U else W

@@ -313,3 +313,41 @@ def test_adaptive_golden_replay(path):
                          rtol=float(case['rtol']), atol=float(case['atol']), dt_min=float(case['dt_min']))
     assert len(calls) == int(case['n_queries'])
     np.testing.assert_allclose(ys.cpu().numpy(), case['ys'], rtol=1e-9, atol=1e-11)
+
+
+@pytest.mark.parametrize('path', helpers.golden_files('logode_'), ids=helpers.case_id)
+def test_log_ode_golden_replay(path):
+    """methods/log_ode.py on the reference's increments and Levy areas."""
+    tsde = _tsde()
+    case = helpers.load(path)
+    dev = torch.device('cuda')
+    sde = helpers.build_problem(case, device=dev)
+    Ws = [torch.from_numpy(w).to(dev) for w in case['W']]
+    Us = [torch.from_numpy(u).to(dev) for u in case['U']]
+    As = [torch.from_numpy(a).to(dev) for a in case['A']]
+    bm = problems.ReplayBM(case['ta'], case['tb'], Ws, Us, levy=str(case['levy']), As=As)
+    y0 = torch.from_numpy(case['y0']).to(dev)
+    ts = torch.from_numpy(case['ts']).to(dev)
+    ys = tsde.sdeint(sde, y0, ts, bm=bm, method='log_ode', dt=float(case['dt']))
+    np.testing.assert_allclose(ys.cpu().numpy(), case['ys'], rtol=1e-11, atol=1e-13)
+
+
+def test_log_ode_and_logqp_with_own_brownian():
+    """log_ode with this repo's BrownianInterval (foster Levy area from the counter), and logqp=True
+    (reference tests/test_sdeint.py:50-68,203-216: shapes (T,B,d) and (T-1,B))."""
+    tsde = _tsde()
+    dev = torch.device('cuda')
+    B, d, m, T = 8, 4, 3, 5
+    sde = problems.TanhGeneral(d, m, 'stratonovich', dtype=torch.float64).to(dev)
+    y0 = torch.full((B, d), 0.2, dtype=torch.float64, device=dev)
+    ts = torch.linspace(0, 0.4, T, dtype=torch.float64, device=dev)
+    ys = tsde.sdeint(sde, y0, ts, method='log_ode', dt=0.05)  # default bm -> foster (sdeint.py:262-270)
+    assert ys.shape == (T, B, d) and torch.isfinite(ys).all()
+
+    class WithPrior(problems.GBMDiagonal):
+        def h(self, t, y):
+            return torch.zeros_like(y)
+
+    sde2 = WithPrior(d, 'ito', dtype=torch.float64).to(dev)
+    ys2, logqp = tsde.sdeint(sde2, y0, ts, method='euler', dt=0.05, logqp=True)
+    assert ys2.shape == (T, B, d) and logqp.shape == (T - 1, B) and (logqp >= 0).all()

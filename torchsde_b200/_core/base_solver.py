@@ -241,6 +241,8 @@ class BaseSDESolver(metaclass=abc.ABCMeta):
         """Ask the Brownian motion to adopt the solver grid (fast path) if it can."""
         bm = self.bm
         binding = None
+        if getattr(self, 'needs_levy_area', False):
+            return None
         if isinstance(bm, BrownianInterval):
             binding = bm.bind_grid(sched.bounds)
         elif isinstance(bm, ReverseBrownian) and isinstance(bm.base_brownian, BrownianInterval):

@@ -393,12 +393,15 @@ class SRK(base_solver.BaseSDESolver):
         return ()
 
 
-class LogODEMidpoint(base_solver.BaseSDESolver):
-    """methods/log_ode.py:25-56 — constructor contract only; the Levy-area step is SURVEY §8(f) 'next'."""
+class LogODEMidpoint(_ProdMixin, base_solver.BaseSDESolver):
+    """methods/log_ode.py:25-56: midpoint scheme plus the Levy-area term sum_{j,k,l} dg_il/dy_j g_jk A_kl
+    (base_sde.py:165-206).  The Levy area A comes from the Brownian motion (davie / foster); the
+    jvp's through the user's g are autograd glue, the tableau arithmetic runs in the fused kernels."""
     weak_order = 1.0
     sde_type = SDE_TYPES.stratonovich
     noise_types = NOISE_TYPES.all()
     levy_area_approximations = (LEVY_AREA_APPROXIMATIONS.davie, LEVY_AREA_APPROXIMATIONS.foster)
+    needs_levy_area = True  # increments are always materialised (W and A) through bm(ta, tb, return_A=True)
 
     def __init__(self, sde, **kwargs):
         if getattr(sde, 'is_adjoint_sde', False):
@@ -408,8 +411,51 @@ class LogODEMidpoint(base_solver.BaseSDESolver):
         self.strong_order = 0.5 if sde.noise_type == NOISE_TYPES.general else 1.0
         super(LogODEMidpoint, self).__init__(sde=sde, **kwargs)
 
+    def aux_times(self, t0, t1, dt):
+        return [t0 + 0.5 * dt]
+
+    def scalars(self, dt):
+        return {'half_dt': float(0.5 * dt)}
+
+    def _dg_ga_jvp_column_sum(self, t, y, a):
+        """base_sde.py:165-185 (v1); zero for non-general noise (:71,205-206)."""
+        if self.sde.noise_type != NOISE_TYPES.general:
+            return None
+        from .adjoint_sde import _jvp
+        with torch.enable_grad():
+            y = y.detach().requires_grad_(True)
+            g = self.sde.g(t, y)
+            ga = torch.bmm(g, a)
+            total = None
+            for col in range(g.size(-1)):
+                term = _jvp(g[..., col], y, ga[..., col])
+                total = term if total is None else total + term
+        return total.detach()
+
     def _step(self, c, y0, extra0, out):
-        raise NotImplementedError("torchsde_b200: the log-ODE (Levy area) step is not implemented yet.")
+        lib = self._lib
+        W, A = self.bm(c.ft0, c.ft1, return_A=True)
+        W = _contig(W)
+        self._feed._cached = (c, W, None)  # the products below reuse this increment
+        yp = torch.empty_like(y0)
+
+        def first(L, nz, f, g):
+            _check(lib.tsde_midpoint_predict(L, nz, _p(y0), _p(f), _p(g), c.scalars['half_dt'], _p(yp)),
+                   "tsde_midpoint_predict")
+
+        self._f_and_g_prod(c, c.t0, y0, first)
+        general = self.sde.noise_type == NOISE_TYPES.general
+        tmp = torch.empty_like(y0) if general else out
+
+        def second(L, nz, fp, gp):
+            _check(lib.tsde_step_euler(L, nz, _p(y0), _p(fp), _p(gp), c.dt, _p(tmp)), "tsde_step_euler")
+
+        self._f_and_g_prod(c, c.aux_t[0], yp, second)
+        if general:
+            dg_ga = _contig(self._dg_ga_jvp_column_sum(c.aux_t[0], yp, A))
+            # y1 = (y0 + dt*f' + g'.dW) + dg_ga                                         log_ode.py:54
+            _check(lib.tsde_linear_interp(self._LU, _p(tmp), _p(dg_ga), 1.0, 1.0, _p(out)), "tsde_linear_interp")
+        return ()
 
 
 def select(method, sde_type):
