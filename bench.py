@@ -207,6 +207,8 @@ def run_ours(args, w, rank, world, local_rank):
     y0_dev = y0_host.to(dev)
     out_host = torch.empty((B, D), dtype=torch.float32).pin_memory()
     opts = {'cuda_graph': not args.no_graph}
+    if args.row_split > 1:
+        opts['row_split'] = args.row_split
     row_offset = rank * B  # weak scaling: every rank integrates its own B trajectories of one global batch
 
     M = D if w.get('kind', 'gbm') == 'gbm' else w['M']
@@ -282,7 +284,7 @@ def run_ours(args, w, rank, world, local_rank):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "method": w['method'], "sde_type": w['sde_type'], "noise": "diagonal",
                    "batch_per_gpu": B, "state": D, "t_steps": T, "dt": dt, "output": "full series (T+1,B,D)",
-                   "cuda_graph": opts['cuda_graph'], "l2_policy": "inputs larger than L2: per-step working set "
+                   "cuda_graph": opts['cuda_graph'], "row_split": args.row_split, "l2_policy": "inputs larger than L2: per-step working set "
                    "80 MiB + 16 MiB ys row streamed into a 16.8 GB series", "parallelism": f"batch-sharded x{world}",
                    "finite": finite},
         "clocks": clocks,
@@ -296,8 +298,8 @@ def run_ours(args, w, rank, world, local_rank):
             "frac": roof['gbs'] / peak, "traffic": roof.get('traffic'),
             "kernel": "ew_kernel<float, MilsteinOp, COUNTER> (tsde_step_milstein)",
             "algorithmic_bytes_per_launch": roof['bytes'], "avg_launch_us": roof['us'], "peak_source": peak_src,
-            "timing": "CUDA events around back-to-back launches of the kernel on torch's current stream, cfg2 "
-                      "tensor sizes, rotating buffer sets larger than L2"},
+            "timing": "CUDA events around a graph replay of back-to-back launches of the kernel (how the solver "
+                      "issues them), cfg2 tensor sizes, rotating buffer sets larger than L2; median of 7"},
         "roofline_whole_step": {"E_bytes_per_traj_step": E, "achieved": value / world * E / 1e9, "peak": peak,
                                 "unit": "GB/s", "frac": value / world * E / 1e9 / peak,
                                 "note": "SURVEY §8(d) E-bytes: solver kernels + the synthetic SDE's own f/g/vjp"},
@@ -329,18 +331,31 @@ def tableau_roofline(w, sde, dev):
     for s_ in sets:
         launch(s_)
     torch.cuda.synchronize(dev)
-    best = None
-    for _ in range(5):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+    # the solver replays its launches from a CUDA graph, so time them the same way: nset launches
+    # (each on a different buffer set) captured once, replayed and bracketed by CUDA events
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
         for s_ in sets:
             launch(s_)
+    graph.replay()
+    torch.cuda.synchronize(dev)
+    times = []
+    for _ in range(7):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        graph.replay()
         e1.record()
         torch.cuda.synchronize(dev)
-        us = e0.elapsed_time(e1) * 1e3 / nset
-        best = us if best is None else min(best, us)
+        times.append(e0.elapsed_time(e1) * 1e3 / nset)
+    us = float(np.median(times))
     nbytes = w['S_tableau_bytes_per_traj_step'] * B
-    return {"us": best, "bytes": nbytes, "gbs": nbytes / (best * 1e-6) / 1e9, "traffic": None}
+    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the committed
+    # `ncu --set full` capture (profiles/r01_ncu_full_all_kernels.csv): 67.15 MB + 3.33 MB (the remaining
+    # writes were still in L2 when the kernel retired)
+    traffic = 70.48e6 if (B, D) == (65536, 64) else None
+    return {"us": us, "bytes": nbytes, "gbs": nbytes / (us * 1e-6) / 1e9, "traffic": traffic}
 
 
 def main():
@@ -351,6 +366,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
     ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--row-split', type=int, default=1)
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     rank = int(os.environ.get('RANK', '0'))

@@ -351,3 +351,17 @@ def test_log_ode_and_logqp_with_own_brownian():
     sde2 = WithPrior(d, 'ito', dtype=torch.float64).to(dev)
     ys2, logqp = tsde.sdeint(sde2, y0, ts, method='euler', dt=0.05, logqp=True)
     assert ys2.shape == (T, B, d) and logqp.shape == (T - 1, B) and (logqp >= 0).all()
+
+
+def test_row_split_graph_is_bit_identical():
+    tsde = _tsde()
+    dev = torch.device('cuda')
+    B, d = 100, 8
+    sde = problems.GBMDiagonal(d, 'ito', seed=3, dtype=torch.float32).to(dev)
+    ts = torch.tensor([0.0, 0.25, 0.5], device=dev)
+    y0 = torch.rand(B, d, device=dev) + 0.1
+    outs = []
+    for opts in ({}, {'cuda_graph': True, 'row_split': 2}, {'cuda_graph': True, 'row_split': 3}):
+        bm = tsde.BrownianInterval(0.0, 0.5, size=(B, d), dtype=torch.float32, device=dev, entropy=21)
+        outs.append(tsde.sdeint(sde, y0, ts, bm=bm, method='milstein', dt=2.0 ** -4, options=opts).clone())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])

@@ -310,6 +310,51 @@ levy_area_kernel(const void* keyp, int64_t row_offset, uint64_t a_id, int64_t ro
   }
 }
 
+// Block-cooperative variant: the (m x m) normal matrix of each row is generated once (m*m/4 Philox
+// calls per row, the minimum) into shared memory with row stride m+1 (conflict-free transposed reads),
+// then A_ij = H_i W_j - W_i H_j + std_ij (N_ij - N_ji) is written with fully coalesced stores.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+levy_area_smem_kernel(const void* keyp, int64_t row_offset, uint64_t a_id, int64_t rows, int m, int rb,
+                      const T* __restrict__ w, const T* __restrict__ hh, T tenth_h, T davie_std, int foster,
+                      T* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int mm = m * m, ld = m + 1, per_row = m * ld;
+  T* sn = reinterpret_cast<T*>(smem_raw);          // [rb][m][m+1]
+  T* sw = sn + (size_t)rb * per_row;                // [rb][m]
+  T* sh = sw + (size_t)rb * m;                      // [rb][m]
+  const Key key = load_key(keyp);
+  const int64_t row0 = (int64_t)blockIdx.x * rb;
+  const int nrows = (int)((rows - row0) < rb ? (rows - row0) : rb);
+  const int qpm = (mm + 3) / 4;
+  for (int i = threadIdx.x; i < nrows * qpm; i += kThreads) {
+    const int r = i / qpm, q = i - r * qpm;
+    T n4[4];
+    normal4(key, a_id, STREAM_A, (uint32_t)(row0 + r + row_offset), (uint32_t)q, n4);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int ij = 4 * q + k;
+      if (ij < mm) sn[r * per_row + (ij / m) * ld + (ij % m)] = n4[k];
+    }
+  }
+  for (int i = threadIdx.x; i < nrows * m; i += kThreads) {
+    sw[i] = w[row0 * m + i];
+    sh[i] = hh[row0 * m + i];
+  }
+  __syncthreads();
+  const int total = nrows * mm;
+  for (int e = threadIdx.x; e < total; e += kThreads) {
+    const int r = e / mm;
+    const int ij = e - r * mm;
+    const int i = ij / m, j = ij - i * m;
+    const T wi = sw[r * m + i], wj = sw[r * m + j], hi = sh[r * m + i], hj = sh[r * m + j];
+    const T noise = sn[r * per_row + i * ld + j] - sn[r * per_row + j * ld + i];
+    const T a = hi * wj - wi * hj;
+    const T std_ = foster ? sqrt(tenth_h * ((tenth_h + hi * hi) + hj * hj)) : davie_std;
+    out[row0 * mm + e] = a + std_ * noise;
+  }
+}
+
 // A <- A + Ai + 0.5 (W (x) Wi - Wi (x) W)                         brownian_interval.py:671
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
@@ -339,6 +384,20 @@ static int levy_impl(const tsde_launch* L, const void* key, int64_t row_offset, 
   if (L->m * L->m > (1ll << 26)) return TSDE_EINVAL;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(L->stream);
   const double r12 = 1.0 / 12.0;
+  const int64_t m = L->m;
+  const size_t per_row = (size_t)(m * (m + 1) + 2 * m) * sizeof(T);
+  if (per_row <= 40 * 1024) {
+    int64_t rb = (int64_t)(40 * 1024 / per_row);
+    if (rb > 32) rb = 32;
+    while (rb > 1 && (L->rows + rb - 1) / rb < 2 * (int64_t)sm_count()) rb >>= 1;
+    const int64_t blocks = (L->rows + rb - 1) / rb;
+    if (blocks <= 0x7fffffffll) {
+      levy_area_smem_kernel<T><<<(unsigned)blocks, kThreads, rb * per_row, st>>>(
+          key, row_offset, a_id, L->rows, (int)m, (int)rb, (const T*)w, (const T*)hh, (T)(0.1 * h),
+          (T)sqrt(r12 * h * h), foster, (T*)out_a);
+      return (int)cudaGetLastError();
+    }
+  }
   levy_area_kernel<T><<<grid_for(total), kThreads, 0, st>>>(
       key, row_offset, a_id, L->rows, L->m, (const T*)w, (const T*)hh, (T)(0.1 * h),
       (T)sqrt(r12 * h * h), foster, (T*)out_a);

@@ -106,11 +106,13 @@ __device__ __forceinline__ void store_quad(T* p, int64_t base, bool vec, int nva
 // aggregation rule (brownian_interval.py:643-672):
 //     H <- ( len_i (H_i + W/2) + (start_i - ta)(H - W_i/2) ) / (end_i - ta) ;  W <- W + W_i
 // Lengths are host doubles rounded once to T (python-float * tensor semantics).
-template <typename T, bool WANT_U>
+constexpr int kSrcCounterMulti = 3;  // internal: COUNTER source merging several primary cells
+
+template <typename T, bool WANT_U, bool MULTI = true>
 __device__ __forceinline__ void counter_noise(const NoiseP<T>& nz, Key key, uint32_t row,
                                               uint32_t q, T (&w)[4], T (&u)[4]) {
   T hh[4];
-  if (nz.n_cells == 1) {
+  if (!MULTI || nz.n_cells == 1) {
     // the solver's own grid: one primary cell per step, scales rounded once on the host
     T n[4];
     normal4(key, nz.cell_id, STREAM_W, row, q, n);
@@ -126,6 +128,7 @@ __device__ __forceinline__ void counter_noise(const NoiseP<T>& nz, Key key, uint
     }
     return;
   }
+  if (!MULTI) return;  // (unreachable; lets the compiler drop the merge loop from single-cell kernels)
   double len0 = nz.cell_h ? nz.cell_h[0] : nz.h;
   {
     T n[4];
@@ -189,14 +192,15 @@ __device__ __forceinline__ void quad_noise(const NoiseP<T>& nz, Key key, int64_t
       if (WANT_U) load_quad(nz.u, base, vec, nvalid, u);
     }
   } else {
+    constexpr bool MULTI = SRC == kSrcCounterMulti;
     const uint32_t grow = (uint32_t)(row + nz.row_offset);
     if (nz.bcast) {
       T w4[4], u4[4];
-      counter_noise<T, WANT_U>(nz, key, grow, 0u, w4, u4);
+      counter_noise<T, WANT_U, MULTI>(nz, key, grow, 0u, w4, u4);
 #pragma unroll
       for (int j = 0; j < 4; ++j) { w[j] = w4[0]; u[j] = WANT_U ? u4[0] : T(0); }
     } else {
-      counter_noise<T, WANT_U>(nz, key, grow, (uint32_t)q, w, u);
+      counter_noise<T, WANT_U, MULTI>(nz, key, grow, (uint32_t)q, w, u);
     }
   }
 }
@@ -205,11 +209,11 @@ __device__ __forceinline__ void quad_noise(const NoiseP<T>& nz, Key key, int64_t
 // Op: struct with  static constexpr int NIN, NOUT; static constexpr bool USES_NOISE, WANT_U;
 //     template<T> __device__ void operator()(const T (&in)[NIN], T w, T u, T (&out)[NOUT]) const
 template <typename T, typename Op, int SRC>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 ew_kernel(const EwP<Op::NIN, Op::NOUT> p, const NoiseP<T> nz, const Op op) {
   constexpr int NIN = Op::NIN, NOUT = Op::NOUT;
   Key key{0u, 0u};
-  if (Op::USES_NOISE && SRC == TSDE_SRC_COUNTER) key = load_key(nz.key);
+  if (Op::USES_NOISE && (SRC == TSDE_SRC_COUNTER || SRC == kSrcCounterMulti)) key = load_key(nz.key);
   const bool vec = p.vec != 0;
   // Each CTA owns one contiguous slice of the quads, slices differ by at most one quad: with
   // gridDim = SMs x resident CTAs every SM gets the same amount of work (no tail wave, no
@@ -343,6 +347,7 @@ inline int launch_ew(const tsde_launch* L, const tsde_noise* nz, bool bcast,
       case TSDE_SRC_MEMORY:
         return go(ew_kernel<T, Op, TSDE_SRC_MEMORY>);
       case TSDE_SRC_COUNTER:
+        if (np.n_cells > 1) return go(ew_kernel<T, Op, kSrcCounterMulti>);
         return go(ew_kernel<T, Op, TSDE_SRC_COUNTER>);
       case TSDE_SRC_UNIT:
         return go(ew_kernel<T, Op, TSDE_SRC_UNIT>);
