@@ -247,3 +247,50 @@ def test_bridge_kernel_vs_reference_golden(path):
     mean = W.reshape(reps, *W0.shape).mean(0)
     expect = 0.3 * W0 + (6 * 0.3 * 0.7 * H0 if levy != 'none' else 0)
     assert (mean - expect).abs().max().item() < 0.05
+
+
+@pytest.mark.parametrize('kind', ['path', 'tree'])
+def test_path_and_tree_bridge_law(kind):
+    """Reference tests/test_brownian_path.py:72-96 and test_brownian_tree.py:79-103: KS test of W(t) at a
+    random time t given the end points (alpha = 1e-5)."""
+    tsde = _tsde()
+    n = 65536
+    rng = np.random.RandomState(3)
+    t0, t1 = 0.0, 1.0
+    w0 = torch.zeros(n, 1, dtype=torch.float64, device=DEV)
+    if kind == 'tree':
+        w1 = torch.randn(n, 1, dtype=torch.float64, device=DEV, generator=torch.Generator(DEV).manual_seed(1))
+        bm = tsde.BrownianTree(t0=t0, w0=w0, t1=t1, w1=w1, entropy=9, tol=1e-10, pool_size=100)
+        end = w1
+    else:
+        bm = tsde.BrownianPath(t0=t0, w0=w0)
+        end = bm(t0, t1)
+    for _ in range(3):
+        t = float(rng.uniform(0.05, 0.95))
+        wt = bm(t0, t)
+        mean = (t - t0) / (t1 - t0) * end
+        std = math.sqrt((t - t0) * (t1 - t) / (t1 - t0))
+        assert _ks(wt - mean, std) > 1e-5
+    # determinism + repr / properties
+    assert torch.equal(bm(0.2, 0.6), bm(0.2, 0.6))
+    assert 'Brownian' in repr(bm) and bm.shape == (n, 1) and bm.dtype == torch.float64
+    assert bm.levy_area_approximation == 'none'
+
+
+def test_interval_properties_and_cache_sizes():
+    tsde = _tsde()
+    for cache_size in (None, 0, 5):
+        bm = tsde.BrownianInterval(0.0, 1.0, size=(8, 2), dtype=torch.float32, device=DEV, entropy=1,
+                                   cache_size=cache_size, pool_size=16, tol=0.0)
+        pts = np.linspace(0, 1, 30)
+        a = [bm(x, y) for x, y in zip(pts[:-1], pts[1:])]
+        b = [bm(x, y) for x, y in zip(pts[:-1], pts[1:])]
+        assert all(torch.equal(x, y) for x, y in zip(a, b))
+        torch.testing.assert_close(sum(a), bm(0.0, 1.0), rtol=1e-4, atol=1e-5)
+        assert bm.cache_size == cache_size and bm.pool_size == 16 and bm.entropy == 1 and bm.tol == 0.0
+        assert bm.dt is None and bm.halfway_tree is False and bm.size() == (8, 2)
+    e1 = tsde.BrownianInterval(0.0, 1.0, size=(8, 2), device=DEV, entropy=1)(0.1, 0.4)
+    e2 = tsde.BrownianInterval(0.0, 1.0, size=(8, 2), device=DEV, entropy=2)(0.1, 0.4)
+    assert not torch.equal(e1, e2)
+    r = tsde.BrownianInterval(0.0, 1.0, size=(8, 2), device=DEV)  # entropy from numpy's global RNG (:489-490)
+    assert isinstance(r.entropy, int)
