@@ -316,6 +316,47 @@ def log_ode_cases():
         print('wrote log_ode', name)
 
 
+def backprop_cases():
+    """Gradients by backpropagation THROUGH the reference solver (plain sdeint under autograd)."""
+    cases = [('gbm', 'ito', 'euler', None, 6, 6), ('gbm', 'ito', 'milstein', None, 6, 6),
+             ('gbm', 'ito', 'milstein', {'grad_free': True}, 5, 5), ('gbm', 'ito', 'srk', None, 8, 8),
+             ('gbm', 'stratonovich', 'heun', None, 6, 6), ('gbm', 'stratonovich', 'midpoint', None, 6, 6),
+             ('gbm', 'stratonovich', 'euler_heun', None, 6, 6), ('gbm', 'stratonovich', 'reversible_heun', None, 6, 6),
+             ('gbm', 'stratonovich', 'milstein', None, 6, 6),
+             ('general', 'ito', 'euler', None, 4, 3), ('general', 'stratonovich', 'heun', None, 4, 8),
+             ('general', 'stratonovich', 'reversible_heun', None, 4, 8),
+             ('additive', 'ito', 'srk', None, 3, 2), ('additive', 'ito', 'milstein', None, 4, 8),
+             ('scalar', 'ito', 'milstein', None, 5, 1), ('scalar', 'ito', 'srk', None, 5, 1),
+             ('scalar', 'stratonovich', 'midpoint', None, 5, 1)]
+    ragged = np.linspace(0.0, 0.3, 5).tolist()
+    for i, (kind, sde_type, method, opts, d, m) in enumerate(cases):
+        torch.manual_seed(31 + i)
+        tdt = torch.float64
+        sde = problems.make(kind, d, m, sde_type, dtype=tdt, seed=i + 2)
+        B = 3
+        y0 = (0.1 + 0.5 * torch.rand(B, d, dtype=tdt)).requires_grad_(True)
+        ts = torch.tensor(ragged if i % 3 == 0 else [0.0, 0.1, 0.2, 0.3], dtype=tdt)
+        levy = 'space-time' if method == 'srk' else 'none'
+        bm_m = d if kind == 'gbm' else m
+        bm = torchsde.BrownianInterval(0.0, 0.3, size=(B, bm_m), dtype=tdt, entropy=600 + i, levy_area_approximation=levy)
+        rec = Recorder(bm)
+        ys = torchsde.sdeint(sde, y0, ts, bm=rec, method=method, dt=0.05, options=opts)
+        weights = torch.linspace(0.5, 1.5, ys.numel(), dtype=tdt).reshape(ys.shape)
+        (ys * weights).sum().backward()
+        tag = method + ('_gf' if opts else '')
+        save = dict(y0=y0.detach().numpy(), ts=ts.numpy(), dt=np.float64(0.05), ys=ys.detach().numpy(),
+                    weights=weights.numpy(), grad_y0=y0.grad.numpy(), kind=kind, d=d, m=m, sde_type=sde_type,
+                    method=method, grad_free=bool(opts), seed=i + 2,
+                    ta=np.array([r[0] for r in rec.log]), tb=np.array([r[1] for r in rec.log]),
+                    W=np.stack([r[2] for r in rec.log]))
+        if rec.log[0][3] is not None:
+            save['U'] = np.stack([r[3] for r in rec.log])
+        for n, p in sde.named_parameters():
+            save['grad.' + n] = p.grad.numpy()
+        np.savez_compressed(os.path.join(HERE, f'backprop_{kind}_{sde_type}_{tag}.npz'), **save)
+        print('wrote backprop', kind, sde_type, tag)
+
+
 def adaptive_cases():
     """Adaptive stepping (base_solver.py:117-142) on identical increments: the recorder logs every proposal's
     three queries; rtol/atol chosen so that proposals get rejected."""
@@ -355,6 +396,9 @@ if __name__ == '__main__':
     if 'adaptive' in sys.argv:
         adaptive_cases()
         sys.exit(0)
+    if 'backprop' in sys.argv:
+        backprop_cases()
+        sys.exit(0)
     if 'logode' in sys.argv:
         log_ode_cases()
         sys.exit(0)
@@ -368,3 +412,4 @@ if __name__ == '__main__':
     adaptive_cases()
     generic_adjoint_cases()
     log_ode_cases()
+    backprop_cases()

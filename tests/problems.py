@@ -171,16 +171,21 @@ class NumpySDE:
 
     def gdg(self, t, y, v2):
         tt, yt = self._t(t, y)
-        yt = yt.requires_grad_(True)
-        g = self.module.g(tt, yt)
-        v = torch.from_numpy(np.ascontiguousarray(v2))
-        go = g * (v.unsqueeze(-2) if g.dim() == 3 else v)
-        out, = torch.autograd.grad(g, yt, go, allow_unused=True)
+        with torch.enable_grad():
+            yt = yt.requires_grad_(True)
+            g = self.module.g(tt, yt)
+            v = torch.from_numpy(np.ascontiguousarray(v2))
+            go = g * (v.unsqueeze(-2) if g.dim() == 3 else v)
+            out, = torch.autograd.grad(g, yt, go.detach(), allow_unused=True)
         return (torch.zeros_like(yt) if out is None else out).detach().numpy().copy()
 
     def vjp_fg(self, t, z, adj_f, adj_g):
         """vjp of (f, g) wrt z and the parameters (reversible_heun.py:119-129)."""
         tt, zt = self._t(t, z)
+        with torch.enable_grad():
+            return self._vjp_fg(tt, zt, adj_f, adj_g)
+
+    def _vjp_fg(self, tt, zt, adj_f, adj_g):
         zt = zt.requires_grad_(True)
         if hasattr(self.module, 'f_and_g'):
             f, g = self.module.f_and_g(tt, zt)

@@ -139,3 +139,46 @@ def test_generic_adjoint_golden_replay(path):
     np.testing.assert_allclose(y0.grad.cpu().numpy(), case['grad_y0'], rtol=1e-8, atol=1e-10)
     for n, p in sde.named_parameters():
         np.testing.assert_allclose(p.grad.cpu().numpy(), case['grad.' + n], rtol=1e-7, atol=1e-9)
+
+
+@pytest.mark.parametrize('path', helpers.golden_files('backprop_'), ids=helpers.case_id)
+def test_backprop_through_solver_golden_replay(path):
+    """Plain sdeint under autograd (every tableau launch an autograd node): gradients equal those of
+    backpropagating through the REFERENCE solver on identical increments."""
+    tsde = _tsde()
+    case = helpers.load(path)
+    sde = problems.make(str(case['kind']), int(case['d']), int(case['m']), str(case['sde_type']),
+                        dtype=torch.float64, seed=int(case['seed'])).to(DEV)
+    y0 = torch.from_numpy(case['y0']).to(DEV).requires_grad_(True)
+    ts = torch.from_numpy(case['ts']).to(DEV)
+    Ws = [torch.from_numpy(w).to(DEV) for w in case['W']]
+    Us = [torch.from_numpy(u).to(DEV) for u in case['U']] if 'U' in case else None
+    bm = problems.ReplayBM(case['ta'], case['tb'], Ws, Us, levy='space-time' if Us is not None else 'none')
+    ys = tsde.sdeint(sde, y0, ts, bm=bm, method=str(case['method']), dt=float(case['dt']),
+                     options={'grad_free': True} if bool(case['grad_free']) else None)
+    assert ys.requires_grad
+    np.testing.assert_allclose(ys.detach().cpu().numpy(), case['ys'], rtol=1e-11, atol=1e-13)
+    (ys * torch.from_numpy(case['weights']).to(DEV)).sum().backward()
+    np.testing.assert_allclose(y0.grad.cpu().numpy(), case['grad_y0'], rtol=1e-9, atol=1e-11)
+    for n, p in sde.named_parameters():
+        np.testing.assert_allclose(p.grad.cpu().numpy(), case['grad.' + n], rtol=1e-8, atol=1e-10)
+
+
+def test_backprop_counter_path_matches_adjoint():
+    """Reference tests/test_adjoint.py:100-154 (test_against_sdeint): the reversible adjoint's gradients equal
+    backprop through the solver, here both on the counter-based Brownian motion."""
+    tsde = _tsde()
+    B, d = 16, 8
+    sde = problems.GBMDiagonal(d, 'stratonovich', seed=4, dtype=torch.float64).to(DEV)
+    ts = torch.tensor([0.0, 0.25, 0.5], dtype=torch.float64, device=DEV)
+    grads = []
+    for fn in (tsde.sdeint, tsde.sdeint_adjoint):
+        for p in sde.parameters():
+            p.grad = None
+        y0 = torch.full((B, d), 0.3, dtype=torch.float64, device=DEV).requires_grad_(True)
+        bm = tsde.BrownianInterval(0.0, 0.5, size=(B, d), dtype=torch.float64, device=DEV, entropy=8)
+        ys = fn(sde, y0, ts, bm=bm, method='reversible_heun', dt=2.0 ** -4)
+        ys.pow(2).sum().backward()
+        grads.append([y0.grad.clone()] + [p.grad.clone() for p in sde.parameters()])
+    for a, b in zip(*grads):
+        torch.testing.assert_close(a, b, rtol=1e-9, atol=1e-11)

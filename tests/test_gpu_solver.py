@@ -25,6 +25,15 @@ def _tsde():
     return torchsde_b200
 
 
+@pytest.fixture(autouse=True)
+def _inference_mode():
+    """These tests exercise the fused fast path: like the reference's diagnostics / benchmarks they solve
+    under torch.no_grad() (with autograd enabled and parameters requiring grad, `sdeint` takes the
+    differentiable path, which tests/test_gpu_adjoint.py covers)."""
+    with torch.no_grad():
+        yield
+
+
 @pytest.mark.parametrize('path', SOLVER_CASES, ids=helpers.case_id)
 def test_golden_replay(path):
     tsde = _tsde()

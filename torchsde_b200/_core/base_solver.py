@@ -70,9 +70,15 @@ class NoiseFeed:
             self._row_offset = binding.interval._row_offset
         self._unit = _cabi.Noise()
         self._unit.source = _cabi.SRC_UNIT
+        self._unit_ref = ctypes.byref(self._unit)
+        self._nz_ref = ctypes.byref(self._nz)
 
     def unit(self):
-        return ctypes.byref(self._unit)
+        return self._unit_ref
+
+    def prime(self, c, w, u=None):
+        """Declare the already-materialised increment of step c (log-ODE queries W and A together)."""
+        self._cached = (c, w, u)
 
     def tensors(self, c, want_u=False):
         """Materialised (W, U) for step c (needed by user-supplied g_prod / f_and_g_prod).
@@ -108,7 +114,7 @@ class NoiseFeed:
         """ctypes reference to a filled `tsde_noise` for step c."""
         if self.binding is not None:
             self.binding.fill(self._nz, c.k, want_u, self._key_ptr, self._row_offset)
-            return ctypes.byref(self._nz)
+            return self._nz_ref
         w, u = self.tensors(c, want_u)
         return self.from_tensors(w, u)
 
@@ -122,7 +128,7 @@ class NoiseFeed:
         nz.n_cells = 1
         nz.cell_h = None
         self._keep = (w, u)  # keep alive until the launch that consumes it has been enqueued
-        return ctypes.byref(nz)
+        return self._nz_ref
 
 
 class BaseSDESolver(metaclass=abc.ABCMeta):
@@ -160,6 +166,8 @@ class BaseSDESolver(metaclass=abc.ABCMeta):
         self._prepared = False
         self._side_stream = None
         self._err_buf = None
+        self._autograd = False
+        self._cur_c = None
 
     def __repr__(self):
         return f"{self.__class__.__name__} of strong order: {self.strong_order}, and weak order: {self.weak_order}"
@@ -178,8 +186,57 @@ class BaseSDESolver(metaclass=abc.ABCMeta):
 
     @abc.abstractmethod
     def _step(self, c, y0, extra0, out):
-        """Advance one step.  Writes y1 into `out` (a (rows, d) tensor) and returns extra1."""
+        """Advance one step.  Returns (y1, extra1); on the fast path y1 is written into `out` (a (rows, d)
+        tensor, e.g. a row of ys) when `out` is given."""
         raise NotImplementedError
+
+    # ------------------------------------------------------------------------------------------
+    # launching
+    # ------------------------------------------------------------------------------------------
+    def _out_like(self, name, ins):
+        if name == 'tsde_milstein_vjp_seed':
+            return torch.empty_like(ins[0])  # grad_outputs has g's shape
+        return torch.empty((self.rows, self.d), dtype=self.dtype, device=self.device)
+
+    def _launch(self, name, L, nz, ins, scalars, outs):
+        args = [L] if nz is None else [L, nz]
+        args += [t.data_ptr() for t in ins]
+        args += list(scalars)
+        args += [o.data_ptr() for o in outs]
+        _cabi.check(getattr(self._lib, name)(*args), name)
+
+    def _k(self, name, L, nz, ins, scalars, out, n_out=1, raw=False):
+        """One C-ABI tableau launch `name(L, [nz], *ins, *scalars, *outs)`.  Fast path: direct launch into
+        `out` (allocated if None).  When gradients flow through the solve (`sdeint` under autograd) the
+        launch becomes an autograd node (autograd_ops.TableauFn)."""
+        if self._autograd and not raw:
+            from .autograd_ops import TableauFn
+            unit = nz is not None and nz is self._feed._unit_ref
+            noise = None
+            if nz is not None and not unit:
+                noise = self._feed.tensors(self._cur_c, self.want_u)
+            return TableauFn.apply(self, name, L is self._L, unit, noise, tuple(scalars), n_out, *ins)
+        if n_out == 1:
+            o = out if out is not None else self._out_like(name, ins)
+            self._launch(name, L, nz, ins, scalars, (o,))
+            return o
+        outs = tuple(self._out_like(name, ins) for _ in range(n_out))
+        self._launch(name, L, nz, ins, scalars, outs)
+        return outs
+
+    def _launch_raw(self, name, use_general, unit, noise, ins, scalars, n_out):
+        """Forward of an autograd node: same kernel, increments taken from the saved tensors."""
+        L = self._L if use_general else self._LU
+        if unit:
+            nz = self._feed.unit()
+        elif noise is not None:
+            nz = self._feed.from_tensors(noise[0], noise[1])
+        else:
+            nz = None
+        ins = [_contig(t) for t in ins]
+        outs = tuple(self._out_like(name, ins) for _ in range(n_out))
+        self._launch(name, L, nz, ins, scalars, outs)
+        return outs
 
     # ------------------------------------------------------------------------------------------
     def _prepare(self, y0):
@@ -202,6 +259,7 @@ class BaseSDESolver(metaclass=abc.ABCMeta):
         self.launch_bm = _cabi.make_launch(self.dtype, _cabi.NOISE_DIAGONAL, self.bm_rows, self.m, self.m, stream)
         self._L = ctypes.byref(self.launch)
         self._LU = ctypes.byref(self.launch_unit)
+        self._LB = ctypes.byref(self.launch_bm)
         self._lib = _cabi.lib()
         self._prepared = True
 
@@ -285,10 +343,11 @@ class BaseSDESolver(metaclass=abc.ABCMeta):
         c = StepContext(self, 0, t0.to(self.device), t1.to(self.device), float(c0), float(c1), float(dt),
                         self.scalars(dt), aux)
         self._feed = NoiseFeed(self, self.bm, None)
-        out = torch.empty_like(y0)
+        self._cur_c = c
+        if self._autograd:
+            return self._step(c, y0, extra0, None)
         with torch.no_grad():
-            extra1 = self._step(c, _contig(y0.detach()), extra0, out)
-        return out, extra1
+            return self._step(c, _contig(y0.detach()), extra0, None)
 
     def integrate(self, y0, ts, extra0):
         """Integrate along trajectory.  Returns ys (T, batch, d) and the final extra state
@@ -296,6 +355,11 @@ class BaseSDESolver(metaclass=abc.ABCMeta):
         if self.adaptive:
             return self._integrate_adaptive(y0, ts, extra0)
         sched = schedule_lib.build_schedule(ts, self.dt)
+        if self._autograd:
+            y0 = _contig(y0)
+            self._prepare(y0)
+            self._feed = NoiseFeed(self, self.bm, self._bind(sched))
+            return self._run_autograd(sched, self._contexts(sched, ts), y0, tuple(extra0))
         y0 = _contig(y0.detach())
         self._prepare(y0)
         binding = self._bind(sched)
@@ -408,8 +472,9 @@ class BaseSDESolver(metaclass=abc.ABCMeta):
                     scratch[flip] = torch.empty_like(ys[0])
                 out = scratch[flip]
                 flip ^= 1
-            extra = self._step(c, curr, extra, out)
-            prev, curr = curr, out
+            self._cur_c = c
+            y1, extra = self._step(c, curr, extra, out)
+            prev, curr = curr, y1
             for o in sched.outputs_after.get(k, ()):
                 if not o.aligned:
                     # interp.py:15-18
@@ -417,3 +482,20 @@ class BaseSDESolver(metaclass=abc.ABCMeta):
                                                              o.w0, o.w1, ys[o.index].data_ptr()),
                                 "tsde_linear_interp")
         return extra
+
+    def _run_autograd(self, sched, ctxs, y0, extra):
+        """Differentiable time loop (plain `sdeint` under autograd): every launch is an autograd node,
+        outputs are collected and stacked like the reference does (base_solver.py:112,147,149)."""
+        self._refresh_stream()
+        ys = [y0]
+        prev = curr = y0
+        for k, c in enumerate(ctxs):
+            self._cur_c = c
+            y1, extra = self._step(c, curr, extra, None)
+            prev, curr = curr, y1
+            for o in sched.outputs_after.get(k, ()):
+                if o.aligned:
+                    ys.append(curr)
+                else:
+                    ys.append(self._k('tsde_linear_interp', self._LU, None, (prev, curr), (o.w0, o.w1), None))
+        return torch.stack(ys, dim=0), extra

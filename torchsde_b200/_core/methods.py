@@ -4,52 +4,43 @@ One class per method of the reference (torchsde/_core/methods/*.py), with the sa
 attributes (strong/weak order, sde_type, noise_types, levy_area_approximations) and the same
 constructor-time errors; ``select`` mirrors methods/__init__.py:26-48.  Each ``_step`` issues the
 user's drift/diffusion calls in the reference's order and replaces the ATen arithmetic of the
-reference's ``step`` by one or two launches through the C ABI (include/torchsde_b200.h).
+reference's ``step`` by one or two launches through the C ABI (include/torchsde_b200.h), issued via
+``self._k(name, L, nz, inputs, scalars, outputs)`` (base_solver.py) — a direct launch on the fast path,
+an autograd node when gradients must flow through the solve.
 """
-import ctypes
-
 import torch
 
 from . import base_solver
 from .base_solver import _contig
-from .. import _cabi
 from ..settings import SDE_TYPES, NOISE_TYPES, LEVY_AREA_APPROXIMATIONS, METHODS, METHOD_OPTIONS
-
-_check = _cabi.check
-
-
-def _p(t):
-    return t.data_ptr()
 
 
 class _ProdMixin:
     """Shared handling of the reference's `f_and_g_prod` / `g_prod` call sites (base_sde.py:51-56)."""
 
-    def _f_and_g_prod(self, c, t, y, out_fn):
-        """Evaluate drift and diffusion at (t, y) the way ForwardSDE.f_and_g_prod would, then call
-        out_fn(L, nz, f, g) where (L, nz, g) are either (general/diag launch, step noise, g) or
-        (unit launch, unit noise, g_prod)."""
+    def _f_and_g_prod(self, c, t, y):
+        """Evaluate drift and diffusion at (t, y) the way ForwardSDE.f_and_g_prod would.  Returns
+        (L, nz, f, g) where (L, nz, g) is either (noise-type launch, step noise, g) or
+        (element-wise launch, unit noise, user-computed g_prod)."""
         sde = self.sde
         mode = sde.f_and_g_prod_mode
         if mode == 'fused':
             f, g = sde.f_and_g(t, y)
-            return out_fn(self._L, self._feed.get(c, self.want_u), _contig(f), _contig(g))
+            return self._L, self._feed.get(c, self.want_u), _contig(f), _contig(g)
         w, _ = self._feed.tensors(c)
         w = w.reshape(self.bm.shape)
         if mode == 'f_and_g_prod':
             f, gp = sde.f_and_g_prod(t, y, w)
         else:
             f, gp = sde.f(t, y), sde.g_prod(t, y, w)
-        return out_fn(self._LU, self._feed.unit(), _contig(f), _contig(gp))
+        return self._LU, self._feed.unit(), _contig(f), _contig(gp)
 
-    def _g_prod(self, c, t, y, out_fn):
+    def _g_prod(self, c, t, y):
         sde = self.sde
         if sde.g_prod_mode == 'fused':
-            g = sde.g(t, y)
-            return out_fn(self._L, self._feed.get(c, self.want_u), _contig(g))
+            return self._L, self._feed.get(c, self.want_u), _contig(sde.g(t, y))
         w, _ = self._feed.tensors(c)
-        gp = sde.g_prod(t, y, w.reshape(self.bm.shape))
-        return out_fn(self._LU, self._feed.unit(), _contig(gp))
+        return self._LU, self._feed.unit(), _contig(sde.g_prod(t, y, w.reshape(self.bm.shape)))
 
 
 class Euler(_ProdMixin, base_solver.BaseSDESolver):
@@ -64,13 +55,8 @@ class Euler(_ProdMixin, base_solver.BaseSDESolver):
         super(Euler, self).__init__(sde=sde, **kwargs)
 
     def _step(self, c, y0, extra0, out):
-        lib = self._lib
-
-        def fin(L, nz, f, g):
-            _check(lib.tsde_step_euler(L, nz, _p(y0), _p(f), _p(g), c.dt, _p(out)), "tsde_step_euler")
-
-        self._f_and_g_prod(c, c.t0, y0, fin)
-        return ()
+        L, nz, f, g = self._f_and_g_prod(c, c.t0, y0)
+        return self._k('tsde_step_euler', L, nz, (y0, f, g), (c.dt,), out), ()
 
 
 class BaseMilstein(_ProdMixin, base_solver.BaseSDESolver):
@@ -102,19 +88,17 @@ class BaseMilstein(_ProdMixin, base_solver.BaseSDESolver):
         return {'sqrt_dt': float(sqrt_dt), 'two_sqrt_dt': float(2 * sqrt_dt)}
 
     def _step(self, c, y0, extra0, out):
-        lib, sde = self._lib, self.sde
+        sde = self.sde
         ito = 1 if self.ito else 0
         if self.options[METHOD_OPTIONS.grad_free]:
             # milstein.py:58-67
             f, g = sde.f_and_g(c.t0, y0)
             f, g = _contig(f), _contig(g)
-            yp = torch.empty_like(y0)
-            _check(lib.tsde_milstein_gf_predict(self._LU, _p(y0), _p(f), _p(g), c.dt, c.scalars['sqrt_dt'], ito,
-                                                _p(yp)), "tsde_milstein_gf_predict")
+            yp = self._k('tsde_milstein_gf_predict', self._LU, None, (y0, f, g), (c.dt, c.scalars['sqrt_dt'], ito),
+                         None)
             g_prime = _contig(sde.g(c.t0, yp))
-            _check(lib.tsde_step_milstein_gf(self._L, self._feed.get(c), _p(y0), _p(f), _p(g), _p(g_prime), c.dt,
-                                             c.scalars['two_sqrt_dt'], ito, _p(out)), "tsde_step_milstein_gf")
-            return ()
+            return self._k('tsde_step_milstein_gf', self._L, self._feed.get(c), (y0, f, g, g_prime),
+                           (c.dt, c.scalars['two_sqrt_dt'], ito), out), ()
         if getattr(sde, 'is_adjoint_sde', False):
             # adjoint SDE: it forms g.v and Milstein's correction itself (adjoint_sde.py:332-377);
             # v2 = 0.5 v is produced by the seed kernel applied to a tensor of ones
@@ -122,40 +106,34 @@ class BaseMilstein(_ProdMixin, base_solver.BaseSDESolver):
             w, _ = self._feed.tensors(c)
             if self._ones is None or self._ones.shape != w.shape:
                 self._ones = torch.ones_like(w)
-            v2 = torch.empty_like(w)
-            _check(lib.tsde_milstein_vjp_seed(ctypes.byref(self.launch_bm), self._feed.from_tensors(w), _p(self._ones),
-                                              c.dt, ito, _p(v2)), "tsde_milstein_vjp_seed")
+            v2 = self._k('tsde_milstein_vjp_seed', self._LB, self._feed.from_tensors(w), (self._ones,), (c.dt, ito),
+                         None, raw=True)
             gp, gdg = sde.g_prod_and_gdg_prod(c.t0, y0, w.reshape(self.bm.shape), v2.reshape(self.bm.shape))
-            _check(lib.tsde_step_milstein(self._LU, self._feed.unit(), _p(y0), _p(f), _p(_contig(gp)),
-                                          _p(_contig(gdg)), c.dt, _p(out)), "tsde_step_milstein")
-            return ()
+            return self._k('tsde_step_milstein', self._LU, self._feed.unit(), (y0, f, _contig(gp), _contig(gdg)),
+                           (c.dt,), out), ()
         if sde.noise_type == NOISE_TYPES.additive:
             f = _contig(sde.f(c.t0, y0))
             # g_prod_and_gdg_prod_additive: (g_prod(t, y, v1), 0.)  base_sde.py:157-158
-            def fin(L, nz, g):
-                _check(lib.tsde_step_euler(L, nz, _p(y0), _p(f), _p(g), c.dt, _p(out)), "tsde_step_euler")
-            self._g_prod(c, c.t0, y0, fin)
-            return ()
+            L, nz, g = self._g_prod(c, c.t0, y0)
+            return self._k('tsde_step_euler', L, nz, (y0, f, g), (c.dt,), out), ()
         f, side = self._drift_async(lambda: _contig(sde.f(c.t0, y0)))
         # g_prod_and_gdg_prod_{diagonal,default}: vjp of g wrt y with grad_outputs g * (0.5 v)
         # base_sde.py:127-155 (always calls self.g, never g_prod)
+        track = self._autograd
         with torch.enable_grad():
-            y = y0.detach().requires_grad_(True)
+            y = y0 if (track and y0.requires_grad) else y0.detach().requires_grad_(True)
             g = sde.g(c.t0, y)
-            gd = _contig(g.detach())
-            go = torch.empty_like(gd)
-            nz = self._feed.get(c)
-            _check(lib.tsde_milstein_vjp_seed(self._L, nz, _p(gd), c.dt, ito, _p(go)), "tsde_milstein_vjp_seed")
+            gd = _contig(g if track else g.detach())
+            go = self._k('tsde_milstein_vjp_seed', self._L, self._feed.get(c), (gd,), (c.dt, ito), None)
             if g.requires_grad:
-                gdg, = torch.autograd.grad(g, y, grad_outputs=go.view_as(g), allow_unused=True)
+                gdg, = torch.autograd.grad(g, y, grad_outputs=go.view_as(g), allow_unused=True,
+                                           retain_graph=track, create_graph=track)
             else:
                 gdg = None
         if gdg is None:
             gdg = torch.zeros_like(y0)
         self._drift_join(f, side)
-        _check(lib.tsde_step_milstein(self._L, self._feed.get(c), _p(y0), _p(f), _p(gd), _p(_contig(gdg)), c.dt,
-                                      _p(out)), "tsde_step_milstein")
-        return ()
+        return self._k('tsde_step_milstein', self._L, self._feed.get(c), (y0, f, gd, _contig(gdg)), (c.dt,), out), ()
 
 
 class MilsteinIto(BaseMilstein):
@@ -180,22 +158,10 @@ class Heun(_ProdMixin, base_solver.BaseSDESolver):
         super(Heun, self).__init__(sde=sde, **kwargs)
 
     def _step(self, c, y0, extra0, out):
-        lib = self._lib
-        yp = torch.empty_like(y0)
-        st = {}
-
-        def first(L, nz, f, g):
-            _check(lib.tsde_step_euler(L, nz, _p(y0), _p(f), _p(g), c.dt, _p(yp)), "tsde_step_euler")
-            st['f'], st['g'] = f, g
-
-        self._f_and_g_prod(c, c.t0, y0, first)
-
-        def second(L, nz, fp, gp):
-            _check(lib.tsde_step_heun(L, nz, _p(y0), _p(st['f']), _p(fp), _p(st['g']), _p(gp), c.dt, _p(out)),
-                   "tsde_step_heun")
-
-        self._f_and_g_prod(c, c.t1, yp, second)
-        return ()
+        L, nz, f, g = self._f_and_g_prod(c, c.t0, y0)
+        yp = self._k('tsde_step_euler', L, nz, (y0, f, g), (c.dt,), None)
+        L, nz, fp, gp = self._f_and_g_prod(c, c.t1, yp)
+        return self._k('tsde_step_heun', L, nz, (y0, f, fp, g, gp), (c.dt,), out), ()
 
 
 class Midpoint(_ProdMixin, base_solver.BaseSDESolver):
@@ -216,20 +182,10 @@ class Midpoint(_ProdMixin, base_solver.BaseSDESolver):
         return {'half_dt': float(0.5 * dt)}
 
     def _step(self, c, y0, extra0, out):
-        lib = self._lib
-        yp = torch.empty_like(y0)
-
-        def first(L, nz, f, g):
-            _check(lib.tsde_midpoint_predict(L, nz, _p(y0), _p(f), _p(g), c.scalars['half_dt'], _p(yp)),
-                   "tsde_midpoint_predict")
-
-        self._f_and_g_prod(c, c.t0, y0, first)
-
-        def second(L, nz, fp, gp):
-            _check(lib.tsde_step_euler(L, nz, _p(y0), _p(fp), _p(gp), c.dt, _p(out)), "tsde_step_euler")
-
-        self._f_and_g_prod(c, c.aux_t[0], yp, second)
-        return ()
+        L, nz, f, g = self._f_and_g_prod(c, c.t0, y0)
+        yp = self._k('tsde_midpoint_predict', L, nz, (y0, f, g), (c.scalars['half_dt'],), None)
+        L, nz, fp, gp = self._f_and_g_prod(c, c.aux_t[0], yp)
+        return self._k('tsde_step_euler', L, nz, (y0, fp, gp), (c.dt,), out), ()
 
 
 class EulerHeun(_ProdMixin, base_solver.BaseSDESolver):
@@ -244,38 +200,25 @@ class EulerHeun(_ProdMixin, base_solver.BaseSDESolver):
         super(EulerHeun, self).__init__(sde=sde, **kwargs)
 
     def _step(self, c, y0, extra0, out):
-        lib = self._lib
-        yp = torch.empty_like(y0)
-        st = {}
-
-        def first(L, nz, f, g):
-            _check(lib.tsde_euler_heun_predict(L, nz, _p(y0), _p(g), _p(yp)), "tsde_euler_heun_predict")
-            st['f'], st['g'], st['unit'] = f, g, L is self._LU
-
-        self._f_and_g_prod(c, c.t0, y0, first)
-
-        def second(L, nz, gp):
-            if (L is self._LU) != st['unit']:
-                raise RuntimeError("torchsde_b200: inconsistent g_prod availability in euler_heun.")
-            _check(lib.tsde_step_euler_heun(L, nz, _p(y0), _p(st['f']), _p(st['g']), _p(gp), c.dt, _p(out)),
-                   "tsde_step_euler_heun")
-
-        if st['unit']:
-            # first product came from the user's (f_and_)g_prod; the reference then calls sde.g_prod
-            sde = self.sde
+        sde = self.sde
+        L, nz, f, g = self._f_and_g_prod(c, c.t0, y0)
+        unit = L is self._LU
+        yp = self._k('tsde_euler_heun_predict', L, nz, (y0, g), (), None)
+        if unit:
+            # first product came from the user's (f_and_)g_prod; the reference then calls sde.g_prod (:38)
             w, _ = self._feed.tensors(c)
             w = w.reshape(self.bm.shape)
             if sde.user_g_prod:
                 gp = sde.g_prod(c.t1, yp, w)
-            else:  # only f_and_g_prod given: reference's g_prod_default needs g -> RuntimeError there too
-                gp = sde.f_and_g_prod(c.t1, yp, w)[1] if not hasattr(sde._base_sde, 'g') else None
-                if gp is None:
-                    raise RuntimeError("torchsde_b200: euler_heun with f_and_g_prod and g but no g_prod is "
-                                       "not supported; provide g_prod or only f/g.")
-            second(self._LU, self._feed.unit(), _contig(gp))
+            elif not hasattr(sde._base_sde, 'g'):
+                gp = sde.f_and_g_prod(c.t1, yp, w)[1]
+            else:
+                raise RuntimeError("torchsde_b200: euler_heun with f_and_g_prod and g but no g_prod is "
+                                   "not supported; provide g_prod or only f/g.")
+            L2, nz2, gp = self._LU, self._feed.unit(), _contig(gp)
         else:
-            self._g_prod(c, c.t1, yp, second)
-        return ()
+            L2, nz2, gp = self._g_prod(c, c.t1, yp)
+        return self._k('tsde_step_euler_heun', L2, nz2, (y0, f, g, gp), (c.dt,), out), ()
 
 
 class ReversibleHeun(base_solver.BaseSDESolver):
@@ -296,16 +239,13 @@ class ReversibleHeun(base_solver.BaseSDESolver):
         return self.sde.f_and_g(t0, y0) + (y0,)
 
     def _step(self, c, y0, extra0, out):
-        lib = self._lib
         f0, g0, z0 = (_contig(x) for x in extra0)
-        z1 = torch.empty_like(y0)
-        _check(lib.tsde_reversible_heun_z(self._L, self._feed.get(c), _p(y0), _p(z0), _p(f0), _p(g0), c.dt, _p(z1)),
-               "tsde_reversible_heun_z")
+        z1 = self._k('tsde_reversible_heun_z', self._L, self._feed.get(c), (y0, z0, f0, g0), (c.dt,), None)
         f1, g1 = self.sde.f_and_g(c.t1, z1)
         f1, g1 = _contig(f1), _contig(g1)
-        _check(lib.tsde_step_reversible_heun(self._L, self._feed.get(c), _p(y0), _p(f0), _p(f1), _p(g0), _p(g1),
-                                             c.scalars['half_dt'], _p(out)), "tsde_step_reversible_heun")
-        return f1, g1, z1
+        y1 = self._k('tsde_step_reversible_heun', self._L, self._feed.get(c), (y0, f0, f1, g0, g1),
+                     (c.scalars['half_dt'],), out)
+        return y1, (f1, g1, z1)
 
 
 class SRK(base_solver.BaseSDESolver):
@@ -338,59 +278,47 @@ class SRK(base_solver.BaseSDESolver):
         return {'rdt': float(1 / dt), 'sqrt_dt': float(dt.sqrt()), 'three_dt': float(3 * dt)}
 
     def _step(self, c, y0, extra0, out):
+        if self.sde.user_g_prod:
+            raise NotImplementedError("torchsde_b200: srk with a user-supplied g_prod is not supported; "
+                                      "provide g (the fused kernel performs the product).")
         if self._additive:
-            return self._additive_step(c, y0, out)
-        return self._diagonal_or_scalar_step(c, y0, out)
+            return self._additive_step(c, y0, out), ()
+        return self._diagonal_or_scalar_step(c, y0, out), ()
 
     def _diagonal_or_scalar_step(self, c, y0, out):
         """srk.py:57-88.  Distinct evaluations only: f0,g0 at (t0,y0); f1 at (t0+dt, H0_1);
         g1 at (t0+dt/4, H1_1); f2 at (t0+dt/2, H0_2); g2 at (t0+dt, H1_2); g3 at (t0+dt/4, H1_3)."""
-        lib, sde, s = self._lib, self.sde, c.scalars
-        if sde.user_g_prod:
-            raise NotImplementedError("torchsde_b200: srk with a user-supplied g_prod is not supported; "
-                                      "provide g (the fused kernel performs the product).")
+        sde, s = self.sde, c.scalars
         t_00, t_1, t_q, t_h = c.aux_t  # t0 + 0*dt, t0 + dt, t0 + dt/4, t0 + dt/2
-        LU = self._LU
+        LU, L = self._LU, self._L
         f0 = _contig(sde.f(t_00, y0))
         g0 = _contig(sde.g(t_00, y0))
-        h0_1, h1_1 = torch.empty_like(y0), torch.empty_like(y0)
-        _check(lib.tsde_srk_diag_stage1(LU, _p(y0), _p(f0), _p(g0), c.dt, s['sqrt_dt'], _p(h0_1), _p(h1_1)),
-               "tsde_srk_diag_stage1")
+        h0_1, h1_1 = self._k('tsde_srk_diag_stage1', LU, None, (y0, f0, g0), (c.dt, s['sqrt_dt']), None, n_out=2)
         f1 = _contig(sde.f(t_1, h0_1))
         g1 = _contig(sde.g(t_q, h1_1))
-        h0_2, h1_2 = torch.empty_like(y0), torch.empty_like(y0)
-        _check(lib.tsde_srk_diag_stage2(self._L, self._feed.get(c, True), _p(y0), _p(f0), _p(g0), _p(f1), _p(g1),
-                                        c.dt, s['rdt'], s['sqrt_dt'], _p(h0_2), _p(h1_2)), "tsde_srk_diag_stage2")
+        h0_2, h1_2 = self._k('tsde_srk_diag_stage2', L, self._feed.get(c, True), (y0, f0, g0, f1, g1),
+                             (c.dt, s['rdt'], s['sqrt_dt']), None, n_out=2)
         f2 = _contig(sde.f(t_h, h0_2))
         g2 = _contig(sde.g(t_1, h1_2))
-        h1_3 = torch.empty_like(y0)
-        _check(lib.tsde_srk_diag_stage3(LU, _p(y0), _p(g0), _p(g1), _p(f2), _p(g2), c.dt, s['sqrt_dt'], _p(h1_3)),
-               "tsde_srk_diag_stage3")
+        h1_3 = self._k('tsde_srk_diag_stage3', LU, None, (y0, g0, g1, f2, g2), (c.dt, s['sqrt_dt']), None)
         g3 = _contig(sde.g(t_q, h1_3))
-        _check(lib.tsde_step_srk_diag(self._L, self._feed.get(c, True), _p(y0), _p(f0), _p(f1), _p(f2), _p(g0),
-                                      _p(g1), _p(g2), _p(g3), c.dt, s['rdt'], s['sqrt_dt'], s['three_dt'],
-                                      _p(out)), "tsde_step_srk_diag")
-        return ()
+        return self._k('tsde_step_srk_diag', L, self._feed.get(c, True), (y0, f0, f1, f2, g0, g1, g2, g3),
+                       (c.dt, s['rdt'], s['sqrt_dt'], s['three_dt']), out)
 
     def _additive_step(self, c, y0, out):
         """srk.py:90-111: f0 = f(t0, y0); gA = g(t0+dt, y0); f1 = f(t0+3/4dt, H0_1); gB = g(t0, y0)."""
-        lib, sde, s = self._lib, self.sde, c.scalars
-        if sde.user_g_prod:
-            raise NotImplementedError("torchsde_b200: srk with a user-supplied g_prod is not supported; "
-                                      "provide g (the fused kernel performs the product).")
+        sde, s = self.sde, c.scalars
+        if self.m == 1:
+            raise NotImplementedError("torchsde_b200: additive srk needs m > 1 (use noise_type='scalar' for m == 1).")
         t_1, t_34, t_00 = c.aux_t
         f0 = _contig(sde.f(t_00, y0))
         ga = _contig(sde.g(t_1, y0))
-        h0_1 = torch.empty_like(y0)
-        if self.m == 1:
-            raise NotImplementedError("torchsde_b200: additive srk needs m > 1 (use noise_type='scalar' for m == 1).")
-        _check(lib.tsde_srk_additive_stage(self._L, self._feed.get(c, True), _p(y0), _p(f0), _p(ga), c.dt, s['rdt'],
-                                           _p(h0_1)), "tsde_srk_additive_stage")
+        h0_1 = self._k('tsde_srk_additive_stage', self._L, self._feed.get(c, True), (y0, f0, ga), (c.dt, s['rdt']),
+                       None)
         f1 = _contig(sde.f(t_34, h0_1))
         gb = _contig(sde.g(t_00, y0))
-        _check(lib.tsde_step_srk_additive(self._L, self._feed.get(c, True), _p(y0), _p(f0), _p(f1), _p(ga), _p(gb),
-                                          c.dt, s['rdt'], _p(out)), "tsde_step_srk_additive")
-        return ()
+        return self._k('tsde_step_srk_additive', self._L, self._feed.get(c, True), (y0, f0, f1, ga, gb),
+                       (c.dt, s['rdt']), out)
 
 
 class LogODEMidpoint(_ProdMixin, base_solver.BaseSDESolver):
@@ -419,43 +347,31 @@ class LogODEMidpoint(_ProdMixin, base_solver.BaseSDESolver):
 
     def _dg_ga_jvp_column_sum(self, t, y, a):
         """base_sde.py:165-185 (v1); zero for non-general noise (:71,205-206)."""
-        if self.sde.noise_type != NOISE_TYPES.general:
-            return None
         from .adjoint_sde import _jvp
+        track = self._autograd
         with torch.enable_grad():
-            y = y.detach().requires_grad_(True)
+            y = y if (track and y.requires_grad) else y.detach().requires_grad_(True)
             g = self.sde.g(t, y)
             ga = torch.bmm(g, a)
             total = None
             for col in range(g.size(-1)):
-                term = _jvp(g[..., col], y, ga[..., col])
+                term = _jvp(g[..., col], y, ga[..., col], create_graph=track)
                 total = term if total is None else total + term
-        return total.detach()
+        return total if track else total.detach()
 
     def _step(self, c, y0, extra0, out):
-        lib = self._lib
         W, A = self.bm(c.ft0, c.ft1, return_A=True)
-        W = _contig(W)
-        self._feed._cached = (c, W, None)  # the products below reuse this increment
-        yp = torch.empty_like(y0)
-
-        def first(L, nz, f, g):
-            _check(lib.tsde_midpoint_predict(L, nz, _p(y0), _p(f), _p(g), c.scalars['half_dt'], _p(yp)),
-                   "tsde_midpoint_predict")
-
-        self._f_and_g_prod(c, c.t0, y0, first)
+        self._feed.prime(c, _contig(W))  # the products below reuse this increment
+        L, nz, f, g = self._f_and_g_prod(c, c.t0, y0)
+        yp = self._k('tsde_midpoint_predict', L, nz, (y0, f, g), (c.scalars['half_dt'],), None)
+        L, nz, fp, gp = self._f_and_g_prod(c, c.aux_t[0], yp)
         general = self.sde.noise_type == NOISE_TYPES.general
-        tmp = torch.empty_like(y0) if general else out
-
-        def second(L, nz, fp, gp):
-            _check(lib.tsde_step_euler(L, nz, _p(y0), _p(fp), _p(gp), c.dt, _p(tmp)), "tsde_step_euler")
-
-        self._f_and_g_prod(c, c.aux_t[0], yp, second)
-        if general:
-            dg_ga = _contig(self._dg_ga_jvp_column_sum(c.aux_t[0], yp, A))
-            # y1 = (y0 + dt*f' + g'.dW) + dg_ga                                         log_ode.py:54
-            _check(lib.tsde_linear_interp(self._LU, _p(tmp), _p(dg_ga), 1.0, 1.0, _p(out)), "tsde_linear_interp")
-        return ()
+        tmp = self._k('tsde_step_euler', L, nz, (y0, fp, gp), (c.dt,), None if general else out)
+        if not general:
+            return tmp, ()
+        dg_ga = _contig(self._dg_ga_jvp_column_sum(c.aux_t[0], yp, A))
+        # y1 = (y0 + dt*f' + g'.dW) + dg_ga                                             log_ode.py:54
+        return self._k('tsde_linear_interp', self._LU, None, (tmp, dg_ga), (1.0, 1.0), out), ()
 
 
 def select(method, sde_type):

@@ -6,8 +6,9 @@ Signature, defaults, validation errors and return conventions follow the referen
 
 Known differences, by design:
 * tensors must live on a CUDA device (there is no CPU path);
-* gradients do not flow through `sdeint` (the tableau kernels are not autograd nodes);
-  use `sdeint_adjoint` for training, as the reference recommends for memory reasons anyway;
+* gradients flow through `sdeint` (each tableau launch is an autograd node, autograd_ops.py) when autograd
+  is enabled and y0 / the SDE's parameters require grad; that path is an eager loop with materialised
+  increments — wrap inference in `torch.no_grad()` (or use `sdeint_adjoint`) to get the fused fast path;
 * `adaptive=True` runs the reference's controller as an eager loop (data-dependent step sizes cannot be
   graph-captured); every proposal still uses the fused kernels.
 """
@@ -55,11 +56,27 @@ def sdeint(sde, y0, ts, bm=None, method=None, dt=1e-3, adaptive=False, rtol=1e-5
     solver = solver_fn(sde=sde, bm=bm, dt=dt, adaptive=adaptive, rtol=rtol, atol=atol, dt_min=dt_min,
                        options=options)
     _cabi.require_cuda(y0)
+    if _needs_autograd(sde, y0, extra_solver_state) and not adaptive:
+        # gradients must flow through the solve: every tableau launch becomes an autograd node
+        # (autograd_ops.py); eager loop, increments materialised (memory O(T), like the reference).
+        solver._autograd = True
+        if extra_solver_state is None:
+            extra_solver_state = solver.init_extra_solver_state(ts[0], y0)
+        ys, extra_solver_state = solver.integrate(y0, ts, extra_solver_state)
+        return parse_return(y0, ys, extra_solver_state, extra, logqp)
     with torch.no_grad():
         if extra_solver_state is None:
             extra_solver_state = solver.init_extra_solver_state(ts[0], y0)
         ys, extra_solver_state = _integrate(solver, y0, ts, extra_solver_state, options)
     return parse_return(y0, ys, extra_solver_state, extra, logqp)
+
+
+def _needs_autograd(sde, y0, extra_solver_state):
+    if not torch.is_grad_enabled():
+        return False
+    if y0.requires_grad or any(p.requires_grad for p in sde.parameters()):
+        return True
+    return any(torch.is_tensor(e) and e.requires_grad for e in (extra_solver_state or ()))
 
 
 def _integrate(solver, y0, ts, extra_solver_state, options):
