@@ -337,8 +337,10 @@ def tableau_roofline(w, sde, dev):
     side.wait_stream(torch.cuda.current_stream(dev))
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph):
+        L.stream = torch.cuda.current_stream(dev).cuda_stream  # launch on the capturing stream
         for s_ in sets:
             launch(s_)
+    L.stream = torch.cuda.current_stream(dev).cuda_stream
     graph.replay()
     torch.cuda.synchronize(dev)
     times = []
