@@ -43,6 +43,10 @@ WORKLOADS = {
                                dt=2.0 ** -10, E_bytes_per_traj_step=(6 * 32 + 2 * 32 * 16) * 4),
     'cfg3_heun_general': dict(method='heun', sde_type='stratonovich', kind='general', B=8192, D=32, M=16, T=500,
                               dt=2.0 ** -10, E_bytes_per_traj_step=2 * (6 * 32 + 2 * 32 * 16) * 4),
+    # cfg2 with per-trajectory parameters (mu, sigma of shape (B, D)): f/g/vjp are contiguous element-wise
+    # products, i.e. PyTorch's vectorised kernels instead of its broadcasting ones.  E = 7 (solver) + 3*3 = 16 D s.
+    'cfg2_pertraj': dict(method='milstein', sde_type='ito', kind='gbm_pertraj', B=65536, D=64, M=64, T=1000,
+                         dt=2.0 ** -10, E_bytes_per_traj_step=16 * 64 * 4, S_tableau_bytes_per_traj_step=5 * 64 * 4),
     # other diagonal tableaus at the cfg2 size
     'cfg2_euler': dict(method='euler', sde_type='ito', kind='gbm', B=65536, D=64, M=64, T=200, dt=2.0 ** -10,
                        E_bytes_per_traj_step=8 * 64 * 4),
@@ -117,6 +121,8 @@ def build_sde(w, device, dtype=torch.float32):
     kind = w.get('kind', 'gbm')
     if kind == 'gbm':
         sde = problems.GBMDiagonal(w['D'], w['sde_type'], seed=1147481649 % 1000, dtype=dtype)
+    elif kind == 'gbm_pertraj':
+        sde = problems.GBMPerTrajectory(w['B'], w['D'], w['sde_type'], seed=649, dtype=dtype)
     else:
         sde = problems.make(kind, w['D'], w['M'], w['sde_type'], dtype=dtype, seed=649)
     return sde.to(device)
@@ -209,9 +215,11 @@ def run_ours(args, w, rank, world, local_rank):
     opts = {'cuda_graph': not args.no_graph}
     if args.row_split > 1:
         opts['row_split'] = args.row_split
+    if args.drift_overlap:
+        opts['drift_overlap'] = args.drift_overlap
     row_offset = rank * B  # weak scaling: every rank integrates its own B trajectories of one global batch
 
-    M = D if w.get('kind', 'gbm') == 'gbm' else w['M']
+    M = D if w.get('kind', 'gbm').startswith('gbm') else w['M']
     opts.update(w.get('options', {}))
 
     def solve(y0, entropy):
@@ -266,7 +274,8 @@ def run_ours(args, w, rank, world, local_rank):
     e2e_value = total_traj_steps / e2e_elapsed
 
     # ---- roofline of the dominant kernel (the fused Milstein tableau), timed in situ ----
-    headline = args.workload.startswith('cfg2') and w['method'] == 'milstein' and not w.get('options')
+    headline = args.workload.startswith('cfg2') and w['method'] == 'milstein' and not w.get('options') \
+        and w.get('kind', 'gbm') == 'gbm'
     roof = tableau_roofline(w, sde, dev) if (rank == 0 and headline) else None
     if rank != 0:
         return
@@ -369,6 +378,7 @@ def main():
     ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--row-split', type=int, default=1)
+    ap.add_argument('--drift-overlap', default=None)
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     rank = int(os.environ.get('RANK', '0'))

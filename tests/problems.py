@@ -38,6 +38,28 @@ class GBMDiagonal(nn.Module):
         return self.sigma * y
 
 
+class GBMPerTrajectory(nn.Module):
+    """GBM whose drift/volatility differ per trajectory (parameter sweeps, heterogeneous ensembles):
+    mu, sigma are (B, d) tensors, so f and g are contiguous element-wise products — the case in which
+    PyTorch uses its vectorised element-wise kernel instead of the (3x slower) broadcasting one."""
+    noise_type = 'diagonal'
+
+    def __init__(self, batch, d, sde_type='ito', seed=0, dtype=torch.float32):
+        super().__init__()
+        self.sde_type = sde_type
+        g = _gen(seed)
+        sigma = torch.sigmoid(torch.randn(batch, d, generator=g, dtype=torch.float64))
+        mu = -sigma ** 2 - torch.sigmoid(torch.randn(batch, d, generator=g, dtype=torch.float64))
+        self.mu = nn.Parameter(mu.to(dtype))
+        self.sigma = nn.Parameter(sigma.to(dtype))
+
+    def f(self, t, y):
+        return self.mu * y
+
+    def g(self, t, y):
+        return self.sigma * y
+
+
 class CosScalar(nn.Module):
     """Scalar noise (m = 1): g = (p cos^2 y)[..., None]."""
     noise_type = 'scalar'
