@@ -317,7 +317,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 levy_area_smem_kernel(const void* keyp, int64_t row_offset, uint64_t a_id, int64_t rows, int m, int rb,
                       const T* __restrict__ w, const T* __restrict__ hh, T tenth_h, T davie_std, int foster,
-                      T* __restrict__ out) {
+                      T* __restrict__ out, int mshift /* log2(m) or -1 */) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int mm = m * m, ld = m + 1, per_row = m * ld;
   T* sn = reinterpret_cast<T*>(smem_raw);          // [rb][m][m+1]
@@ -334,7 +334,9 @@ levy_area_smem_kernel(const void* keyp, int64_t row_offset, uint64_t a_id, int64
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int ij = 4 * q + k;
-      if (ij < mm) sn[r * per_row + (ij / m) * ld + (ij % m)] = n4[k];
+      const int i2 = mshift >= 0 ? (ij >> mshift) : (ij / m);
+      const int j2 = mshift >= 0 ? (ij & (m - 1)) : (ij - i2 * m);
+      if (ij < mm) sn[r * per_row + i2 * ld + j2] = n4[k];
     }
   }
   for (int i = threadIdx.x; i < nrows * m; i += kThreads) {
@@ -344,9 +346,18 @@ levy_area_smem_kernel(const void* keyp, int64_t row_offset, uint64_t a_id, int64
   __syncthreads();
   const int total = nrows * mm;
   for (int e = threadIdx.x; e < total; e += kThreads) {
-    const int r = e / mm;
-    const int ij = e - r * mm;
-    const int i = ij / m, j = ij - i * m;
+    int r, ij, i, j;
+    if (mshift >= 0) {
+      r = e >> (2 * mshift);
+      ij = e & (mm - 1);
+      i = ij >> mshift;
+      j = ij & (m - 1);
+    } else {
+      r = e / mm;
+      ij = e - r * mm;
+      i = ij / m;
+      j = ij - i * m;
+    }
     const T wi = sw[r * m + i], wj = sw[r * m + j], hi = sh[r * m + i], hj = sh[r * m + j];
     const T noise = sn[r * per_row + i * ld + j] - sn[r * per_row + j * ld + i];
     const T a = hi * wj - wi * hj;
@@ -391,10 +402,12 @@ static int levy_impl(const tsde_launch* L, const void* key, int64_t row_offset, 
     if (rb > 32) rb = 32;
     while (rb > 1 && (L->rows + rb - 1) / rb < 2 * (int64_t)sm_count()) rb >>= 1;
     const int64_t blocks = (L->rows + rb - 1) / rb;
+    int mshift = -1;
+    if ((m & (m - 1)) == 0) { mshift = 0; while ((1ll << mshift) < m) ++mshift; }
     if (blocks <= 0x7fffffffll) {
       levy_area_smem_kernel<T><<<(unsigned)blocks, kThreads, rb * per_row, st>>>(
           key, row_offset, a_id, L->rows, (int)m, (int)rb, (const T*)w, (const T*)hh, (T)(0.1 * h),
-          (T)sqrt(r12 * h * h), foster, (T*)out_a);
+          (T)sqrt(r12 * h * h), foster, (T*)out_a, mshift);
       return (int)cudaGetLastError();
     }
   }
