@@ -374,3 +374,21 @@ def test_row_split_graph_is_bit_identical():
         bm = tsde.BrownianInterval(0.0, 0.5, size=(B, d), dtype=torch.float32, device=dev, entropy=21)
         outs.append(tsde.sdeint(sde, y0, ts, bm=bm, method='milstein', dt=2.0 ** -4, options=opts).clone())
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
+@pytest.mark.parametrize('d,m', [(33, 4), (64, 16), (40, 8), (128, 32), (5, 128)])
+def test_general_kernel_shapes_vs_oracle(d, m):
+    """General-noise fused GEMV tile across row lengths that take the row-major sweep (d*m/4 >= 128,
+    including lengths that are not a multiple of the warp size) and the flat sweep."""
+    tsde = _tsde()
+    dev = torch.device('cuda')
+    B = 19
+    sde = problems.TanhGeneral(d, m, 'stratonovich', seed=5, dtype=torch.float64).to(dev)
+    sde_cpu = problems.TanhGeneral(d, m, 'stratonovich', seed=5, dtype=torch.float64)
+    y0 = torch.full((B, d), 0.25, dtype=torch.float64)
+    ts = np.array([0.0, 0.125, 0.25])
+    bm = tsde.BrownianInterval(0.0, 0.25, size=(B, m), dtype=torch.float64, device=dev, entropy=77)
+    ys = tsde.sdeint(sde, y0.to(dev), torch.from_numpy(ts).to(dev), bm=bm, method='heun', dt=2.0 ** -4)
+    ref, _ = solvers.make('heun', problems.NumpySDE(sde_cpu), _oracle_bm_from(bm, B, m, np.float64, False),
+                          2.0 ** -4).integrate(y0.numpy(), ts)
+    np.testing.assert_allclose(ys.cpu().numpy(), ref, rtol=1e-11, atol=1e-12)

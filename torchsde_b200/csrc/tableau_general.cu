@@ -194,7 +194,6 @@ gen_cta_kernel(const GenP<Op::NE, Op::NG, Op::NO> p, const NoiseP<T> nz, const O
     st4(sw + r * m + 4 * q, w);
     if (Op::WANT_U) st4(su + r * m + 4 * q, u);
   }
-  // issue the first batch of g loads before waiting for the increments
   const int total = nrows * per_row;
   for (int c0 = 0; c0 < total; c0 += kGenThreads * kGenUnroll) {
     T gv[kGenUnroll][NG][4];
@@ -242,9 +241,12 @@ gen_cta_kernel(const GenP<Op::NE, Op::NG, Op::NO> p, const NoiseP<T> nz, const O
         for (int k = 0; k < NP; ++k)
           part[k] = part[k] + op.gval(k, gj) * op.weight(k, w4[j], Op::WANT_U ? u4[j] : T(0));
       }
-      for (int off = 1; off < mq; off <<= 1) {
 #pragma unroll
-        for (int k = 0; k < NP; ++k) part[k] = part[k] + __shfl_xor_sync(0xffffffffu, part[k], off);
+      for (int off = 1; off < 32; off <<= 1) {
+        if (off < mq) {  // uniform
+#pragma unroll
+          for (int k = 0; k < NP; ++k) part[k] = part[k] + __shfl_xor_sync(0xffffffffu, part[k], off);
+        }
       }
       if (valid[un] && mcs[un] == 0) {
         T e[NE > 0 ? NE : 1], o[NO];
