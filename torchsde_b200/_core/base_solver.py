@@ -269,8 +269,8 @@ class BaseSDESolver(metaclass=abc.ABCMeta):
     # latency-bound element-wise kernels of the user's f overlap with the g chain instead of
     # queueing behind it.  Evaluation *order* of f and g is not observable for pure callables.
     def _drift_async(self, fn):
-        if not self.options.get('overlap_drift', True):
-            return fn(), None
+        if self._autograd or not self.options.get('overlap_drift', True):
+            return fn(), None  # (under autograd keep one stream: AccumulateGrad nodes remember theirs)
         main = torch.cuda.current_stream(self.device)
         side = self._side_stream
         if side is None:
