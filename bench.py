@@ -380,7 +380,9 @@ def main():
     ap.add_argument('--row-split', type=int, default=1)
     ap.add_argument('--drift-overlap', default=None)
     args = ap.parse_args()
-    w = WORKLOADS[args.workload]
+    w = dict(WORKLOADS[args.workload])
+    if os.environ.get('TSDE_BENCH_B'):  # experiments only: override the batch size
+        w['B'] = int(os.environ['TSDE_BENCH_B'])
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))

@@ -10,6 +10,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/torchsde_b200.h"
 #include "philox.cuh"
@@ -19,6 +20,15 @@ namespace tsde {
 constexpr int kThreads = 256;
 constexpr int kSMs = 148;        // B200
 constexpr int kBlocksPerSM = 8;  // 2048 threads / SM
+
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TSDE_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 
 inline int sm_count() {
   static int n = 0;
@@ -277,7 +287,15 @@ ew_fast_kernel(const EwP<Op::NIN, Op::NOUT> p, const NoiseP<T> nz, const Op op) 
   const uint32_t q_end = (uint32_t)(((uint64_t)nquads * (blockIdx.x + 1)) / gridDim.x);
   const uint32_t qshift = (uint32_t)p.qshift, qmask = (1u << qshift) - 1u;
   const uint32_t row_off = (uint32_t)nz.row_offset;
-  for (uint32_t Q = q_begin + threadIdx.x; Q < q_end; Q += kThreads) {
+  // Programmatic dependent launch: this grid may start while its predecessor in the stream/graph is
+  // still draining.  Everything that does not touch the predecessor's outputs — the Philox/Box-Muller
+  // work of the thread's first quad — runs before `griddepcontrol.wait`; all loads and stores come after.
+  T w0[4], u0[4];
+  const uint32_t Q0 = q_begin + threadIdx.x;
+  if (Op::USES_NOISE && SRC == TSDE_SRC_COUNTER && Q0 < q_end)
+    counter_noise<T, Op::WANT_U, false>(nz, key, (Q0 >> qshift) + row_off, Q0 & qmask, w0, u0);
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  for (uint32_t Q = Q0; Q < q_end; Q += kThreads) {
     const size_t base = (size_t)Q * 4;  // d == 4 * qpr: quads are laid out contiguously
     T in[NIN > 0 ? NIN : 1][4];
 #pragma unroll
@@ -285,7 +303,12 @@ ew_fast_kernel(const EwP<Op::NIN, Op::NOUT> p, const NoiseP<T> nz, const Op op) 
     T w[4], u[4];
     if (Op::USES_NOISE) {
       if (SRC == TSDE_SRC_COUNTER) {
-        counter_noise<T, Op::WANT_U, false>(nz, key, (Q >> qshift) + row_off, Q & qmask, w, u);
+        if (Q == Q0) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { w[j] = w0[j]; u[j] = Op::WANT_U ? u0[j] : T(0); }
+        } else {
+          counter_noise<T, Op::WANT_U, false>(nz, key, (Q >> qshift) + row_off, Q & qmask, w, u);
+        }
       } else if (SRC == TSDE_SRC_MEMORY) {
         ld4(nz.w + base, w);
         if (Op::WANT_U) ld4(nz.u + base, u);
@@ -377,6 +400,7 @@ inline int launch_ew(const tsde_launch* L, const tsde_noise* nz, bool bcast,
   }
   p.small = p.nquads < (1ll << 31) ? 1 : 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(L->stream);
+  bool pdl = false;
   auto go = [&](auto kernel) -> int {
     // Persistent, balanced grid: one wave of resident CTAs, each owning an equal contiguous slice.
     static int resident = 0;  // CTAs per SM of this instantiation (queried once)
@@ -388,11 +412,25 @@ inline int launch_ew(const tsde_launch* L, const tsde_noise* nz, bool bcast,
     const int64_t cap = (int64_t)sm_count() * resident;
     int64_t blocks = (p.nquads + kThreads - 1) / kThreads;  // small problems: one quad per thread
     if (blocks > cap) blocks = cap;                          // large: one resident wave, sliced evenly
+    if (pdl) {
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3((unsigned)blocks);
+      cfg.blockDim = dim3(kThreads);
+      cfg.dynamicSmemBytes = 0;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      return (int)cudaLaunchKernelEx(&cfg, kernel, p, np, op);
+    }
     kernel<<<(unsigned)blocks, kThreads, 0, st>>>(p, np, op);
     return (int)cudaGetLastError();
   };
   const bool fast = p.vec && !bcast && p.qshift >= 0 && p.small && np.n_cells == 1 &&
                     (L->rows + (nz ? nz->row_offset : 0)) < 0xFFFFFFFFll;
+  pdl = fast && pdl_enabled();
   if constexpr (!Op::USES_NOISE) {
     if (fast) return go(ew_fast_kernel<T, Op, TSDE_SRC_UNIT>);
     return go(ew_kernel<T, Op, TSDE_SRC_UNIT>);

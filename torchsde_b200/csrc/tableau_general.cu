@@ -178,6 +178,10 @@ gen_cta_kernel(const GenP<Op::NE, Op::NG, Op::NO> p, const NoiseP<T> nz, const O
   const int per_row = (int)p.d * mq;
   const int64_t row0 = (int64_t)blockIdx.x * rw;
   const int nrows = (int)((p.rows - row0) < rw ? (p.rows - row0) : rw);
+  // Programmatic dependent launch: the counter-based increments do not depend on the predecessor
+  // kernel's outputs, so they are produced before `griddepcontrol.wait`; user-supplied increments
+  // (MEMORY source) and all of g / e are read after it.
+  if (SRC == TSDE_SRC_MEMORY) asm volatile("griddepcontrol.wait;" ::: "memory");
   // phase 1: increments of the group's rows (<= 32 quads)
   if (tid < nrows * mq) {
     Key key{0u, 0u};
@@ -194,6 +198,7 @@ gen_cta_kernel(const GenP<Op::NE, Op::NG, Op::NO> p, const NoiseP<T> nz, const O
     st4(sw + r * m + 4 * q, w);
     if (Op::WANT_U) st4(su + r * m + 4 * q, u);
   }
+  if (SRC != TSDE_SRC_MEMORY) asm volatile("griddepcontrol.wait;" ::: "memory");
   const int total = nrows * per_row;
   for (int c0 = 0; c0 < total; c0 += kGenThreads * kGenUnroll) {
     T gv[kGenUnroll][NG][4];
@@ -293,12 +298,19 @@ static int launch_gen(const tsde_launch* L, const tsde_noise* nz,
     const int64_t ngroups = (L->rows + rw - 1) / rw;
     if (ngroups > 0x7fffffffll) return TSDE_EINVAL;
     const size_t smem = (size_t)rw * L->m * sizeof(T) * (Op::WANT_U ? 2 : 1);
-    if (nz->source == TSDE_SRC_MEMORY) {
-      gen_cta_kernel<T, Op, TSDE_SRC_MEMORY><<<(unsigned)ngroups, kGenThreads, smem, st>>>(p, np, op);
-    } else {
-      gen_cta_kernel<T, Op, TSDE_SRC_COUNTER><<<(unsigned)ngroups, kGenThreads, smem, st>>>(p, np, op);
-    }
-    return (int)cudaGetLastError();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)ngroups);
+    cfg.blockDim = dim3(kGenThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (nz->source == TSDE_SRC_MEMORY)
+      return (int)cudaLaunchKernelEx(&cfg, gen_cta_kernel<T, Op, TSDE_SRC_MEMORY>, p, np, op);
+    return (int)cudaLaunchKernelEx(&cfg, gen_cta_kernel<T, Op, TSDE_SRC_COUNTER>, p, np, op);
   }
   // generic path: rows per block ~16 work items per thread, bounded by shared memory for the increments
   const int64_t per_row = L->d;
