@@ -234,7 +234,7 @@ def _backward_plan(engine, ys, ts, extras):
     with torch.cuda.graph(g):
         plan.out = engine.sweep(plan.ys, plan.grad_ys, plan.extras, plan.grad_extras, alias_names=names)
     plan.graph = g
-    plans[key] = plan
+    graph_mod._remember(plans, key, plan)
     return plan
 
 

@@ -29,6 +29,13 @@ from . import schedule as schedule_lib
 from .._brownian import BrownianInterval, ReverseBrownian
 
 _PLANS = weakref.WeakKeyDictionary()
+MAX_PLANS_PER_SDE = 4  # every plan owns its output series (T x B x D): keep the cache small
+
+
+def _remember(plans, key, plan):
+    while len(plans) >= MAX_PLANS_PER_SDE:
+        plans.pop(next(iter(plans)))  # oldest first (dicts keep insertion order)
+    plans[key] = plan
 
 
 class _Plan:
@@ -64,7 +71,7 @@ def integrate_captured(solver, y0, ts, extra0):
     plan = plans.get(key)
     if plan is None:
         plan = _capture(solver, sched, binding, y0, ts, extra0)
-        plans[key] = plan
+        _remember(plans, key, plan)
     plan.y0.copy_(y0)
     plan.key.copy_(binding.interval.key_tensor())
     for dst, src in zip(plan.extra_in, extra0):
@@ -203,7 +210,7 @@ def _integrate_captured_split(solver, y0, ts):
         with torch.no_grad(), torch.cuda.graph(graph):
             body()
         plan.graph = graph
-        plans[key] = plan
+        _remember(plans, key, plan)
     plan.y0.copy_(y0)
     plan.key.copy_(binding.interval.key_tensor())
     plan.graph.replay()
