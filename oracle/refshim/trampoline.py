@@ -3,7 +3,6 @@ not installed in this image and cannot be downloaded.  Used ONLY by tests/golden
 import the reference here; semantics per its usage in torchsde/_brownian/brownian_interval.py:183-315:
 run a generator; a yielded generator is run and its return value sent back; `raise TailCall(g)`
 replaces the current frame by g."""
-import types
 class TailCall(Exception):
     def __init__(self, gen): self.gen = gen
 def trampoline(gen):

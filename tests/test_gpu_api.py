@@ -1,6 +1,4 @@
 """API-surface behaviour of sdeint on the GPU (reference sdeint.py:27-112 argument handling)."""
-import warnings
-
 import pytest
 import torch
 

@@ -11,7 +11,6 @@ import torch
 from scipy import stats
 
 from oracle import brownian as obm
-from oracle import philox
 from . import helpers
 
 pytestmark = pytest.mark.gpu

@@ -4,8 +4,6 @@ Thin wrappers with the reference's signatures and semantics
 (torchsde/_brownian/derived.py:22-50, 52-103, 106-191, 194-205) over the CUDA-backed
 `BrownianInterval`.
 """
-import torch
-
 from . import brownian_base
 from . import interval as brownian_interval
 

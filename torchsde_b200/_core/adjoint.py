@@ -20,7 +20,6 @@ _brownian/derived.py:27-30).
 Not implemented yet (SURVEY §8(f) "next"): the generic `AdjointSDE` path for
 euler/milstein/midpoint adjoints, double backward, adaptive adjoint stepping.
 """
-import ctypes
 import warnings
 
 import torch

@@ -12,11 +12,7 @@ The table below lists c_oi for every entry point of include/torchsde_b200.h that
 The backward arithmetic is a handful of torch element-wise ops on the materialised increments (what the
 reference's own backward does); the hot no-grad / adjoint paths never come here.
 """
-import ctypes
-
 import torch
-
-from .. import _cabi
 
 _S13, _S23, _S16 = 1.0 / 3, 2.0 / 3, 1.0 / 6
 
@@ -120,11 +116,7 @@ class TableauFn(torch.autograd.Function):
             for i, (kind, c) in enumerate(table[o]):
                 shape = ctx.in_shapes[i]
                 if kind == 'e' or ctx.unit:
-                    if torch.is_tensor(c) and c.dim() == 2 and c.shape[1] == 1 and g_o.dim() == 2:
-                        term = g_o * c  # scalar noise: one channel broadcast over d
-                    else:
-                        term = g_o * c
-                    term = term.reshape(shape) if term.numel() == int(torch.Size(shape).numel()) else term
+                    term = g_o * c  # (scalar noise: a (rows, 1) coefficient broadcasts over d)
                 elif kind == 'gg':  # g-shaped input AND output (Milstein's vjp seed)
                     term = g_o * (c.unsqueeze(-2) if g_o.dim() == 3 else c)
                 else:  # 'g': adjoint of the product g.v

@@ -25,7 +25,7 @@ import torch
 
 from . import schedule as schedule_lib
 from .. import _cabi
-from .._brownian import BaseBrownian, BrownianInterval, ReverseBrownian, GridBinding
+from .._brownian import BrownianInterval, ReverseBrownian
 from ..settings import NOISE_TYPES
 
 

@@ -26,7 +26,6 @@ import torch
 
 from . import base_solver
 from . import schedule as schedule_lib
-from .._brownian import BrownianInterval, ReverseBrownian
 
 _PLANS = weakref.WeakKeyDictionary()
 MAX_PLANS_PER_SDE = 4  # every plan owns its output series (T x B x D): keep the cache small
