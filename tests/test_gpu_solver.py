@@ -392,3 +392,30 @@ def test_general_kernel_shapes_vs_oracle(d, m):
     ref, _ = solvers.make('heun', problems.NumpySDE(sde_cpu), _oracle_bm_from(bm, B, m, np.float64, False),
                           2.0 ** -4).integrate(y0.numpy(), ts)
     np.testing.assert_allclose(ys.cpu().numpy(), ref, rtol=1e-11, atol=1e-12)
+
+
+@pytest.mark.parametrize('d', [12, 20, 48, 100, 36])
+def test_fast_kernel_non_power_of_two_rows(d):
+    """d % 4 == 0 with d/4 not a power of two takes the specialised kernel through the magic-number
+    division: registers == materialised increments (bit-equal) and shard invariance."""
+    tsde = _tsde()
+    dev = torch.device('cuda')
+    B = 257
+    sde = problems.GBMDiagonal(d, 'ito', seed=d, dtype=torch.float32).to(dev)
+    y0 = torch.full((B, d), 0.3, device=dev)
+    ts = torch.tensor([0.0, 0.25], device=dev)
+    bm = tsde.BrownianInterval(0.0, 0.25, size=(B, d), dtype=torch.float32, device=dev, entropy=d)
+    fast = tsde.sdeint(sde, y0, ts, bm=bm, method='srk' if d == 36 else 'milstein', dt=2.0 ** -3) if d != 36 else None
+    if d == 36:
+        bm = tsde.BrownianInterval(0.0, 0.25, size=(B, d), dtype=torch.float32, device=dev, entropy=d,
+                                   levy_area_approximation='space-time')
+        fast = tsde.sdeint(sde, y0, ts, bm=bm, method='srk', dt=2.0 ** -3)
+
+    class Mat:
+        shape, levy_area_approximation = bm.shape, bm.levy_area_approximation
+
+        def __call__(self, ta, tb=None, return_U=False, return_A=False):
+            return bm(ta, tb, return_U=return_U)
+
+    slow = tsde.sdeint(sde, y0, ts, bm=Mat(), method='srk' if d == 36 else 'milstein', dt=2.0 ** -3)
+    assert torch.equal(fast, slow)

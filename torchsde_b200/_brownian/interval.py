@@ -558,6 +558,13 @@ class BrownianInterval(brownian_base.BaseBrownian):
             if self._dt is not None and self._root.kind == _LEAF and self._root_value is None \
                     and self._user_W is None and self._user_H is None and not self._halfway_tree:
                 self._bind_uniform(self._dt)
+            fast = self._query_cells_wu(ta_r, tb_r, tb - ta) if (self._have_H and not self._have_A) else None
+            if fast is not None:
+                W, U = fast
+                W, U = W.reshape(self._size), U.reshape(self._size)
+                if return_U:
+                    return (W, U, None) if return_A else (W, U)
+                return (W, None) if return_A else W
             W, H, A = self._query(ta_r, tb_r)
             U = None
             if self._have_H:
@@ -578,6 +585,37 @@ class BrownianInterval(brownian_base.BaseBrownian):
         if return_A:
             return W, A
         return W
+
+    def _query_cells_wu(self, ta, tb, h_total):
+        """Single-launch answer (W, U) when [ta, tb] is exactly a run of whole primary cells of the root
+        grid (the access pattern of a fixed-step solver / of sequential dt-spaced queries): U is formed in
+        the same kernel as W, H is never materialised."""
+        root = self._root
+        if root.kind != _GRID:
+            return None
+        b = root.bounds
+        i = bisect.bisect_left(b, ta)
+        if i >= len(b) or b[i] != ta:
+            return None
+        j = bisect.bisect_left(b, tb, i)
+        if j >= len(b) or b[j] != tb or j <= i:
+            return None
+        nz = _cabi.Noise()
+        nz.source = _cabi.SRC_COUNTER
+        nz.want_u = 1
+        nz.key = self.key_tensor().data_ptr()
+        nz.cell_id = (root.cell_base + i) & _MASK64
+        nz.row_offset = self._row_offset
+        nz.n_cells = j - i
+        nz.h = b[i + 1] - b[i]
+        nz.h_total = h_total
+        nz.cell_h = self._cell_h_dev(root).data_ptr() + 8 * i if j - i > 1 else None
+        W, U = self._new(), self._new()
+        L = self._launch()
+        _cabi.check(_cabi.lib().tsde_brownian_cells(ctypes.byref(L), ctypes.byref(nz), W.data_ptr(), U.data_ptr(),
+                                                    None), "tsde_brownian_cells")
+        self._last = root
+        return W, U
 
     def _piece_value(self, piece):
         if isinstance(piece, _Node):

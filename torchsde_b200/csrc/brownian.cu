@@ -7,23 +7,6 @@
 namespace tsde {
 
 // ---- cells -> (W, U, H) ---------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(kThreads)
-cells_kernel(NoiseP<T> nz, int64_t rows, int64_t m, int64_t qpr, int vec, T* out_w) {
-  const Key key = load_key(nz.key);
-  const int64_t nquads = rows * qpr;
-  const int64_t stride = (int64_t)gridDim.x * kThreads;
-  for (int64_t Q = (int64_t)blockIdx.x * kThreads + threadIdx.x; Q < nquads; Q += stride) {
-    const int64_t row = Q / qpr, q = Q - row * qpr;
-    const int64_t base = row * m + 4 * q;
-    const int64_t rem = m - 4 * q;
-    const int nvalid = rem < 4 ? (int)rem : 4;
-    T w[4], u[4];
-    counter_noise<T, false>(nz, key, (uint32_t)(row + nz.row_offset), (uint32_t)q, w, u);
-    store_quad(out_w, base, vec != 0, nvalid, w);
-  }
-}
-
 // Variant that also exposes H itself (the bridge descent consumes it).
 template <typename T>
 __device__ __forceinline__ void counter_wh(const NoiseP<T>& nz, Key key, uint32_t row, uint32_t q,
@@ -87,6 +70,17 @@ cells_wh_kernel(NoiseP<T> nz, int64_t rows, int64_t m, int64_t qpr, int vec, T* 
   }
 }
 
+// W (and U) of a run of cells through the row-wise framework (specialised kernel + PDL when it applies)
+template <typename T, bool WANT>
+struct CellsOp {
+  static constexpr int NIN = 0, NOUT = WANT ? 2 : 1;
+  static constexpr bool USES_NOISE = true, WANT_U = WANT;
+  __device__ __forceinline__ void operator()(const T (&)[1], T w, T u, T (&out)[NOUT]) const {
+    out[0] = w;
+    if (WANT) out[NOUT - 1] = u;
+  }
+};
+
 static inline unsigned grid_for(int64_t nquads) {
   int64_t blocks = (nquads + kThreads - 1) / kThreads;
   const int64_t cap = (int64_t)kSMs * kBlocksPerSM;
@@ -105,13 +99,22 @@ static int cells_impl(const tsde_launch* L, const tsde_noise* nz, void* out_w, v
   const bool vec = (m % 4 == 0) && aligned16(out_w) && (!out_u || aligned16(out_u)) &&
                    (!out_h || aligned16(out_h));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(L->stream);
-  if (out_u || out_h) {
+  if (out_h) {
     cells_wh_kernel<T><<<grid_for(nquads), kThreads, 0, st>>>(np, rows, m, qpr, vec, (T*)out_w,
                                                              (T*)out_u, (T*)out_h);
-  } else {
-    cells_kernel<T><<<grid_for(nquads), kThreads, 0, st>>>(np, rows, m, qpr, vec, (T*)out_w);
+    return (int)cudaGetLastError();
   }
-  return (int)cudaGetLastError();
+  tsde_launch r = *L;
+  r.d = m;
+  r.noise_type = TSDE_NOISE_DIAGONAL;
+  tsde_noise z = *nz;
+  if (out_u) {
+    z.want_u = 1;
+    void* outs[2] = {out_w, out_u};
+    return launch_ew<T, CellsOp<T, true>>(&r, &z, false, nullptr, outs, CellsOp<T, true>{});
+  }
+  void* outs[1] = {out_w};
+  return launch_ew<T, CellsOp<T, false>>(&r, &z, false, nullptr, outs, CellsOp<T, false>{});
 }
 
 // ---- Brownian bridge descent ------------------------------------------------------------------

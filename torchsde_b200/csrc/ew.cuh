@@ -69,6 +69,7 @@ struct EwP {
   int32_t vec;     // all pointers 16B-aligned and d % 4 == 0
   int32_t qshift;  // log2(qpr) if qpr is a power of two, else -1
   int32_t small;   // nquads < 2^31: 32-bit index arithmetic
+  uint64_t qmagic; // ceil(2^40 / qpr): row = (Q * qmagic) >> 40, exact while Q * qpr < 2^40
 };
 
 // ---- vector load / store helpers ---------------------------------------------------------
@@ -285,15 +286,22 @@ ew_fast_kernel(const EwP<Op::NIN, Op::NOUT> p, const NoiseP<T> nz, const Op op) 
   const uint32_t nquads = (uint32_t)p.nquads;
   const uint32_t q_begin = (uint32_t)(((uint64_t)nquads * blockIdx.x) / gridDim.x);
   const uint32_t q_end = (uint32_t)(((uint64_t)nquads * (blockIdx.x + 1)) / gridDim.x);
-  const uint32_t qshift = (uint32_t)p.qshift, qmask = (1u << qshift) - 1u;
+  const bool pow2 = p.qshift >= 0;
+  const uint32_t qshift = pow2 ? (uint32_t)p.qshift : 0u, qmask = (1u << qshift) - 1u;
+  const uint32_t qpr32 = (uint32_t)p.qpr;
+  const uint64_t qmagic = p.qmagic;
   const uint32_t row_off = (uint32_t)nz.row_offset;
+  auto row_of = [&](uint32_t Q) -> uint32_t { return pow2 ? (Q >> qshift) : (uint32_t)(((uint64_t)Q * qmagic) >> 40); };
+  auto quad_of = [&](uint32_t Q, uint32_t row) -> uint32_t { return pow2 ? (Q & qmask) : (Q - row * qpr32); };
   // Programmatic dependent launch: this grid may start while its predecessor in the stream/graph is
   // still draining.  Everything that does not touch the predecessor's outputs — the Philox/Box-Muller
   // work of the thread's first quad — runs before `griddepcontrol.wait`; all loads and stores come after.
   T w0[4], u0[4];
   const uint32_t Q0 = q_begin + threadIdx.x;
-  if (Op::USES_NOISE && SRC == TSDE_SRC_COUNTER && Q0 < q_end)
-    counter_noise<T, Op::WANT_U, false>(nz, key, (Q0 >> qshift) + row_off, Q0 & qmask, w0, u0);
+  if (Op::USES_NOISE && SRC == TSDE_SRC_COUNTER && Q0 < q_end) {
+    const uint32_t r0 = row_of(Q0);
+    counter_noise<T, Op::WANT_U, false>(nz, key, r0 + row_off, quad_of(Q0, r0), w0, u0);
+  }
   asm volatile("griddepcontrol.wait;" ::: "memory");
   for (uint32_t Q = Q0; Q < q_end; Q += kThreads) {
     const size_t base = (size_t)Q * 4;  // d == 4 * qpr: quads are laid out contiguously
@@ -307,7 +315,8 @@ ew_fast_kernel(const EwP<Op::NIN, Op::NOUT> p, const NoiseP<T> nz, const Op op) 
 #pragma unroll
           for (int j = 0; j < 4; ++j) { w[j] = w0[j]; u[j] = Op::WANT_U ? u0[j] : T(0); }
         } else {
-          counter_noise<T, Op::WANT_U, false>(nz, key, (Q >> qshift) + row_off, Q & qmask, w, u);
+          const uint32_t r = row_of(Q);
+          counter_noise<T, Op::WANT_U, false>(nz, key, r + row_off, quad_of(Q, r), w, u);
         }
       } else if (SRC == TSDE_SRC_MEMORY) {
         ld4(nz.w + base, w);
@@ -399,6 +408,7 @@ inline int launch_ew(const tsde_launch* L, const tsde_noise* nz, bool bcast,
     p.qshift = sh;
   }
   p.small = p.nquads < (1ll << 31) ? 1 : 0;
+  p.qmagic = ((1ull << 40) + (uint64_t)p.qpr - 1) / (uint64_t)p.qpr;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(L->stream);
   bool pdl = false;
   auto go = [&](auto kernel) -> int {
@@ -428,7 +438,8 @@ inline int launch_ew(const tsde_launch* L, const tsde_noise* nz, bool bcast,
     kernel<<<(unsigned)blocks, kThreads, 0, st>>>(p, np, op);
     return (int)cudaGetLastError();
   };
-  const bool fast = p.vec && !bcast && p.qshift >= 0 && p.small && np.n_cells == 1 &&
+  const bool divisible = p.qshift >= 0 || (p.nquads * p.qpr < (1ll << 40) && p.qpr < (1ll << 20));
+  const bool fast = p.vec && !bcast && divisible && p.small && np.n_cells == 1 &&
                     (L->rows + (nz ? nz->row_offset : 0)) < 0xFFFFFFFFll;
   pdl = fast && pdl_enabled();
   if constexpr (!Op::USES_NOISE) {
