@@ -199,52 +199,66 @@ gen_cta_kernel(const GenP<Op::NE, Op::NG, Op::NO> p, const NoiseP<T> nz, const O
     if (Op::WANT_U) st4(su + r * m + 4 * q, u);
   }
   if (SRC != TSDE_SRC_MEMORY) asm volatile("griddepcontrol.wait;" ::: "memory");
+  // Streaming sweep over the group's g tile (contiguous: element offset = tile0 + 4 * chunk).
+  // Index arithmetic is hoisted: a thread's Brownian quad `mc` never changes (128 % mq == 0), its
+  // (row, d) position advances by a constant number of (row, d) slots per load, tracked incrementally.
   const int total = nrows * per_row;
-  for (int c0 = 0; c0 < total; c0 += kGenThreads * kGenUnroll) {
+  const int64_t tile0 = row0 * p.d * m;          // first g element of the group
+  const int64_t slot0 = row0 * p.d;               // first (row, d) slot of the group
+  const int mc = tid & (mq - 1);
+  const int d = (int)p.d;
+  const int slots_per_load = kGenThreads >> mq_shift;
+  int slot = tid >> mq_shift;                      // (row, d) slot of this thread's next chunk
+  int r = slot / d;                                // row inside the group (one division per thread)
+  int dd = slot - r * d;
+  bool synced = false;
+  for (int base = 0; base < total; base += kGenThreads * kGenUnroll) {  // CTA-uniform trip count
+    const int c0 = base + tid;
     T gv[kGenUnroll][NG][4];
-    int rr[kGenUnroll], mcs[kGenUnroll];
-    int64_t eoffs[kGenUnroll];
+    T ev[kGenUnroll][NE > 0 ? NE : 1];  // element-wise operands, fetched together with g (not after the reduce)
+    int rr[kGenUnroll], slots[kGenUnroll];
     bool valid[kGenUnroll];
 #pragma unroll
     for (int un = 0; un < kGenUnroll; ++un) {
-      const int c = c0 + un * kGenThreads + tid;
+      const int c = c0 + un * kGenThreads;
       valid[un] = c < total;
-      const int cc = valid[un] ? c : 0;
-      const int r = cc / per_row;
-      const int rem = cc - r * per_row;
-      const int dd = rem >> mq_shift;
-      const int mc = rem & (mq - 1);
       rr[un] = r;
-      mcs[un] = mc;
-      eoffs[un] = (row0 + r) * p.d + dd;
-      const int64_t goff = eoffs[un] * m + 4 * mc;
+      slots[un] = slot;
+      if (valid[un] && mc == 0) {
+#pragma unroll
+        for (int i = 0; i < NE; ++i) ev[un][i] = reinterpret_cast<const T*>(p.e[i])[slot0 + slot];
+      }
 #pragma unroll
       for (int i = 0; i < NG; ++i) {
         if (valid[un]) {
-          ld4(reinterpret_cast<const T*>(p.g[i]) + goff, gv[un][i]);
+          ld4(reinterpret_cast<const T*>(p.g[i]) + tile0 + 4 * (int64_t)c, gv[un][i]);
         } else {
 #pragma unroll
           for (int j = 0; j < 4; ++j) gv[un][i][j] = T(0);
         }
       }
+      slot += slots_per_load;
+      dd += slots_per_load;
+      while (dd >= d) { dd -= d; ++r; }
     }
-    if (c0 == 0) __syncthreads();  // increments visible (uniform: every thread runs iteration 0)
+    if (!synced) { __syncthreads(); synced = true; }  // increments visible (first pass is uniform)
 #pragma unroll
     for (int un = 0; un < kGenUnroll; ++un) {
       T part[NP];
 #pragma unroll
       for (int k = 0; k < NP; ++k) part[k] = T(0);
       T w4[4], u4[4];
-      ld4(sw + rr[un] * m + 4 * mcs[un], w4);
-      if (Op::WANT_U) ld4(su + rr[un] * m + 4 * mcs[un], u4);
+      const int rs = valid[un] ? rr[un] : 0;
+      ld4(sw + rs * m + 4 * mc, w4);
+      if (Op::WANT_U) ld4(su + rs * m + 4 * mc, u4);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         T gj[NG];
 #pragma unroll
         for (int i = 0; i < NG; ++i) gj[i] = gv[un][i][j];
 #pragma unroll
-        for (int k = 0; k < NP; ++k)
-          part[k] = part[k] + op.gval(k, gj) * op.weight(k, w4[j], Op::WANT_U ? u4[j] : T(0));
+        for (int k = 0; k < NP; ++k)  // fused multiply-add: the contraction's rounding is not pinned (bmm)
+          part[k] = fma(op.gval(k, gj), op.weight(k, w4[j], Op::WANT_U ? u4[j] : T(0)), part[k]);
       }
 #pragma unroll
       for (int off = 1; off < 32; off <<= 1) {
@@ -253,17 +267,18 @@ gen_cta_kernel(const GenP<Op::NE, Op::NG, Op::NO> p, const NoiseP<T> nz, const O
           for (int k = 0; k < NP; ++k) part[k] = part[k] + __shfl_xor_sync(0xffffffffu, part[k], off);
         }
       }
-      if (valid[un] && mcs[un] == 0) {
+      if (valid[un] && mc == 0) {
+        const int64_t eoff = slot0 + slots[un];
         T e[NE > 0 ? NE : 1], o[NO];
 #pragma unroll
-        for (int i = 0; i < NE; ++i) e[i] = reinterpret_cast<const T*>(p.e[i])[eoffs[un]];
+        for (int i = 0; i < NE; ++i) e[i] = ev[un][i];
         op.combine(e, part, o);
 #pragma unroll
-        for (int i = 0; i < NO; ++i) reinterpret_cast<T*>(p.o[i])[eoffs[un]] = o[i];
+        for (int i = 0; i < NO; ++i) reinterpret_cast<T*>(p.o[i])[eoff] = o[i];
       }
     }
   }
-  if (total == 0) __syncthreads();
+  if (!synced) __syncthreads();
 }
 
 template <typename T, typename Op>
