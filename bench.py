@@ -47,6 +47,9 @@ WORKLOADS = {
     # products, i.e. PyTorch's vectorised kernels instead of its broadcasting ones.  E = 7 (solver) + 3*3 = 16 D s.
     'cfg2_pertraj': dict(method='milstein', sde_type='ito', kind='gbm_pertraj', B=65536, D=64, M=64, T=1000,
                          dt=2.0 ** -10, E_bytes_per_traj_step=16 * 64 * 4, S_tableau_bytes_per_traj_step=5 * 64 * 4),
+    # general noise in the HBM-bound regime (g = 256 MiB per evaluation)
+    'cfg3_euler_general_large': dict(method='euler', sde_type='ito', kind='general', B=65536, D=64, M=16, T=100,
+                                     dt=2.0 ** -10, E_bytes_per_traj_step=(6 * 64 + 2 * 64 * 16) * 4),
     # other diagonal tableaus at the cfg2 size
     'cfg2_euler': dict(method='euler', sde_type='ito', kind='gbm', B=65536, D=64, M=64, T=200, dt=2.0 ** -10,
                        E_bytes_per_traj_step=8 * 64 * 4),

@@ -419,3 +419,33 @@ def test_fast_kernel_non_power_of_two_rows(d):
 
     slow = tsde.sdeint(sde, y0, ts, bm=Mat(), method='srk' if d == 36 else 'milstein', dt=2.0 ** -3)
     assert torch.equal(fast, slow)
+
+
+def test_strong_orders_on_one_brownian_path():
+    """Convergence orders as in the reference's diagnostics (diagnostics/inspection.py:71-140), against the
+    analytic GBM solution y0 exp((mu - sigma^2/2) t + sigma W_t) with W_t read from the SAME Brownian object:
+    checks that solves on nested grids (merged primary cells) and `bm(0, t)` describe one consistent path, and
+    that Euler / Milstein / SRK show strong orders 0.5 / 1.0 / 1.5."""
+    tsde = _tsde()
+    dev = torch.device('cuda')
+    B, d = 16384, 4
+    sde = problems.GBMDiagonal(d, 'ito', seed=7, dtype=torch.float64).to(dev)
+    y0 = torch.full((B, d), 0.5, dtype=torch.float64, device=dev)
+    ts = torch.tensor([0.0, 1.0], dtype=torch.float64, device=dev)
+    bm = tsde.BrownianInterval(0.0, 1.0, size=(B, d), dtype=torch.float64, device=dev, entropy=2024,
+                               levy_area_approximation='space-time')
+    tsde.sdeint(sde, y0, ts, bm=bm, method='euler', dt=2.0 ** -9)       # binds the finest grid first
+    W1 = bm(0.0, 1.0)
+    mu, sigma = sde.mu.detach(), sde.sigma.detach()
+    exact = y0 * torch.exp((mu - 0.5 * sigma ** 2) * 1.0 + sigma * W1)
+    dts = [2.0 ** -k for k in range(2, 8)]
+    slopes = {}
+    for method in ('euler', 'milstein', 'srk'):
+        errs = []
+        for dt in dts:
+            y1 = tsde.sdeint(sde, y0, ts, bm=bm, method=method, dt=dt)[-1]
+            errs.append(float(((y1 - exact) ** 2).sum(1).mean().sqrt()))
+        slopes[method] = np.polyfit(np.log(dts), np.log(errs), 1)[0]
+    assert 0.4 < slopes['euler'] < 0.65, slopes
+    assert 0.85 < slopes['milstein'] < 1.15, slopes
+    assert 1.3 < slopes['srk'] < 1.7, slopes
