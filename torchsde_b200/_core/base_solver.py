@@ -263,13 +263,13 @@ class BaseSDESolver(metaclass=abc.ABCMeta):
         self._lib = _cabi.lib()
         self._prepared = True
 
-    # -- drift on a parallel branch --------------------------------------------------------------
+    # -- drift on a parallel branch (options={'overlap_drift': True}; off by default) --------------
     # f(t, y) and the diffusion chain g -> (vjp) are independent given y.  Issuing the drift on a
-    # side stream makes them parallel branches of the captured graph (fork/join), so PyTorch's
-    # latency-bound element-wise kernels of the user's f overlap with the g chain instead of
-    # queueing behind it.  Evaluation *order* of f and g is not observable for pure callables.
+    # side stream makes them parallel branches of the captured graph (fork/join).  Measured on cfg2 the
+    # gain is within noise (each of PyTorch's element-wise kernels already fills every SM slot), so the
+    # default keeps a single stream; evaluation *order* of f and g is not observable for pure callables.
     def _drift_async(self, fn):
-        if self._autograd or not self.options.get('overlap_drift', True):
+        if self._autograd or not self.options.get('overlap_drift', False):
             return fn(), None  # (under autograd keep one stream: AccumulateGrad nodes remember theirs)
         main = torch.cuda.current_stream(self.device)
         side = self._side_stream

@@ -39,13 +39,11 @@ class Schedule:
         for o in outputs:
             outs_after.setdefault(o.step, []).append(o)
         self.outputs_after = outs_after
+        self._aligned = {o.step: o.index for o in outputs if o.aligned}
 
     def aligned_row(self, k):
         """Row of ys that coincides with the end of step k (or None)."""
-        for o in self.outputs_after.get(k, ()):
-            if o.aligned:
-                return o.index
-        return None
+        return self._aligned.get(k)
 
 
 def build_schedule(ts, dt):
