@@ -272,7 +272,12 @@ def run_ours(args, w, rank, world, local_rank):
     barrier()
     e2e_elapsed = e0.elapsed_time(e1) * 1e-3
 
+    per_rank_ms = [elapsed / args.steps * 1e3]
     if world > 1:
+        mine = torch.tensor([elapsed], device=dev, dtype=torch.float64)
+        every = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        per_rank_ms = [float(x.item()) / args.steps * 1e3 for x in every]
         t = torch.tensor([elapsed, e2e_elapsed], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed, e2e_elapsed = t.tolist()
@@ -304,6 +309,7 @@ def run_ours(args, w, rank, world, local_rank):
                    "80 MiB + 16 MiB ys row streamed into a 16.8 GB series", "parallelism": f"batch-sharded x{world}",
                    "finite": finite},
         "clocks": clocks,
+        "per_rank_ms_per_step": [round(x, 3) for x in per_rank_ms],
         "e2e": {"value": e2e_value, "unit": "traj-steps/s", "h2d_bytes_per_step": int(y0_host.numel() * 4),
                 "d2h_bytes_per_step": int(out_host.numel() * 4), "ms_per_step": e2e_elapsed / args.steps * 1e3,
                 "result_copied": "ys[-1] (terminal states)",

@@ -354,7 +354,7 @@ class BaseSDESolver(metaclass=abc.ABCMeta):
         (base_solver.py:92-149, fixed-step branch)."""
         if self.adaptive:
             return self._integrate_adaptive(y0, ts, extra0)
-        sched = schedule_lib.build_schedule(ts, self.dt)
+        sched = schedule_lib.get_schedule(ts, self.dt)
         if self._autograd:
             y0 = _contig(y0)
             self._prepare(y0)

@@ -44,7 +44,7 @@ class _Plan:
 def _plan_key(solver, y0, ts, extra0, binding):
     node = binding.node
     return (type(solver).__name__, tuple(y0.shape), y0.dtype, str(y0.device),
-            tuple(ts.detach().cpu().tolist()), str(ts.dtype),
+            schedule_lib.ts_values(ts), str(ts.dtype),
             float(solver.dt) if not torch.is_tensor(solver.dt) else float(solver.dt),
             tuple(sorted((k, repr(v)) for k, v in solver.options.items())),
             solver.bm.levy_area_approximation, tuple(solver.bm.shape),
@@ -57,7 +57,7 @@ def integrate_captured(solver, y0, ts, extra0):
     if int(solver.options.get('row_split', 1)) > 1 and not extra0:
         return _integrate_captured_split(solver, y0, ts)
     sde_obj = solver.sde._base_sde
-    sched = schedule_lib.build_schedule(ts, solver.dt)
+    sched = schedule_lib.get_schedule(ts, solver.dt)
     y0 = base_solver._contig(y0.detach())
     solver._prepare(y0)
     binding = solver._bind(sched)
@@ -141,7 +141,7 @@ def _integrate_captured_split(solver, y0, ts):
     import copy
     k = int(solver.options['row_split'])
     sde_obj = solver.sde._base_sde
-    sched = schedule_lib.build_schedule(ts, solver.dt)
+    sched = schedule_lib.get_schedule(ts, solver.dt)
     y0 = base_solver._contig(y0.detach())
     solver._prepare(y0)
     binding = solver._bind(sched)

@@ -8,7 +8,46 @@ are evaluated once with 0-d CPU tensors of the same dtype (so rounding — e.g. 
 of ``curr_t + dt`` in fp32, which gives 1001 steps for dt=1e-3 on [0,1] — is bit-identical), and
 the resulting plan is what the CUDA-graph time loop executes.
 """
+import weakref
+
 import torch
+
+_VALUES = {}     # (id(ts), version) -> (weakref(ts), tuple of python floats)
+_SCHEDULES = {}  # (id(ts), version, dt) -> (weakref(ts), Schedule)
+_MAX_CACHED = 16
+
+
+def _remember(cache, key, value):
+    while len(cache) >= _MAX_CACHED:
+        cache.pop(next(iter(cache)))
+    cache[key] = value
+
+
+def ts_values(ts):
+    """The evaluation times as python floats.  Cached per tensor object (identity + in-place version
+    counter), so that repeated solves on the same `ts` tensor do not synchronise with the device."""
+    key = (id(ts), ts._version)
+    hit = _VALUES.get(key)
+    if hit is not None and hit[0]() is ts:
+        return hit[1]
+    vals = tuple(ts.detach().to('cpu').tolist())
+    _remember(_VALUES, key, (weakref.ref(ts), vals))
+    return vals
+
+
+def get_schedule(ts, dt):
+    """`build_schedule` with a cache: planning a 1000-step grid costs ~10 ms of host time (0-d tensor
+    arithmetic in ts' dtype, deliberately identical to the reference's), which would otherwise be paid —
+    serialised with the GPU by the device->host read of `ts` — on every solve of a training loop."""
+    dkey = (id(dt), dt._version) if torch.is_tensor(dt) else float(dt)
+    key = (id(ts), ts._version, dkey)
+    hit = _SCHEDULES.get(key)
+    if hit is not None and hit[0]() is ts:
+        return hit[1]
+    sched = build_schedule(ts, dt)
+    sched.values = ts_values(ts)
+    _remember(_SCHEDULES, key, (weakref.ref(ts), sched))
+    return sched
 
 
 class Output:

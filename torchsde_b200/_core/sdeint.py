@@ -18,6 +18,7 @@ import torch
 
 from . import base_sde
 from . import methods
+from . import schedule as schedule_lib
 from .. import _cabi
 from .._brownian import BrownianInterval
 from ..settings import LEVY_AREA_APPROXIMATIONS, METHODS, NOISE_TYPES, SDE_TYPES
@@ -127,6 +128,21 @@ class _Sizes:
             raise ValueError("Noise sizes not consistent.")
 
 
+_TS_FROM_LIST = {}
+
+
+def _tensor_from_list(values, dtype, device):
+    """`ts` given as a list/tuple of floats (sdeint.py:161-164): the tensor is built once per distinct
+    (values, dtype, device) so that the host-side plan of the grid can be reused across calls."""
+    key = (values, dtype, str(device))
+    t = _TS_FROM_LIST.get(key)
+    if t is None:
+        if len(_TS_FROM_LIST) >= 16:
+            _TS_FROM_LIST.pop(next(iter(_TS_FROM_LIST)))
+        t = _TS_FROM_LIST[key] = torch.tensor(values, dtype=dtype, device=device)
+    return t
+
+
 def _is_strictly_increasing(ts):
     return all(x < y for x, y in zip(ts[:-1], ts[1:]))
 
@@ -171,8 +187,8 @@ def check_contract(sde, y0, ts, bm, method, adaptive, options, names, logqp):
     if not torch.is_tensor(ts):
         if not isinstance(ts, (tuple, list)) or not all(isinstance(t, (float, int)) for t in ts):
             raise ValueError("Evaluation times `ts` must be a 1-D Tensor or list/tuple of floats.")
-        ts = torch.tensor(ts, dtype=y0.dtype, device=y0.device)
-    if not _is_strictly_increasing(ts.detach().cpu().tolist() if ts.is_cuda else ts):
+        ts = _tensor_from_list(tuple(ts), y0.dtype, y0.device)
+    if not _is_strictly_increasing(schedule_lib.ts_values(ts)):
         raise ValueError("Evaluation times `ts` must be strictly increasing.")
 
     sizes = _Sizes(sde.noise_type)
@@ -232,7 +248,8 @@ def check_contract(sde, y0, ts, bm, method, adaptive, options, names, logqp):
             levy_area_approximation = LEVY_AREA_APPROXIMATIONS.foster
         else:
             levy_area_approximation = LEVY_AREA_APPROXIMATIONS.none
-        bm = BrownianInterval(t0=ts[0], t1=ts[-1], size=(sizes.batch[0], sizes.noise[0]), dtype=y0.dtype,
+        vals = schedule_lib.ts_values(ts)
+        bm = BrownianInterval(t0=vals[0], t1=vals[-1], size=(sizes.batch[0], sizes.noise[0]), dtype=y0.dtype,
                               device=y0.device, levy_area_approximation=levy_area_approximation)
 
     options = {} if options is None else options.copy()

@@ -41,6 +41,7 @@ template <typename T>
 struct MilsteinOp {
   static constexpr int NIN = 4, NOUT = 1;
   static constexpr bool USES_NOISE = true, WANT_U = false;
+  static constexpr bool STREAM_INPUTS = true;  // y0, f, g, gdg are all dead after the step's last kernel
   T dt;
   __device__ __forceinline__ void operator()(const T (&in)[4], T w, T, T (&out)[1]) const {
     const T y0 = in[0], f = in[1], g = in[2], gdg = in[3];
@@ -67,6 +68,7 @@ template <typename T>
 struct MilsteinGfOp {
   static constexpr int NIN = 4, NOUT = 1;
   static constexpr bool USES_NOISE = true, WANT_U = false;
+  static constexpr bool STREAM_INPUTS = true;  // last kernel of the step: every operand is dead afterwards
   T dt, two_sqrt_dt;
   int ito;
   __device__ __forceinline__ void operator()(const T (&in)[4], T w, T, T (&out)[1]) const {
@@ -82,6 +84,7 @@ template <typename T>
 struct HeunOp {
   static constexpr int NIN = 5, NOUT = 1;
   static constexpr bool USES_NOISE = true, WANT_U = false;
+  static constexpr bool STREAM_INPUTS = true;  // last kernel of the step: every operand is dead afterwards
   T dt;
   __device__ __forceinline__ void operator()(const T (&in)[5], T w, T, T (&out)[1]) const {
     const T y0 = in[0], f = in[1], fp = in[2], g = in[3], gp = in[4];
@@ -116,6 +119,7 @@ template <typename T>
 struct EulerHeunOp {
   static constexpr int NIN = 4, NOUT = 1;
   static constexpr bool USES_NOISE = true, WANT_U = false;
+  static constexpr bool STREAM_INPUTS = true;  // last kernel of the step: every operand is dead afterwards
   T dt;
   __device__ __forceinline__ void operator()(const T (&in)[4], T w, T, T (&out)[1]) const {
     const T y0 = in[0], f = in[1], g = in[2], gp = in[3];
@@ -193,6 +197,7 @@ template <typename T>
 struct SrkDiagFinalOp {
   static constexpr int NIN = 8, NOUT = 1;
   static constexpr bool USES_NOISE = true, WANT_U = true;
+  static constexpr bool STREAM_INPUTS = true;  // last kernel of the step: every operand is dead afterwards
   T dt, rdt, sqrt_dt;
   T three_dt;              // 3*dt as the reference's 0-d tensor product (srk.py:64)
   T alpha[3];

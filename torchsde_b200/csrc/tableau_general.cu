@@ -231,7 +231,8 @@ gen_cta_kernel(const GenP<Op::NE, Op::NG, Op::NO> p, const NoiseP<T> nz, const O
 #pragma unroll
       for (int i = 0; i < NG; ++i) {
         if (valid[un]) {
-          ld4(reinterpret_cast<const T*>(p.g[i]) + tile0 + 4 * (int64_t)c, gv[un][i]);
+          if (streams_inputs<Op>::value) ld4cs(reinterpret_cast<const T*>(p.g[i]) + tile0 + 4 * (int64_t)c, gv[un][i]);
+          else ld4(reinterpret_cast<const T*>(p.g[i]) + tile0 + 4 * (int64_t)c, gv[un][i]);
         } else {
 #pragma unroll
           for (int j = 0; j < 4; ++j) gv[un][i][j] = T(0);
@@ -367,6 +368,7 @@ template <typename T>
 struct GHeunOp {
   static constexpr int NE = 3, NG = 2, NP = 2, NO = 1;
   static constexpr bool WANT_U = false;
+  static constexpr bool STREAM_INPUTS = true;  // last kernel of the step: the g tiles are dead afterwards
   T dt;
   __device__ __forceinline__ T gval(int p, const T (&g)[2]) const { return g[p]; }
   __device__ __forceinline__ T weight(int, T w, T) const { return w; }
@@ -402,6 +404,7 @@ template <typename T>
 struct GEulerHeunOp {
   static constexpr int NE = 2, NG = 2, NP = 2, NO = 1;
   static constexpr bool WANT_U = false;
+  static constexpr bool STREAM_INPUTS = true;  // last kernel of the step: the g tiles are dead afterwards
   T dt;
   __device__ __forceinline__ T gval(int p, const T (&g)[2]) const { return g[p]; }
   __device__ __forceinline__ T weight(int, T w, T) const { return w; }
@@ -456,6 +459,7 @@ template <typename T>
 struct GSraFinalOp {
   static constexpr int NE = 3, NG = 2, NP = 2, NO = 1;
   static constexpr bool WANT_U = true;
+  static constexpr bool STREAM_INPUTS = true;  // last kernel of the step: the g tiles are dead afterwards
   T dt, rdt, third, two_thirds;
   __device__ __forceinline__ T gval(int p, const T (&g)[2]) const { return g[p]; }
   __device__ __forceinline__ T weight(int p, T w, T u) const {
