@@ -218,8 +218,6 @@ def run_ours(args, w, rank, world, local_rank):
     opts = {'cuda_graph': not args.no_graph}
     if args.row_split > 1:
         opts['row_split'] = args.row_split
-    if args.drift_overlap:
-        opts['drift_overlap'] = args.drift_overlap
     row_offset = rank * B  # weak scaling: every rank integrates its own B trajectories of one global batch
 
     M = D if w.get('kind', 'gbm').startswith('gbm') else w['M']
@@ -392,7 +390,6 @@ def main():
     ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--row-split', type=int, default=1)
-    ap.add_argument('--drift-overlap', default=None)
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
     if os.environ.get('TSDE_BENCH_B'):  # experiments only: override the batch size

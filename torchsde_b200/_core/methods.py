@@ -119,17 +119,11 @@ class BaseMilstein(_ProdMixin, base_solver.BaseSDESolver):
         # g_prod_and_gdg_prod_{diagonal,default}: vjp of g wrt y with grad_outputs g * (0.5 v)
         # base_sde.py:127-155 (always calls self.g, never g_prod)
         track = self._autograd
-        order = self.options.get('drift_overlap', 'seed')
-        if order != 'seed':
-            f, side = self._drift_async(lambda: _contig(sde.f(c.t0, y0)))
+        f, side = self._drift_async(lambda: _contig(sde.f(c.t0, y0)))  # reference order: f first (milstein.py:68)
         with torch.enable_grad():
             y = y0 if (track and y0.requires_grad) else y0.detach().requires_grad_(True)
             g = sde.g(c.t0, y)
             gd = _contig(g if track else g.detach())
-            if order == 'seed':
-                # fork the drift here: PyTorch's load/store-bound element-wise kernels of f then run next
-                # to the issue-bound seed kernel (complementary bottlenecks) instead of next to g
-                f, side = self._drift_async(lambda: _contig(sde.f(c.t0, y0)))
             go = self._k('tsde_milstein_vjp_seed', self._L, self._feed.get(c), (gd,), (c.dt, ito), None)
             if g.requires_grad:
                 gdg, = torch.autograd.grad(g, y, grad_outputs=go.view_as(g), allow_unused=True,
