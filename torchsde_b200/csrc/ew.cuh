@@ -6,11 +6,15 @@
 // HBM plan (B200: 148 SMs, ~6.5 TB/s measured copy bandwidth): each input tensor is read
 // once with 128-bit loads, each output written once with 128-bit stores; every thread issues
 // all of its loads before the first dependent use (NIN independent LDG.128 in flight per
-// thread), the grid is a multiple of the SM count (persistent grid-stride loop).
+// thread); the grid is one resident wave (SM count x occupancy), each CTA owning an equal
+// contiguous slice of the quads.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+
+#include <mutex>
+#include <unordered_map>
 
 #include "../../include/torchsde_b200.h"
 #include "philox.cuh"
@@ -46,6 +50,23 @@ inline int sm_count() {
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = kSMs;
   }
+  return n;
+}
+
+// Resident CTAs per SM of one kernel instantiation at kThreads threads, queried once per kernel.
+// (Keyed by the kernel's address: instantiations that differ only in a non-type template argument
+// share a function-pointer type, so a function-local static would be shared between them.)
+template <typename K>
+inline int resident_ctas(K kernel) {
+  static std::mutex mu;
+  static std::unordered_map<const void*, int> cache;
+  const void* id = reinterpret_cast<const void*>(kernel);
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(id);
+  if (it != cache.end()) return it->second;
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kThreads, 0) != cudaSuccess || n < 1) n = 1;
+  cache.emplace(id, n);
   return n;
 }
 
@@ -442,13 +463,7 @@ inline int launch_ew(const tsde_launch* L, const tsde_noise* nz, bool bcast,
   bool pdl = false;
   auto go = [&](auto kernel) -> int {
     // Persistent, balanced grid: one wave of resident CTAs, each owning an equal contiguous slice.
-    static int resident = 0;  // CTAs per SM of this instantiation (queried once)
-    if (resident == 0) {
-      int n = 0;
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kThreads, 0) != cudaSuccess || n < 1) n = 1;
-      resident = n;
-    }
-    const int64_t cap = (int64_t)sm_count() * resident;
+    const int64_t cap = (int64_t)sm_count() * resident_ctas(kernel);
     int64_t blocks = (p.nquads + kThreads - 1) / kThreads;  // small problems: one quad per thread
     if (blocks > cap) blocks = cap;                          // large: one resident wave, sliced evenly
     if (pdl) {
