@@ -1,0 +1,68 @@
+"""The TMA-staged general-noise path (`gen_tma_kernel`, TSDE_GEN_TMA) against the default tile kernel.
+
+Both kernels use the same chunk -> lane mapping, the same fused multiply-add chain inside a 4-chunk and the
+same xor-tree across chunks, so for identical increments their outputs must be BIT-IDENTICAL; the default
+kernel itself is pinned against the oracle / the reference's golden files in test_gpu_solver.py.
+"""
+import pytest
+import torch
+
+from . import problems
+
+pytestmark = pytest.mark.gpu
+
+
+def _solve(method, sde_type, kind, B, d, m, dtype, levy, materialise, graph=False):
+    import torchsde_b200 as tsde
+    dev = torch.device('cuda')
+    sde = problems.make(kind, d, m, sde_type, dtype=dtype, seed=11).to(dev)
+    y0 = torch.full((B, d), 0.25, dtype=dtype, device=dev)
+    ts = torch.tensor([0.0, 0.125, 0.25], dtype=dtype, device=dev)
+    bm = tsde.BrownianInterval(0.0, 0.25, size=(B, m), dtype=dtype, device=dev, entropy=99,
+                               levy_area_approximation=levy)
+    if materialise:  # increments handed over as tensors (TSDE_SRC_MEMORY) instead of regenerated from the counter
+        inner = bm
+
+        class Materialised:
+            shape, levy_area_approximation = inner.shape, inner.levy_area_approximation
+
+            def __call__(self, ta, tb=None, return_U=False, return_A=False):
+                return inner(ta, tb, return_U=return_U)
+
+        bm = Materialised()
+    with torch.no_grad():
+        return tsde.sdeint(sde, y0, ts, bm=bm, method=method, dt=2.0 ** -5,
+                           options={'cuda_graph': True} if graph else None).clone()
+
+
+CASES = [
+    # method, sde_type, problem kind, B, d, m, levy
+    ('euler', 'ito', 'general', 1000, 32, 16, 'none'),
+    ('heun', 'stratonovich', 'general', 777, 64, 16, 'none'),          # ragged last tile, two g operands
+    ('midpoint', 'stratonovich', 'general', 513, 8, 4, 'none'),
+    ('euler_heun', 'stratonovich', 'general', 300, 12, 32, 'none'),
+    ('reversible_heun', 'stratonovich', 'general', 260, 16, 8, 'none'),
+    ('srk', 'ito', 'additive', 515, 32, 16, 'space-time'),              # (W, U) weights
+    ('euler', 'ito', 'general', 3, 4, 128, 'none'),                     # fewer tiles than stages
+]
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float64], ids=['f32', 'f64'])
+@pytest.mark.parametrize('materialise', [False, True], ids=['counter', 'memory'])
+@pytest.mark.parametrize('case', CASES, ids=lambda c: '-'.join(map(str, c)))
+def test_tma_path_bit_identical(case, materialise, dtype, monkeypatch):
+    method, sde_type, kind, B, d, m, levy = case
+    monkeypatch.setenv('TSDE_GEN_TMA', '0')
+    base = _solve(method, sde_type, kind, B, d, m, dtype, levy, materialise)
+    monkeypatch.setenv('TSDE_GEN_TMA', '2')
+    tma = _solve(method, sde_type, kind, B, d, m, dtype, levy, materialise)
+    assert torch.isfinite(base).all()
+    assert torch.equal(base, tma), f"max abs diff {(base - tma).abs().max().item()}"
+
+
+def test_tma_path_in_cuda_graph(monkeypatch):
+    monkeypatch.setenv('TSDE_GEN_TMA', '0')
+    base = _solve('heun', 'stratonovich', 'general', 2048, 32, 16, torch.float32, 'none', False)
+    monkeypatch.setenv('TSDE_GEN_TMA', '2')
+    tma = _solve('heun', 'stratonovich', 'general', 2048, 32, 16, torch.float32, 'none', False, graph=True)
+    assert torch.equal(base, tma)

@@ -38,7 +38,7 @@ template <typename T, typename Op, int SRC>
 __global__ void __launch_bounds__(kThreads)
 gen_kernel(const GenP<Op::NE, Op::NG, Op::NO> p, const NoiseP<T> nz, const Op op) {
   constexpr int NE = Op::NE, NG = Op::NG, NP = Op::NP, NO = Op::NO;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   T* sw = reinterpret_cast<T*>(smem_raw);
   T* su = sw + (size_t)p.rb * p.m;
 
@@ -169,7 +169,7 @@ template <typename T, typename Op, int SRC>
 __global__ void __launch_bounds__(kGenThreads)
 gen_cta_kernel(const GenP<Op::NE, Op::NG, Op::NO> p, const NoiseP<T> nz, const Op op) {
   constexpr int NE = Op::NE, NG = Op::NG, NP = Op::NP, NO = Op::NO;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   const int m = (int)p.m, mq = p.mq, rw = p.rb;  // rb = rows per group here
   const int mq_shift = __ffs(mq) - 1;
@@ -282,6 +282,306 @@ gen_cta_kernel(const GenP<Op::NE, Op::NG, Op::NO> p, const NoiseP<T> nz, const O
   if (!synced) __syncthreads();
 }
 
+// ---- TMA-staged persistent path (large batches) -------------------------------------------------
+// For g tensors much larger than what one wave of small CTAs keeps in flight, the tile stream is
+// driven by the copy engine instead of by per-thread loads: a persistent CTA owns a contiguous
+// range of row groups ("tiles": rs rows, i.e. rs*d*m contiguous elements of every g operand and
+// rs*d of every element-wise operand) and keeps kTmaStages tiles in flight with 1-D bulk copies
+// (`cp.async.bulk.shared::cluster.global`, completion counted in bytes on an mbarrier per stage).
+// One elected thread arms the barrier and issues the copies; all threads wait on the barrier's
+// phase parity, contract out of shared memory with the same chunk -> lane mapping and summation
+// order as `gen_cta_kernel` (so both paths are bit-identical), and a single __syncthreads per tile
+// hands the stage back for refilling.  The next tile's Brownian increments are produced while the
+// current one is contracted (double-buffered in shared memory).
+constexpr int kTmaThreads = 256;
+constexpr int kTmaStages = 4;
+constexpr int kTmaUnroll = 4;
+
+struct TmaP {
+  int64_t n_tiles;
+  int32_t rs;            // rows per tile
+  uint32_t g_stride;     // bytes between the g operands of one stage (128-byte multiple)
+  uint32_t e_stride;     // bytes between the element-wise operands of one stage
+  uint32_t stage_stride; // bytes per stage
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* ptr) {
+  return (uint32_t)__cvta_generic_to_shared(ptr);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+template <bool EVICT_FIRST>
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar,
+                                         uint64_t policy) {
+  if (EVICT_FIRST) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+  } else {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+  }
+}
+
+template <typename T, typename Op, int SRC>
+__global__ void __launch_bounds__(kTmaThreads)
+gen_tma_kernel(const GenP<Op::NE, Op::NG, Op::NO> p, const NoiseP<T> nz, const Op op, const TmaP tp) {
+  constexpr int NE = Op::NE, NG = Op::NG, NP = Op::NP, NO = Op::NO;
+  constexpr bool kEvictFirst = streams_inputs<Op>::value;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);  // kTmaStages barriers in the first 128 bytes
+  unsigned char* stages = smem_raw + 128;
+  const int tid = threadIdx.x;
+  const int m = (int)p.m, mq = p.mq, d = (int)p.d, rs = tp.rs;
+  const int mq_shift = __ffs(mq) - 1;
+  T* sw = reinterpret_cast<T*>(stages + (size_t)kTmaStages * tp.stage_stride);  // 2 x (rs x m)
+  T* su = sw + 2 * rs * m;                                                       // 2 x (rs x m) if WANT_U
+  const int64_t t_begin = (tp.n_tiles * blockIdx.x) / gridDim.x;
+  const int64_t t_end = (tp.n_tiles * (blockIdx.x + 1)) / gridDim.x;
+  const int n_my = (int)(t_end - t_begin);
+  Key key{0u, 0u};
+  if (SRC == TSDE_SRC_COUNTER) key = load_key(nz.key);
+
+  auto rows_of = [&](int64_t t) -> int {
+    const int64_t left = p.rows - t * rs;
+    return left < rs ? (int)left : rs;
+  };
+  // Brownian increments of tile t -> buffer `buf` (one Philox quad per thread; rs * mq <= kTmaThreads)
+  auto make_noise = [&](int64_t t, int buf) {
+    const int nr = rows_of(t);
+    if (tid < nr * mq) {
+      const int r = tid >> mq_shift, q = tid & (mq - 1);
+      const int64_t row = t * rs + r;
+      T w[4], u[4];
+      if (SRC == TSDE_SRC_COUNTER) {
+        counter_noise<T, Op::WANT_U>(nz, key, (uint32_t)(row + nz.row_offset), (uint32_t)q, w, u);
+      } else {
+        ld4(nz.w + row * m + 4 * q, w);
+        if (Op::WANT_U) ld4(nz.u + row * m + 4 * q, u);
+      }
+      st4(sw + (buf * rs + r) * m + 4 * q, w);
+      if (Op::WANT_U) st4(su + (buf * rs + r) * m + 4 * q, u);
+    }
+  };
+  uint64_t policy = 0;
+  if (kEvictFirst) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+  auto issue = [&](int64_t t, int s) {  // elected thread only
+    const int nr = rows_of(t);
+    const uint32_t gb = (uint32_t)((size_t)nr * d * m * sizeof(T));
+    const uint32_t eb = (uint32_t)((size_t)nr * d * sizeof(T));
+    unsigned char* sp = stages + (size_t)s * tp.stage_stride;
+    mbar_arrive_expect_tx(&full[s], NG * gb + NE * eb);
+#pragma unroll
+    for (int i = 0; i < NG; ++i)
+      bulk_g2s<kEvictFirst>(sp + (size_t)i * tp.g_stride,
+                            reinterpret_cast<const T*>(p.g[i]) + t * rs * (int64_t)d * m, gb, &full[s], policy);
+#pragma unroll
+    for (int i = 0; i < NE; ++i)
+      bulk_g2s<false>(sp + (size_t)NG * tp.g_stride + (size_t)i * tp.e_stride,
+                      reinterpret_cast<const T*>(p.e[i]) + t * rs * (int64_t)d, eb, &full[s], 0);
+  };
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kTmaStages; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  // Programmatic dependent launch: counter-based increments do not depend on the predecessor.
+  if (SRC == TSDE_SRC_COUNTER && n_my > 0) make_noise(t_begin, 0);
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (SRC != TSDE_SRC_COUNTER && n_my > 0) make_noise(t_begin, 0);
+  __syncthreads();  // barriers initialised, increments of the first tile visible
+  if (tid == 0) {
+    for (int s = 0; s < kTmaStages && s < n_my; ++s) issue(t_begin + s, s);
+  }
+
+  const int mc = tid & (mq - 1);
+  const int slots_per_load = kTmaThreads >> mq_shift;
+  const int slot_init = tid >> mq_shift;
+  const int r_init = slot_init / d;
+  const int dd_init = slot_init - r_init * d;
+  for (int it = 0; it < n_my; ++it) {
+    const int s = it % kTmaStages;
+    const uint32_t parity = (uint32_t)((it / kTmaStages) & 1);
+    const int64_t t = t_begin + it;
+    const int nrows = rows_of(t);
+    const int total = nrows * d * mq;              // chunks (4 elements) in this tile
+    const int64_t slot0 = t * rs * (int64_t)d;     // first (row, d) slot of the tile
+    const T* swb = sw + (it & 1) * rs * m;
+    const T* sub = su + (it & 1) * rs * m;
+    const unsigned char* sp = stages + (size_t)s * tp.stage_stride;
+    mbar_wait(&full[s], parity);
+    int slot = slot_init, r = r_init, dd = dd_init;
+    for (int base = 0; base < total; base += kTmaThreads * kTmaUnroll) {  // CTA-uniform trip count
+      T gv[kTmaUnroll][NG][4];
+      T ev[kTmaUnroll][NE > 0 ? NE : 1];
+      int rr[kTmaUnroll], slots[kTmaUnroll];
+      bool valid[kTmaUnroll];
+#pragma unroll
+      for (int un = 0; un < kTmaUnroll; ++un) {
+        const int c = base + un * kTmaThreads + tid;
+        valid[un] = c < total;
+        rr[un] = r;
+        slots[un] = slot;
+#pragma unroll
+        for (int i = 0; i < NG; ++i) {
+          if (valid[un]) {
+            ld4(reinterpret_cast<const T*>(sp + (size_t)i * tp.g_stride) + 4 * c, gv[un][i]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) gv[un][i][j] = T(0);
+          }
+        }
+        if (valid[un] && mc == 0) {
+#pragma unroll
+          for (int i = 0; i < NE; ++i)
+            ev[un][i] = reinterpret_cast<const T*>(sp + (size_t)NG * tp.g_stride + (size_t)i * tp.e_stride)[slot];
+        }
+        slot += slots_per_load;
+        dd += slots_per_load;
+        while (dd >= d) { dd -= d; ++r; }
+      }
+#pragma unroll
+      for (int un = 0; un < kTmaUnroll; ++un) {
+        T part[NP];
+#pragma unroll
+        for (int k = 0; k < NP; ++k) part[k] = T(0);
+        T w4[4], u4[4];
+        const int rsel = valid[un] ? rr[un] : 0;
+        ld4(swb + rsel * m + 4 * mc, w4);
+        if (Op::WANT_U) ld4(sub + rsel * m + 4 * mc, u4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          T gj[NG];
+#pragma unroll
+          for (int i = 0; i < NG; ++i) gj[i] = gv[un][i][j];
+#pragma unroll
+          for (int k = 0; k < NP; ++k)
+            part[k] = fma(op.gval(k, gj), op.weight(k, w4[j], Op::WANT_U ? u4[j] : T(0)), part[k]);
+        }
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          if (off < mq) {  // uniform
+#pragma unroll
+            for (int k = 0; k < NP; ++k) part[k] = part[k] + __shfl_xor_sync(0xffffffffu, part[k], off);
+          }
+        }
+        if (valid[un] && mc == 0) {
+          T e[NE > 0 ? NE : 1], o[NO];
+#pragma unroll
+          for (int i = 0; i < NE; ++i) e[i] = ev[un][i];
+          op.combine(e, part, o);
+#pragma unroll
+          for (int i = 0; i < NO; ++i) reinterpret_cast<T*>(p.o[i])[slot0 + slots[un]] = o[i];
+        }
+      }
+    }
+    if (it + 1 < n_my) make_noise(t + 1, (it + 1) & 1);
+    __syncthreads();  // every thread is done with stage s and with the increments of tile `it`
+    if (tid == 0 && it + kTmaStages < n_my) issue(t + kTmaStages, s);
+  }
+}
+
+// 0: never, 1: when the batch is large enough to fill the pipeline (default), 2: whenever eligible.
+inline int gen_tma_mode() {
+  const char* e = getenv("TSDE_GEN_TMA");
+  if (!e) return 0;
+  if (e[0] == '0') return 0;
+  if (e[0] == '2' || e[0] == 'f') return 2;
+  return 1;
+}
+
+constexpr int kTmaNotEligible = -12345;
+
+// Per kernel instantiation: opt in to the dynamic shared memory once, and cache the occupancy.
+template <typename K>
+static int tma_resident_ctas(K kernel, size_t smem) {
+  static std::mutex mu;
+  static std::unordered_map<const void*, std::pair<size_t, int>> cache;  // kernel -> (smem opted in, CTAs/SM)
+  const void* id = reinterpret_cast<const void*>(kernel);
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(id);
+  if (it != cache.end() && it->second.first == smem) return it->second.second;
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kTmaThreads, smem) != cudaSuccess) {
+    cudaGetLastError();
+    n = 0;
+  }
+  cache[id] = std::make_pair(smem, n);
+  return n;
+}
+
+template <typename T, typename Op>
+static int launch_gen_tma(const tsde_launch* L, const tsde_noise* nz, GenP<Op::NE, Op::NG, Op::NO> p,
+                          const NoiseP<T>& np, const Op& op, int mode, cudaStream_t st) {
+  // Eligibility: bulk copies need 16-byte aligned, 16-byte-multiple extents for every operand tile.
+  if (L->d % 4 != 0) return kTmaNotEligible;
+  for (int i = 0; i < Op::NE; ++i) if (!aligned16(p.e[i])) return kTmaNotEligible;
+  const int64_t mq = L->m / 4;
+  const size_t row_bytes = (size_t)L->d * L->m * sizeof(T);
+  constexpr size_t kStageTarget = 24 * 1024;  // bytes of g per stage (all NG operands)
+  if (Op::NG * row_bytes > 32 * 1024) return kTmaNotEligible;
+  int64_t rs = (int64_t)(kStageTarget / (Op::NG * row_bytes));
+  if (rs < 1) rs = 1;
+  if (rs > kTmaThreads / mq) rs = kTmaThreads / mq;
+  auto up128 = [](size_t x) { return (x + 127) & ~(size_t)127; };
+  TmaP tp{};
+  tp.rs = (int32_t)rs;
+  tp.g_stride = (uint32_t)up128((size_t)rs * row_bytes);
+  tp.e_stride = (uint32_t)up128((size_t)rs * L->d * sizeof(T));
+  tp.stage_stride = (uint32_t)(Op::NG * tp.g_stride + Op::NE * tp.e_stride);
+  tp.n_tiles = (L->rows + rs - 1) / rs;
+  const size_t smem = 128 + (size_t)kTmaStages * tp.stage_stride +
+                      2 * (size_t)rs * L->m * sizeof(T) * (Op::WANT_U ? 2 : 1);
+  if (smem > 200 * 1024) return kTmaNotEligible;
+  p.rb = (int32_t)rs;
+  auto go = [&](auto kernel) -> int {
+    const int resident = tma_resident_ctas(kernel, smem);
+    if (resident < 1) return kTmaNotEligible;
+    const int64_t cap = (int64_t)sm_count() * resident;
+    if (mode < 2 && tp.n_tiles < 2 * kTmaStages * cap) return kTmaNotEligible;  // too small to fill the pipeline
+    const int64_t blocks = tp.n_tiles < cap ? tp.n_tiles : cap;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)blocks);
+    cfg.blockDim = dim3(kTmaThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return (int)cudaLaunchKernelEx(&cfg, kernel, p, np, op, tp);
+  };
+  if (nz->source == TSDE_SRC_MEMORY) return go(gen_tma_kernel<T, Op, TSDE_SRC_MEMORY>);
+  return go(gen_tma_kernel<T, Op, TSDE_SRC_COUNTER>);
+}
+
 template <typename T, typename Op>
 static int launch_gen(const tsde_launch* L, const tsde_noise* nz,
                       std::initializer_list<const void*> es, std::initializer_list<const void*> gs,
@@ -308,6 +608,10 @@ static int launch_gen(const tsde_launch* L, const tsde_noise* nz,
   if (L->rows + nz->row_offset > 0xFFFFFFFFll) return TSDE_EINVAL;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(L->stream);
   if (vec) {
+    if (int mode = gen_tma_mode()) {
+      int rc = launch_gen_tma<T, Op>(L, nz, p, np, op, mode, st);
+      if (rc != kTmaNotEligible) return rc;
+    }
     // one 128-thread CTA per group of rw rows
     const int64_t rw = 32 / mq;
     p.rb = (int32_t)rw;
