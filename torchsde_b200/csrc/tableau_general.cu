@@ -288,11 +288,12 @@ gen_cta_kernel(const GenP<Op::NE, Op::NG, Op::NO> p, const NoiseP<T> nz, const O
 // range of row groups ("tiles": rs rows, i.e. rs*d*m contiguous elements of every g operand and
 // rs*d of every element-wise operand) and keeps kTmaStages tiles in flight with 1-D bulk copies
 // (`cp.async.bulk.shared::cluster.global`, completion counted in bytes on an mbarrier per stage).
-// One elected thread arms the barrier and issues the copies; all threads wait on the barrier's
-// phase parity, contract out of shared memory with the same chunk -> lane mapping and summation
-// order as `gen_cta_kernel` (so both paths are bit-identical), and a single __syncthreads per tile
-// hands the stage back for refilling.  The next tile's Brownian increments are produced while the
-// current one is contracted (double-buffered in shared memory).
+// Warp-specialised: a producer warp arms each stage's `full` barrier, issues the copies (one lane)
+// and produces the tile's Brownian increments into the same stage (all lanes, Philox in registers);
+// eight consumer warps wait on the barrier's phase parity, contract out of shared memory with the
+// same chunk -> lane mapping and summation order as `gen_cta_kernel` (so both paths are
+// bit-identical), and hand the stage back through an `empty` barrier (one arrive per warp).  There
+// is no CTA-wide barrier in the steady state.
 constexpr int kTmaThreads = 256;
 constexpr int kTmaStages = 4;
 constexpr int kTmaUnroll = 4;
@@ -302,6 +303,8 @@ struct TmaP {
   int32_t rs;            // rows per tile
   uint32_t g_stride;     // bytes between the g operands of one stage (128-byte multiple)
   uint32_t e_stride;     // bytes between the element-wise operands of one stage
+  uint32_t w_stride;     // bytes of one increment buffer (rs x m elements, 128-byte multiple)
+  int32_t d_shift;       // log2(d)
   uint32_t stage_stride; // bytes per stage
 };
 
@@ -315,6 +318,9 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done;
@@ -327,6 +333,28 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(addr), "r"(parity)
         : "memory");
   } while (!done);
+}
+__device__ __forceinline__ void lds4(uint32_t addr, float (&v)[4]) {
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr));
+}
+__device__ __forceinline__ void lds4(uint32_t addr, double (&v)[4]) {
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "r"(addr));
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v[2]), "=d"(v[3]) : "r"(addr + 16u));
+}
+template <typename T>
+__device__ __forceinline__ T lds1(uint32_t addr);
+template <>
+__device__ __forceinline__ float lds1<float>(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+template <>
+__device__ __forceinline__ double lds1<double>(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
 }
 template <bool EVICT_FIRST>
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar,
@@ -343,134 +371,147 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
   }
 }
 
-template <typename T, typename Op, int SRC>
-__global__ void __launch_bounds__(kTmaThreads)
+template <typename T, typename Op, int SRC, int MQ_SHIFT>
+__global__ void __launch_bounds__(kTmaThreads + 32)
 gen_tma_kernel(const GenP<Op::NE, Op::NG, Op::NO> p, const NoiseP<T> nz, const Op op, const TmaP tp) {
   constexpr int NE = Op::NE, NG = Op::NG, NP = Op::NP, NO = Op::NO;
   constexpr bool kEvictFirst = streams_inputs<Op>::value;
+  constexpr int kConsumerWarps = kTmaThreads / 32;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);  // kTmaStages barriers in the first 128 bytes
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);  // [kTmaStages] tile + increments have landed
+  uint64_t* empty = full + kTmaStages;                      // [kTmaStages] every consumer warp is done
   unsigned char* stages = smem_raw + 128;
   const int tid = threadIdx.x;
-  const int m = (int)p.m, mq = p.mq, d = (int)p.d, rs = tp.rs;
-  const int mq_shift = __ffs(mq) - 1;
-  T* sw = reinterpret_cast<T*>(stages + (size_t)kTmaStages * tp.stage_stride);  // 2 x (rs x m)
-  T* su = sw + 2 * rs * m;                                                       // 2 x (rs x m) if WANT_U
+  const int warp = tid >> 5, lane = tid & 31;
+  constexpr int mq = 1 << MQ_SHIFT, mq_shift = MQ_SHIFT;  // m / 4, compile-time: the shuffle tree is static
+  const int m = (int)p.m, d = (int)p.d, rs = tp.rs;
+  const int d_shift = tp.d_shift;                          // d is a power of two on this path
   const int64_t t_begin = (tp.n_tiles * blockIdx.x) / gridDim.x;
   const int64_t t_end = (tp.n_tiles * (blockIdx.x + 1)) / gridDim.x;
   const int n_my = (int)(t_end - t_begin);
-  Key key{0u, 0u};
-  if (SRC == TSDE_SRC_COUNTER) key = load_key(nz.key);
-
   auto rows_of = [&](int64_t t) -> int {
     const int64_t left = p.rows - t * rs;
     return left < rs ? (int)left : rs;
   };
-  // Brownian increments of tile t -> buffer `buf` (one Philox quad per thread; rs * mq <= kTmaThreads)
-  auto make_noise = [&](int64_t t, int buf) {
-    const int nr = rows_of(t);
-    if (tid < nr * mq) {
-      const int r = tid >> mq_shift, q = tid & (mq - 1);
-      const int64_t row = t * rs + r;
-      T w[4], u[4];
-      if (SRC == TSDE_SRC_COUNTER) {
-        counter_noise<T, Op::WANT_U>(nz, key, (uint32_t)(row + nz.row_offset), (uint32_t)q, w, u);
-      } else {
-        ld4(nz.w + row * m + 4 * q, w);
-        if (Op::WANT_U) ld4(nz.u + row * m + 4 * q, u);
-      }
-      st4(sw + (buf * rs + r) * m + 4 * q, w);
-      if (Op::WANT_U) st4(su + (buf * rs + r) * m + 4 * q, u);
-    }
-  };
-  uint64_t policy = 0;
-  if (kEvictFirst) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-  auto issue = [&](int64_t t, int s) {  // elected thread only
-    const int nr = rows_of(t);
-    const uint32_t gb = (uint32_t)((size_t)nr * d * m * sizeof(T));
-    const uint32_t eb = (uint32_t)((size_t)nr * d * sizeof(T));
-    unsigned char* sp = stages + (size_t)s * tp.stage_stride;
-    mbar_arrive_expect_tx(&full[s], NG * gb + NE * eb);
-#pragma unroll
-    for (int i = 0; i < NG; ++i)
-      bulk_g2s<kEvictFirst>(sp + (size_t)i * tp.g_stride,
-                            reinterpret_cast<const T*>(p.g[i]) + t * rs * (int64_t)d * m, gb, &full[s], policy);
-#pragma unroll
-    for (int i = 0; i < NE; ++i)
-      bulk_g2s<false>(sp + (size_t)NG * tp.g_stride + (size_t)i * tp.e_stride,
-                      reinterpret_cast<const T*>(p.e[i]) + t * rs * (int64_t)d, eb, &full[s], 0);
-  };
+  // stage layout: NG g tiles | NE element-wise tiles | increments W (rs x m) | U (rs x m, if wanted)
+  auto stage_ptr = [&](int s) -> unsigned char* { return stages + (size_t)s * tp.stage_stride; };
+  const uint32_t w_off = NG * tp.g_stride + NE * tp.e_stride;
+  const uint32_t u_off = w_off + tp.w_stride;
 
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < kTmaStages; ++s) mbar_init(&full[s], 1);
+    for (int s = 0; s < kTmaStages; ++s) {
+      mbar_init(&full[s], 2);                 // the copy-issuing arrive (+ its byte count) and the increments' arrive
+      mbar_init(&empty[s], kConsumerWarps);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  // Programmatic dependent launch: counter-based increments do not depend on the predecessor.
-  if (SRC == TSDE_SRC_COUNTER && n_my > 0) make_noise(t_begin, 0);
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  if (SRC != TSDE_SRC_COUNTER && n_my > 0) make_noise(t_begin, 0);
-  __syncthreads();  // barriers initialised, increments of the first tile visible
-  if (tid == 0) {
-    for (int s = 0; s < kTmaStages && s < n_my; ++s) issue(t_begin + s, s);
+  __syncthreads();
+
+  if (warp == kConsumerWarps) {
+    // ---------------- producer warp: bulk copies (lane 0) and Brownian increments (all lanes) ----------
+    Key key{0u, 0u};
+    if (SRC == TSDE_SRC_COUNTER) key = load_key(nz.key);
+    uint64_t policy = 0;
+    if (kEvictFirst) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    bool waited = false;  // griddepcontrol.wait once, before the first read of global memory
+    for (int it = 0; it < n_my; ++it) {
+      const int s = it % kTmaStages;
+      const int64_t t = t_begin + it;
+      const int nr = rows_of(t);
+      unsigned char* sp = stage_ptr(s);
+      if (it >= kTmaStages) mbar_wait(&empty[s], (uint32_t)(((it / kTmaStages) - 1) & 1));
+      if (!waited) { asm volatile("griddepcontrol.wait;" ::: "memory"); waited = true; }
+      // copies first (asynchronous), then the increments while the bytes are in flight
+      if (lane == 0) {
+        const uint32_t gb = (uint32_t)((size_t)nr * d * m * sizeof(T));
+        const uint32_t eb = (uint32_t)((size_t)nr * d * sizeof(T));
+        mbar_arrive_expect_tx(&full[s], NG * gb + NE * eb);
+#pragma unroll
+        for (int i = 0; i < NG; ++i)
+          bulk_g2s<kEvictFirst>(sp + (size_t)i * tp.g_stride,
+                                reinterpret_cast<const T*>(p.g[i]) + t * rs * (int64_t)d * m, gb, &full[s], policy);
+#pragma unroll
+        for (int i = 0; i < NE; ++i)
+          bulk_g2s<false>(sp + (size_t)NG * tp.g_stride + (size_t)i * tp.e_stride,
+                          reinterpret_cast<const T*>(p.e[i]) + t * rs * (int64_t)d, eb, &full[s], 0);
+      }
+      T* swb = reinterpret_cast<T*>(sp + w_off);
+      T* sub = reinterpret_cast<T*>(sp + u_off);
+      for (int i = lane; i < nr * mq; i += 32) {  // one Philox quad per lane and pass
+        const int r = i >> mq_shift, q = i & (mq - 1);
+        const int64_t row = t * rs + r;
+        T w[4], u[4];
+        if (SRC == TSDE_SRC_COUNTER) {
+          counter_noise<T, Op::WANT_U>(nz, key, (uint32_t)(row + nz.row_offset), (uint32_t)q, w, u);
+        } else {
+          ld4(nz.w + row * m + 4 * q, w);
+          if (Op::WANT_U) ld4(nz.u + row * m + 4 * q, u);
+        }
+        st4(swb + r * m + 4 * q, w);
+        if (Op::WANT_U) st4(sub + r * m + 4 * q, u);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[s]);  // increments written (ordered by __syncwarp; arrive releases)
+    }
+    return;
   }
 
+  // ---------------- consumer warps: contract out of shared memory, combine, store ----------------------
+  // Chunk c (4 consecutive elements of the tile, c = pass * 256 + tid) belongs to (row, d) slot c >> MQ_SHIFT
+  // and to row slot >> d_shift of the tile: no divisions, no per-chunk bookkeeping.  Shared memory is
+  // addressed with 32-bit shared-window addresses.
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // the predecessor's reads of our outputs are complete
   const int mc = tid & (mq - 1);
-  const int slots_per_load = kTmaThreads >> mq_shift;
-  const int slot_init = tid >> mq_shift;
-  const int r_init = slot_init / d;
-  const int dd_init = slot_init - r_init * d;
+  const uint32_t stage0_addr = smem_u32(stages);
+  const uint32_t g_lane_off = (uint32_t)tid * 4u * (uint32_t)sizeof(T);
   for (int it = 0; it < n_my; ++it) {
     const int s = it % kTmaStages;
-    const uint32_t parity = (uint32_t)((it / kTmaStages) & 1);
     const int64_t t = t_begin + it;
     const int nrows = rows_of(t);
-    const int total = nrows * d * mq;              // chunks (4 elements) in this tile
-    const int64_t slot0 = t * rs * (int64_t)d;     // first (row, d) slot of the tile
-    const T* swb = sw + (it & 1) * rs * m;
-    const T* sub = su + (it & 1) * rs * m;
-    const unsigned char* sp = stages + (size_t)s * tp.stage_stride;
-    mbar_wait(&full[s], parity);
-    int slot = slot_init, r = r_init, dd = dd_init;
-    for (int base = 0; base < total; base += kTmaThreads * kTmaUnroll) {  // CTA-uniform trip count
+    const int total = (nrows << d_shift) << mq_shift;   // chunks in this tile
+    const int64_t slot0 = (t * rs) << d_shift;          // first (row, d) slot of the tile
+    const uint32_t sp = stage0_addr + (uint32_t)s * tp.stage_stride;
+    const uint32_t e_addr = sp + NG * tp.g_stride;
+    const uint32_t w_addr = sp + w_off + (uint32_t)(4 * mc) * (uint32_t)sizeof(T);
+    const uint32_t u_addr = w_addr + tp.w_stride;
+    mbar_wait(&full[s], (uint32_t)((it / kTmaStages) & 1));
+    for (int base = 0; base < total; base += kTmaThreads * kTmaUnroll) {  // warp-uniform trip count
       T gv[kTmaUnroll][NG][4];
       T ev[kTmaUnroll][NE > 0 ? NE : 1];
-      int rr[kTmaUnroll], slots[kTmaUnroll];
       bool valid[kTmaUnroll];
 #pragma unroll
       for (int un = 0; un < kTmaUnroll; ++un) {
         const int c = base + un * kTmaThreads + tid;
         valid[un] = c < total;
-        rr[un] = r;
-        slots[un] = slot;
+        const uint32_t goff = (uint32_t)(base + un * kTmaThreads) * 4u * (uint32_t)sizeof(T) + g_lane_off;
 #pragma unroll
         for (int i = 0; i < NG; ++i) {
           if (valid[un]) {
-            ld4(reinterpret_cast<const T*>(sp + (size_t)i * tp.g_stride) + 4 * c, gv[un][i]);
+            lds4(sp + (uint32_t)i * tp.g_stride + goff, gv[un][i]);
           } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j) gv[un][i][j] = T(0);
           }
         }
         if (valid[un] && mc == 0) {
+          const uint32_t slot = (uint32_t)c >> mq_shift;
 #pragma unroll
-          for (int i = 0; i < NE; ++i)
-            ev[un][i] = reinterpret_cast<const T*>(sp + (size_t)NG * tp.g_stride + (size_t)i * tp.e_stride)[slot];
+          for (int i = 0; i < NE; ++i) ev[un][i] = lds1<T>(e_addr + (uint32_t)i * tp.e_stride + slot * (uint32_t)sizeof(T));
         }
-        slot += slots_per_load;
-        dd += slots_per_load;
-        while (dd >= d) { dd -= d; ++r; }
       }
 #pragma unroll
       for (int un = 0; un < kTmaUnroll; ++un) {
+        const int c = base + un * kTmaThreads + tid;
+        const uint32_t slot = (uint32_t)c >> mq_shift;
+        const uint32_t rsel = valid[un] ? (slot >> d_shift) : 0u;
         T part[NP];
 #pragma unroll
         for (int k = 0; k < NP; ++k) part[k] = T(0);
         T w4[4], u4[4];
-        const int rsel = valid[un] ? rr[un] : 0;
-        ld4(swb + rsel * m + 4 * mc, w4);
-        if (Op::WANT_U) ld4(sub + rsel * m + 4 * mc, u4);
+        lds4(w_addr + rsel * (uint32_t)m * (uint32_t)sizeof(T), w4);
+        if (Op::WANT_U) lds4(u_addr + rsel * (uint32_t)m * (uint32_t)sizeof(T), u4);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           T gj[NG];
@@ -481,11 +522,9 @@ gen_tma_kernel(const GenP<Op::NE, Op::NG, Op::NO> p, const NoiseP<T> nz, const O
             part[k] = fma(op.gval(k, gj), op.weight(k, w4[j], Op::WANT_U ? u4[j] : T(0)), part[k]);
         }
 #pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-          if (off < mq) {  // uniform
+        for (int off = 1; off < mq; off <<= 1) {
 #pragma unroll
-            for (int k = 0; k < NP; ++k) part[k] = part[k] + __shfl_xor_sync(0xffffffffu, part[k], off);
-          }
+          for (int k = 0; k < NP; ++k) part[k] = part[k] + __shfl_xor_sync(0xffffffffu, part[k], off);
         }
         if (valid[un] && mc == 0) {
           T e[NE > 0 ? NE : 1], o[NO];
@@ -493,20 +532,25 @@ gen_tma_kernel(const GenP<Op::NE, Op::NG, Op::NO> p, const NoiseP<T> nz, const O
           for (int i = 0; i < NE; ++i) e[i] = ev[un][i];
           op.combine(e, part, o);
 #pragma unroll
-          for (int i = 0; i < NO; ++i) reinterpret_cast<T*>(p.o[i])[slot0 + slots[un]] = o[i];
+          for (int i = 0; i < NO; ++i) reinterpret_cast<T*>(p.o[i])[slot0 + slot] = o[i];
         }
       }
     }
-    if (it + 1 < n_my) make_noise(t + 1, (it + 1) & 1);
-    __syncthreads();  // every thread is done with stage s and with the increments of tile `it`
-    if (tid == 0 && it + kTmaStages < n_my) issue(t + kTmaStages, s);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);  // this warp no longer reads stage s
   }
 }
 
-// 0: never, 1: when the batch is large enough to fill the pipeline (default), 2: whenever eligible.
-inline int gen_tma_mode() {
+// Which launches take the TMA-staged kernel (TSDE_GEN_TMA):
+//   unset  m = 64 only, when the batch fills the pipeline — the one regime where it measurably beats the
+//          per-thread-load kernel (B=65536, d=32, m=64: 92 us vs 111 us, 93 % vs 77 % of the HBM peak; for m = 16
+//          the two tie at 87 % for one g operand and the per-thread-load kernel wins 100 % vs 97 % for two;
+//          profiles/r01_gen_tma_ab.log);
+//   0      never;   1  every eligible shape when the batch fills the pipeline;   2  every eligible shape.
+// Both kernels are bit-identical (tests/test_gpu_general_tma.py), so the choice never changes results.
+inline int gen_tma_mode(int64_t mq) {
   const char* e = getenv("TSDE_GEN_TMA");
-  if (!e) return 0;
+  if (!e) return mq == 16 ? 1 : 0;
   if (e[0] == '0') return 0;
   if (e[0] == '2' || e[0] == 'f') return 2;
   return 1;
@@ -528,7 +572,7 @@ static int tma_resident_ctas(K kernel, size_t smem) {
     return 0;
   }
   int n = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kTmaThreads, smem) != cudaSuccess) {
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kTmaThreads + 32, smem) != cudaSuccess) {
     cudaGetLastError();
     n = 0;
   }
@@ -540,24 +584,32 @@ template <typename T, typename Op>
 static int launch_gen_tma(const tsde_launch* L, const tsde_noise* nz, GenP<Op::NE, Op::NG, Op::NO> p,
                           const NoiseP<T>& np, const Op& op, int mode, cudaStream_t st) {
   // Eligibility: bulk copies need 16-byte aligned, 16-byte-multiple extents for every operand tile.
-  if (L->d % 4 != 0) return kTmaNotEligible;
+  if (L->d % 4 != 0 || (L->d & (L->d - 1)) != 0 || L->d > (1 << 20)) return kTmaNotEligible;  // d = 2^k >= 4
   for (int i = 0; i < Op::NE; ++i) if (!aligned16(p.e[i])) return kTmaNotEligible;
   const int64_t mq = L->m / 4;
+  if (mq != 2 && mq != 4 && mq != 8 && mq != 16) return kTmaNotEligible;  // instantiated shuffle trees
   const size_t row_bytes = (size_t)L->d * L->m * sizeof(T);
-  constexpr size_t kStageTarget = 24 * 1024;  // bytes of g per stage (all NG operands)
-  if (Op::NG * row_bytes > 32 * 1024) return kTmaNotEligible;
+  // 16 KiB of every g operand per stage: measured optimum (three resident CTAs for one operand; with two
+  // operands a single resident CTA already streams at 97 % of the HBM peak)
+  size_t kStageTarget = (size_t)Op::NG * 16 * 1024;
+  if (const char* e = getenv("TSDE_GEN_TMA_KB")) {  // tuning knob, KiB per operand (profiles/gen_tma_ab.py)
+    const long kb = atol(e);
+    if (kb >= 1 && kb <= 48) kStageTarget = (size_t)Op::NG * kb * 1024;
+  }
+  if (Op::NG * row_bytes > 32 * 1024 && Op::NG * row_bytes > kStageTarget) return kTmaNotEligible;
   int64_t rs = (int64_t)(kStageTarget / (Op::NG * row_bytes));
   if (rs < 1) rs = 1;
   if (rs > kTmaThreads / mq) rs = kTmaThreads / mq;
   auto up128 = [](size_t x) { return (x + 127) & ~(size_t)127; };
   TmaP tp{};
   tp.rs = (int32_t)rs;
+  for (tp.d_shift = 0; (1ll << tp.d_shift) < L->d; ++tp.d_shift) {}
   tp.g_stride = (uint32_t)up128((size_t)rs * row_bytes);
   tp.e_stride = (uint32_t)up128((size_t)rs * L->d * sizeof(T));
-  tp.stage_stride = (uint32_t)(Op::NG * tp.g_stride + Op::NE * tp.e_stride);
+  tp.w_stride = (uint32_t)up128((size_t)rs * L->m * sizeof(T));
+  tp.stage_stride = (uint32_t)(Op::NG * tp.g_stride + Op::NE * tp.e_stride + (Op::WANT_U ? 2 : 1) * tp.w_stride);
   tp.n_tiles = (L->rows + rs - 1) / rs;
-  const size_t smem = 128 + (size_t)kTmaStages * tp.stage_stride +
-                      2 * (size_t)rs * L->m * sizeof(T) * (Op::WANT_U ? 2 : 1);
+  const size_t smem = 128 + (size_t)kTmaStages * tp.stage_stride;
   if (smem > 200 * 1024) return kTmaNotEligible;
   p.rb = (int32_t)rs;
   auto go = [&](auto kernel) -> int {
@@ -568,7 +620,7 @@ static int launch_gen_tma(const tsde_launch* L, const tsde_noise* nz, GenP<Op::N
     const int64_t blocks = tp.n_tiles < cap ? tp.n_tiles : cap;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)blocks);
-    cfg.blockDim = dim3(kTmaThreads);
+    cfg.blockDim = dim3(kTmaThreads + 32);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -578,8 +630,13 @@ static int launch_gen_tma(const tsde_launch* L, const tsde_noise* nz, GenP<Op::N
     cfg.numAttrs = 1;
     return (int)cudaLaunchKernelEx(&cfg, kernel, p, np, op, tp);
   };
-  if (nz->source == TSDE_SRC_MEMORY) return go(gen_tma_kernel<T, Op, TSDE_SRC_MEMORY>);
-  return go(gen_tma_kernel<T, Op, TSDE_SRC_COUNTER>);
+  const bool mem = nz->source == TSDE_SRC_MEMORY;
+  switch (mq) {
+    case 2: return mem ? go(gen_tma_kernel<T, Op, TSDE_SRC_MEMORY, 1>) : go(gen_tma_kernel<T, Op, TSDE_SRC_COUNTER, 1>);
+    case 4: return mem ? go(gen_tma_kernel<T, Op, TSDE_SRC_MEMORY, 2>) : go(gen_tma_kernel<T, Op, TSDE_SRC_COUNTER, 2>);
+    case 8: return mem ? go(gen_tma_kernel<T, Op, TSDE_SRC_MEMORY, 3>) : go(gen_tma_kernel<T, Op, TSDE_SRC_COUNTER, 3>);
+    default: return mem ? go(gen_tma_kernel<T, Op, TSDE_SRC_MEMORY, 4>) : go(gen_tma_kernel<T, Op, TSDE_SRC_COUNTER, 4>);
+  }
 }
 
 template <typename T, typename Op>
@@ -608,7 +665,7 @@ static int launch_gen(const tsde_launch* L, const tsde_noise* nz,
   if (L->rows + nz->row_offset > 0xFFFFFFFFll) return TSDE_EINVAL;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(L->stream);
   if (vec) {
-    if (int mode = gen_tma_mode()) {
+    if (int mode = gen_tma_mode(mq)) {
       int rc = launch_gen_tma<T, Op>(L, nz, p, np, op, mode, st);
       if (rc != kTmaNotEligible) return rc;
     }
