@@ -100,6 +100,11 @@ typedef struct tsde_noise {
 int tsde_abi_version(void);
 /* Last CUDA error string of this library's runtime instance (for diagnostics). */
 const char* tsde_error_string(int code);
+/* Diagnostics: how many launches of a kernel family this process has issued so far (tests use it to
+   check which general-noise tile kernel a shape was routed to). */
+#define TSDE_KERNEL_GEN_CTA 0  /* per-thread-load tile kernel                       */
+#define TSDE_KERNEL_GEN_TMA 1  /* TMA-staged persistent tile kernel (bulk copies)   */
+int64_t tsde_kernel_launches(int32_t family);
 
 /* ------------------------------------------------------------------------ */
 /* Brownian source  (replaces torchsde/_brownian/brownian_interval.py)       */

@@ -36,15 +36,21 @@ def _solve(method, sde_type, kind, B, d, m, dtype, levy, materialise, graph=Fals
 
 
 CASES = [
-    # method, sde_type, problem kind, B, d, m, levy
+    # method, sde_type, problem kind, B, d, m, levy       (eligible: d a power of two >= 4, m in {8, 16, 32, 64})
     ('euler', 'ito', 'general', 1000, 32, 16, 'none'),
     ('heun', 'stratonovich', 'general', 777, 64, 16, 'none'),          # ragged last tile, two g operands
-    ('midpoint', 'stratonovich', 'general', 513, 8, 4, 'none'),
-    ('euler_heun', 'stratonovich', 'general', 300, 12, 32, 'none'),
+    ('midpoint', 'stratonovich', 'general', 513, 8, 8, 'none'),
+    ('euler_heun', 'stratonovich', 'general', 300, 16, 32, 'none'),
     ('reversible_heun', 'stratonovich', 'general', 260, 16, 8, 'none'),
     ('srk', 'ito', 'additive', 515, 32, 16, 'space-time'),              # (W, U) weights
-    ('euler', 'ito', 'general', 3, 4, 128, 'none'),                     # fewer tiles than stages
+    ('euler', 'ito', 'general', 3, 4, 64, 'none'),                      # fewer tiles than stages
+    ('euler', 'ito', 'general', 2100, 128, 64, 'none'),                 # one 32 KiB row per stage
 ]
+
+
+def _launches(family):
+    from torchsde_b200 import _cabi
+    return _cabi.lib().tsde_kernel_launches(family)
 
 
 @pytest.mark.parametrize('dtype', [torch.float32, torch.float64], ids=['f32', 'f64'])
@@ -53,11 +59,45 @@ CASES = [
 def test_tma_path_bit_identical(case, materialise, dtype, monkeypatch):
     method, sde_type, kind, B, d, m, levy = case
     monkeypatch.setenv('TSDE_GEN_TMA', '0')
+    n_tma = _launches(1)
     base = _solve(method, sde_type, kind, B, d, m, dtype, levy, materialise)
+    assert _launches(1) == n_tma, "TSDE_GEN_TMA=0 must keep the per-thread-load kernel"
     monkeypatch.setenv('TSDE_GEN_TMA', '2')
+    n_cta = _launches(0)
     tma = _solve(method, sde_type, kind, B, d, m, dtype, levy, materialise)
+    if d * m * base.element_size() <= 32 * 1024:  # (fp64 rows of 64 KiB exceed a stage: stays on the default kernel)
+        assert _launches(1) > n_tma and _launches(0) == n_cta, "shape was not routed to the TMA-staged kernel"
     assert torch.isfinite(base).all()
     assert torch.equal(base, tma), f"max abs diff {(base - tma).abs().max().item()}"
+
+
+def test_default_routing(monkeypatch):
+    """Without TSDE_GEN_TMA: m = 64 goes to the TMA-staged kernel once the batch fills the pipeline, m = 16 never."""
+    import ctypes
+    from torchsde_b200 import _cabi
+    monkeypatch.delenv('TSDE_GEN_TMA', raising=False)
+    dev = torch.device('cuda')
+    lib = _cabi.lib()
+    key = torch.tensor([7], dtype=torch.int64, device=dev)
+    for (B, D, M), expect_tma in (((65536, 32, 64), True), ((256, 32, 64), False), ((65536, 32, 16), False)):
+        L = _cabi.make_launch(torch.float32, _cabi.NOISE_GENERAL, B, D, M)
+        nz = _cabi.Noise()
+        nz.source, nz.key, nz.cell_id, nz.n_cells, nz.h, nz.h_total = _cabi.SRC_COUNTER, key.data_ptr(), 5, 1, 0.01, 0.01
+        y, f, g = torch.rand(B, D, device=dev), torch.rand(B, D, device=dev), torch.rand(B, D, M, device=dev)
+        outs = []
+        for mode in (None, '0'):
+            if mode is None:
+                monkeypatch.delenv('TSDE_GEN_TMA', raising=False)
+            else:
+                monkeypatch.setenv('TSDE_GEN_TMA', mode)
+            o = torch.empty(B, D, device=dev)
+            before = lib.tsde_kernel_launches(1)
+            _cabi.check(lib.tsde_step_euler(ctypes.byref(L), ctypes.byref(nz), y.data_ptr(), f.data_ptr(),
+                                            g.data_ptr(), 0.01, o.data_ptr()), 'tsde_step_euler')
+            if mode is None:
+                assert (lib.tsde_kernel_launches(1) > before) == expect_tma, (B, D, M)
+            outs.append(o)
+        assert torch.equal(outs[0], outs[1])
 
 
 def test_tma_path_in_cuda_graph(monkeypatch):

@@ -92,6 +92,8 @@ def lib():
     handle.tsde_abi_version.restype = ctypes.c_int
     handle.tsde_error_string.restype = ctypes.c_char_p
     handle.tsde_error_string.argtypes = [ctypes.c_int]
+    handle.tsde_kernel_launches.restype = ctypes.c_int64
+    handle.tsde_kernel_launches.argtypes = [ctypes.c_int32]
     for name, argtypes in SIGNATURES.items():
         fn = getattr(handle, name)  # AttributeError here = header/library mismatch: fail loudly
         fn.restype = ctypes.c_int

@@ -19,6 +19,7 @@ int tsde_diag_step_reversible_heun(const tsde_launch*, const tsde_noise*, const 
 int tsde_diag_adjoint_reversible_heun_a(const tsde_launch*, const tsde_noise*, const void*, const void*, const void*, const void*, const void*, const void*, const void*, double, double, void*, void*, void*);
 int tsde_diag_adjoint_reversible_heun_b(const tsde_launch*, const tsde_noise*, const void*, const void*, const void*, const void*, const void*, const void*, const void*, const void*, double, double, void*, void*, void*, void*, void*);
 // tableau_general.cu
+int64_t tsde_general_kernel_launches(int32_t);
 int tsde_general_step_euler(const tsde_launch*, const tsde_noise*, const void*, const void*, const void*, double, void*);
 int tsde_general_step_heun(const tsde_launch*, const tsde_noise*, const void*, const void*, const void*, const void*, const void*, double, void*);
 int tsde_general_midpoint_predict(const tsde_launch*, const tsde_noise*, const void*, const void*, const void*, double, void*);
@@ -42,6 +43,8 @@ static inline bool bad(const tsde_launch* L) {
 extern "C" {
 
 int tsde_abi_version(void) { return TSDE_ABI_VERSION; }
+
+int64_t tsde_kernel_launches(int32_t family) { return tsde_general_kernel_launches(family); }
 
 const char* tsde_error_string(int code) {
   if (code == TSDE_EINVAL) return "torchsde_b200: invalid argument (contract violation)";

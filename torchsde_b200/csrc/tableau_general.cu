@@ -12,11 +12,15 @@
 // Summation order: within a 4-chunk left to right, chunks combined by a fixed xor-tree; results
 // are bitwise reproducible and independent of batch sharding, and agree with torch.bmm to
 // rounding (bmm's own order is unspecified), which is how the parity tests treat them.
+#include <atomic>
+
 #include "ew.cuh"
 
 namespace tsde {
 
 constexpr int kMaxRowsPerBlock = 64;
+
+static std::atomic<int64_t> g_launches[2];  // TSDE_KERNEL_GEN_CTA, TSDE_KERNEL_GEN_TMA
 
 template <int NE, int NG, int NO>
 struct GenP {
@@ -628,6 +632,7 @@ static int launch_gen_tma(const tsde_launch* L, const tsde_noise* nz, GenP<Op::N
     attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    g_launches[TSDE_KERNEL_GEN_TMA].fetch_add(1, std::memory_order_relaxed);
     return (int)cudaLaunchKernelEx(&cfg, kernel, p, np, op, tp);
   };
   const bool mem = nz->source == TSDE_SRC_MEMORY;
@@ -685,6 +690,7 @@ static int launch_gen(const tsde_launch* L, const tsde_noise* nz,
     attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    g_launches[TSDE_KERNEL_GEN_CTA].fetch_add(1, std::memory_order_relaxed);
     if (nz->source == TSDE_SRC_MEMORY)
       return (int)cudaLaunchKernelEx(&cfg, gen_cta_kernel<T, Op, TSDE_SRC_MEMORY>, p, np, op);
     return (int)cudaLaunchKernelEx(&cfg, gen_cta_kernel<T, Op, TSDE_SRC_COUNTER>, p, np, op);
@@ -1089,6 +1095,11 @@ int tsde_general_adjoint_reversible_heun_b(const tsde_launch* L, const tsde_nois
   return TSDE_DISPATCH_DTYPE(
       L, (launch_outer<float>(L, nz, nullptr, adj_y0, 0.5, adj_z1, -1.0, adj_g1)),
       (launch_outer<double>(L, nz, nullptr, adj_y0, 0.5, adj_z1, -1.0, adj_g1)));
+}
+
+int64_t tsde_general_kernel_launches(int32_t family) {
+  if (family < 0 || family > 1) return -1;
+  return tsde::g_launches[family].load(std::memory_order_relaxed);
 }
 
 }  // extern "C"
