@@ -310,6 +310,8 @@ struct TmaP {
   uint32_t w_stride;     // bytes of one increment buffer (rs x m elements, 128-byte multiple)
   int32_t d_shift;       // log2(d)
   uint32_t stage_stride; // bytes per stage
+  uint32_t scratch_np_stride;  // bytes of one array of per-chunk partial dot products (one per product of the tableau)
+  uint32_t scratch_stride;     // bytes of one scratch buffer (NP arrays); two buffers follow the stages
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* ptr) {
@@ -359,6 +361,12 @@ __device__ __forceinline__ double lds1<double>(uint32_t addr) {
   double v;
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
   return v;
+}
+__device__ __forceinline__ void sts1(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void sts1(uint32_t addr, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
 }
 template <bool EVICT_FIRST>
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar,
@@ -463,82 +471,102 @@ gen_tma_kernel(const GenP<Op::NE, Op::NG, Op::NO> p, const NoiseP<T> nz, const O
   }
 
   // ---------------- consumer warps: contract out of shared memory, combine, store ----------------------
-  // Chunk c (4 consecutive elements of the tile, c = pass * 256 + tid) belongs to (row, d) slot c >> MQ_SHIFT
-  // and to row slot >> d_shift of the tile: no divisions, no per-chunk bookkeeping.  Shared memory is
-  // addressed with 32-bit shared-window addresses.
+  // Two phases per tile, both with consecutive lanes on consecutive shared-memory words (conflict-free):
+  //   1. lane-per-chunk: chunk c (4 consecutive elements of the tile, (row, d) slot c >> MQ_SHIFT, Brownian
+  //      quad c & (mq - 1)) -> its 4-term dot product with the increments (the same FMA chain as
+  //      gen_cta_kernel), written to a scratch array in shared memory;
+  //   2. lane-per-output: slot s sums its mq partials with the same pairwise tree as gen_cta_kernel's
+  //      xor-shuffle (so the result is bit-identical), applies the tableau and stores — coalesced.
+  // No shuffles, no predicated epilogue in the hot loop: ~12 instructions per 16-byte chunk instead of ~65.
+  // The scratch array is double-buffered, so one consumer-wide named barrier per tile suffices.
   asm volatile("griddepcontrol.wait;" ::: "memory");  // the predecessor's reads of our outputs are complete
-  const int mc = tid & (mq - 1);
   const uint32_t stage0_addr = smem_u32(stages);
-  const uint32_t g_lane_off = (uint32_t)tid * 4u * (uint32_t)sizeof(T);
+  const uint32_t scratch0_addr = stage0_addr + (uint32_t)kTmaStages * tp.stage_stride;
+  const uint32_t mcq = (uint32_t)(tid & (mq - 1)) * 4u * (uint32_t)sizeof(T);  // byte offset of this lane's quad in a row of W
   for (int it = 0; it < n_my; ++it) {
     const int s = it % kTmaStages;
     const int64_t t = t_begin + it;
     const int nrows = rows_of(t);
-    const int total = (nrows << d_shift) << mq_shift;   // chunks in this tile
-    const int64_t slot0 = (t * rs) << d_shift;          // first (row, d) slot of the tile
+    const int nslots = nrows << d_shift;                 // (row, d) outputs of this tile
+    const int total = nslots << mq_shift;                // chunks in this tile
+    const int64_t slot0 = (t * rs) << d_shift;           // first (row, d) slot of the tile
     const uint32_t sp = stage0_addr + (uint32_t)s * tp.stage_stride;
     const uint32_t e_addr = sp + NG * tp.g_stride;
-    const uint32_t w_addr = sp + w_off + (uint32_t)(4 * mc) * (uint32_t)sizeof(T);
+    const uint32_t w_addr = sp + w_off + mcq;
     const uint32_t u_addr = w_addr + tp.w_stride;
+    const uint32_t scr = scratch0_addr + (uint32_t)(it & 1) * tp.scratch_stride;  // [NP][chunks] partials
     mbar_wait(&full[s], (uint32_t)((it / kTmaStages) & 1));
-    for (int base = 0; base < total; base += kTmaThreads * kTmaUnroll) {  // warp-uniform trip count
+    // ---- phase 1 ----
+    for (int base = 0; base < total; base += kTmaThreads * kTmaUnroll) {
       T gv[kTmaUnroll][NG][4];
-      T ev[kTmaUnroll][NE > 0 ? NE : 1];
-      bool valid[kTmaUnroll];
 #pragma unroll
       for (int un = 0; un < kTmaUnroll; ++un) {
         const int c = base + un * kTmaThreads + tid;
-        valid[un] = c < total;
-        const uint32_t goff = (uint32_t)(base + un * kTmaThreads) * 4u * (uint32_t)sizeof(T) + g_lane_off;
+        if (c < total) {
 #pragma unroll
-        for (int i = 0; i < NG; ++i) {
-          if (valid[un]) {
-            lds4(sp + (uint32_t)i * tp.g_stride + goff, gv[un][i]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) gv[un][i][j] = T(0);
-          }
-        }
-        if (valid[un] && mc == 0) {
-          const uint32_t slot = (uint32_t)c >> mq_shift;
-#pragma unroll
-          for (int i = 0; i < NE; ++i) ev[un][i] = lds1<T>(e_addr + (uint32_t)i * tp.e_stride + slot * (uint32_t)sizeof(T));
+          for (int i = 0; i < NG; ++i) lds4(sp + (uint32_t)i * tp.g_stride + (uint32_t)c * 4u * (uint32_t)sizeof(T), gv[un][i]);
         }
       }
 #pragma unroll
       for (int un = 0; un < kTmaUnroll; ++un) {
         const int c = base + un * kTmaThreads + tid;
-        const uint32_t slot = (uint32_t)c >> mq_shift;
-        const uint32_t rsel = valid[un] ? (slot >> d_shift) : 0u;
-        T part[NP];
+        if (c < total) {
+          const uint32_t row = ((uint32_t)c >> mq_shift) >> d_shift;
+          T w4[4], u4[4];
+          lds4(w_addr + row * (uint32_t)m * (uint32_t)sizeof(T), w4);
+          if (Op::WANT_U) lds4(u_addr + row * (uint32_t)m * (uint32_t)sizeof(T), u4);
+          T part[NP];
 #pragma unroll
-        for (int k = 0; k < NP; ++k) part[k] = T(0);
-        T w4[4], u4[4];
-        lds4(w_addr + rsel * (uint32_t)m * (uint32_t)sizeof(T), w4);
-        if (Op::WANT_U) lds4(u_addr + rsel * (uint32_t)m * (uint32_t)sizeof(T), u4);
+          for (int k = 0; k < NP; ++k) part[k] = T(0);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          T gj[NG];
+          for (int j = 0; j < 4; ++j) {
+            T gj[NG];
 #pragma unroll
-          for (int i = 0; i < NG; ++i) gj[i] = gv[un][i][j];
+            for (int i = 0; i < NG; ++i) gj[i] = gv[un][i][j];
+#pragma unroll
+            for (int k = 0; k < NP; ++k)
+              part[k] = fma(op.gval(k, gj), op.weight(k, w4[j], Op::WANT_U ? u4[j] : T(0)), part[k]);
+          }
 #pragma unroll
           for (int k = 0; k < NP; ++k)
-            part[k] = fma(op.gval(k, gj), op.weight(k, w4[j], Op::WANT_U ? u4[j] : T(0)), part[k]);
-        }
-#pragma unroll
-        for (int off = 1; off < mq; off <<= 1) {
-#pragma unroll
-          for (int k = 0; k < NP; ++k) part[k] = part[k] + __shfl_xor_sync(0xffffffffu, part[k], off);
-        }
-        if (valid[un] && mc == 0) {
-          T e[NE > 0 ? NE : 1], o[NO];
-#pragma unroll
-          for (int i = 0; i < NE; ++i) e[i] = ev[un][i];
-          op.combine(e, part, o);
-#pragma unroll
-          for (int i = 0; i < NO; ++i) reinterpret_cast<T*>(p.o[i])[slot0 + slot] = o[i];
+            sts1(scr + ((uint32_t)k * tp.scratch_np_stride) + (uint32_t)c * (uint32_t)sizeof(T), part[k]);
         }
       }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kTmaThreads) : "memory");  // consumer warps only: partials visible
+    // ---- phase 2 ----
+    for (int slot = tid; slot < nslots; slot += kTmaThreads) {
+      T gp[NP];
+#pragma unroll
+      for (int k = 0; k < NP; ++k) {
+        T pp[mq];
+        const uint32_t a = scr + (uint32_t)k * tp.scratch_np_stride + ((uint32_t)slot << mq_shift) * (uint32_t)sizeof(T);
+        if (mq >= 4) {
+#pragma unroll
+          for (int q = 0; q < mq / 4; ++q) {
+            T v[4];
+            lds4(a + (uint32_t)q * 4u * (uint32_t)sizeof(T), v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pp[(4 * q + j) & (mq - 1)] = v[j];
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < mq; ++q) pp[q] = lds1<T>(a + (uint32_t)q * (uint32_t)sizeof(T));
+        }
+        // pairwise tree in natural order == the xor-shuffle tree seen from lane 0
+#pragma unroll
+        for (int w = 1; w < mq; w <<= 1) {
+#pragma unroll
+          for (int i = 0; i + w < mq; i += 2 * w) pp[i] = pp[i] + pp[i + w];
+        }
+        gp[k] = pp[0];
+      }
+      T e[NE > 0 ? NE : 1], o[NO];
+#pragma unroll
+      for (int i = 0; i < NE; ++i) e[i] = lds1<T>(e_addr + (uint32_t)i * tp.e_stride + (uint32_t)slot * (uint32_t)sizeof(T));
+      op.combine(e, gp, o);
+#pragma unroll
+      for (int i = 0; i < NO; ++i) reinterpret_cast<T*>(p.o[i])[slot0 + slot] = o[i];
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);  // this warp no longer reads stage s
@@ -613,7 +641,9 @@ static int launch_gen_tma(const tsde_launch* L, const tsde_noise* nz, GenP<Op::N
   tp.w_stride = (uint32_t)up128((size_t)rs * L->m * sizeof(T));
   tp.stage_stride = (uint32_t)(Op::NG * tp.g_stride + Op::NE * tp.e_stride + (Op::WANT_U ? 2 : 1) * tp.w_stride);
   tp.n_tiles = (L->rows + rs - 1) / rs;
-  const size_t smem = 128 + (size_t)kTmaStages * tp.stage_stride;
+  tp.scratch_np_stride = (uint32_t)up128((size_t)rs * L->d * mq * sizeof(T));
+  tp.scratch_stride = (uint32_t)(Op::NP * tp.scratch_np_stride);
+  const size_t smem = 128 + (size_t)kTmaStages * tp.stage_stride + 2 * (size_t)tp.scratch_stride;
   if (smem > 200 * 1024) return kTmaNotEligible;
   p.rb = (int32_t)rs;
   auto go = [&](auto kernel) -> int {
