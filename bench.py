@@ -317,7 +317,7 @@ def run_ours(args, w, rank, world, local_rank):
         "roofline": None if roof is None else {
             "bound": "hbm", "achieved": roof['gbs'], "peak": peak, "unit": "GB/s",
             "frac": roof['gbs'] / peak, "traffic": roof.get('traffic'),
-            "kernel": "ew_kernel<float, MilsteinOp, COUNTER> (tsde_step_milstein)",
+            "kernel": "ew_fast_kernel<float, MilsteinOp, COUNTER> (tsde_step_milstein)",
             "algorithmic_bytes_per_launch": roof['bytes'], "avg_launch_us": roof['us'], "peak_source": peak_src,
             "timing": "CUDA events around a graph replay of back-to-back launches of the kernel (how the solver "
                       "issues them), cfg2 tensor sizes, rotating buffer sets larger than L2; median of 7"},
