@@ -132,7 +132,7 @@ class NoiseFeed:
 
 
 class BaseSDESolver(metaclass=abc.ABCMeta):
-    """API for fixed-step solvers (adaptive stepping: see DESIGN.md, "next")."""
+    """API of the solvers: fixed-step (`integrate` / `_run`) and adaptive (`_integrate_adaptive`)."""
 
     strong_order = None
     weak_order = None
