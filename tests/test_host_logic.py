@@ -235,3 +235,22 @@ def test_halfway_tree_structure_is_query_order_independent():
     pa = [[(p.start, p.end, p.id) for p in a._locate(a._round(x), a._round(y))] for x, y in qs]
     pb = [[(p.start, p.end, p.id) for p in b._locate(b._round(x), b._round(y))] for x, y in reversed(qs)][::-1]
     assert pa == pb
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to ours): one JSON line with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, TSDE_BENCH_B='2048')
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1',
+                          '--warmup', '0'], check=True, cwd=ROOT, env=env, capture_output=True, text=True).stdout
+    lines = [ln for ln in out.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and d['unit'] == 'traj-steps/s' and d['higher_is_better'] is True
+    for key in ('metric', 'value', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'scaling', 'dtype', 'data', 'config'):
+        assert key in d, key
+    assert d['value'] > 0 and d['e2e']['value'] == d['value'] and d['e2e']['h2d_bytes_per_step'] == 0
+    cb = d['cpu_baseline']
+    assert cb['kind'] == 'port' and cb['cores'] >= 1 and str(cb['cores']) in cb['threads_tried']
