@@ -161,7 +161,7 @@ int tsde_brownian_merge_area(const tsde_launch* L, void* a0, const void* a1,
                              const void* w0, const void* w1);
 
 /* ------------------------------------------------------------------------ */
-/* Step tableaus  (replace torchsde/_core/methods/*.py  .step bodies)        */
+/* Step tableaus  (replace torchsde/_core/methods/<name>.py  .step bodies)        */
 /* `g*` arguments are (rows,d) for DIAGONAL and (rows,d,m) for GENERAL.      */
 /* ------------------------------------------------------------------------ */
 
