@@ -254,3 +254,16 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert d['value'] > 0 and d['e2e']['value'] == d['value'] and d['e2e']['h2d_bytes_per_step'] == 0
     cb = d['cpu_baseline']
     assert cb['kind'] == 'port' and cb['cores'] >= 1 and str(cb['cores']) in cb['threads_tried']
+
+
+def test_header_is_plain_c():
+    """The drop-in boundary is a C ABI: the header must compile as C (no C++, no torch types), warning-free."""
+    import shutil
+    import subprocess
+    gcc = shutil.which('gcc')
+    if gcc is None:
+        pytest.skip("no gcc")
+    hdr = os.path.join(ROOT, 'include', 'torchsde_b200.h')
+    r = subprocess.run([gcc, '-std=c99', '-fsyntax-only', '-Wall', '-Wextra', '-Werror', '-x', 'c', hdr],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
