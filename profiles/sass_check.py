@@ -47,7 +47,9 @@ def main():
         k = d.split('(')[0].split('<')[0].replace('void ', '')
         fam[k] = fam.get(k, 0) + 1
     for k, v in sorted(fam.items()):
-        print(f"   fp32 with a stack frame: {k} x{v} (8-24 bytes, the producer warp's increment staging; off the consumer loop)")
+        print(f"   fp32 with a stack frame: {k} x{v}")
+    print("   (small frames: generic fallback kernels, and the increment staging of gen_tma_kernel's producer warp — none on a"
+          " hot loop; the specialised ew_fast_kernel / gen_cta_kernel instantiations have none)")
     print()
     for label, pat in PICK:
         hit = [(n, d) for n, d in zip(names, dem) if re.search(pat, d)]
