@@ -13,6 +13,8 @@
 // are bitwise reproducible and independent of batch sharding, and agree with torch.bmm to
 // rounding (bmm's own order is unspecified), which is how the parity tests treat them.
 #include <atomic>
+#include <map>
+#include <utility>
 
 #include "ew.cuh"
 
@@ -686,8 +688,10 @@ constexpr int kTmaNotEligible = -12345;
 template <typename K>
 static int tma_resident_ctas(K kernel, size_t smem) {
   static std::mutex mu;
-  static std::unordered_map<const void*, std::pair<size_t, int>> cache;  // kernel -> (smem opted in, CTAs/SM)
-  const void* id = reinterpret_cast<const void*>(kernel);
+  static std::map<std::pair<const void*, int>, std::pair<size_t, int>> cache;  // (kernel, device) -> (smem opted in, CTAs/SM)
+  int dev = 0;
+  cudaGetDevice(&dev);  // function attributes are per device
+  const std::pair<const void*, int> id(reinterpret_cast<const void*>(kernel), dev);
   std::lock_guard<std::mutex> lock(mu);
   auto it = cache.find(id);
   if (it != cache.end() && it->second.first == smem) return it->second.second;
