@@ -267,3 +267,27 @@ def test_header_is_plain_c():
     r = subprocess.run([gcc, '-std=c99', '-fsyntax-only', '-Wall', '-Wextra', '-Werror', '-x', 'c', hdr],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_schedule_cache_is_keyed_by_the_value_of_dt():
+    """A fresh dt tensor per call may reuse the id of a dead one: the cached time grid must follow dt's value."""
+    import gc
+    from torchsde_b200._core import schedule
+    ts = torch.tensor([0.0, 1.0])
+    reused = False
+    for _ in range(50):
+        dt1 = torch.tensor(0.1)
+        ident = id(dt1)
+        assert schedule.get_schedule(ts, dt1).n_steps == 10
+        del dt1
+        gc.collect()
+        dt2 = torch.tensor(0.05)
+        reused = reused or id(dt2) == ident
+        assert schedule.get_schedule(ts, dt2).n_steps == 20
+        assert schedule.get_schedule(ts, 0.25).n_steps == 4
+        if reused:
+            break
+    # same value, different dtype of dt: the grid is accumulated in the promoted dtype -> separate entries
+    a = schedule.get_schedule(ts, torch.tensor(0.1, dtype=torch.float32))
+    b = schedule.get_schedule(ts, torch.tensor(0.1, dtype=torch.float64))
+    assert a is not b

@@ -39,7 +39,10 @@ def get_schedule(ts, dt):
     """`build_schedule` with a cache: planning a 1000-step grid costs ~10 ms of host time (0-d tensor
     arithmetic in ts' dtype, deliberately identical to the reference's), which would otherwise be paid —
     serialised with the GPU by the device->host read of `ts` — on every solve of a training loop."""
-    dkey = (id(dt), dt._version) if torch.is_tensor(dt) else float(dt)
+    # dt is keyed by VALUE (and dtype: it takes part in the grid's type promotion), never by identity: a training loop
+    # that passes a fresh `torch.tensor(dt)` per call gets recycled object ids, and an identity key would then serve the
+    # grid of an earlier, different step size.  (`ts` is keyed by identity + version and guarded by a weak reference.)
+    dkey = (float(dt), str(dt.dtype)) if torch.is_tensor(dt) else float(dt)
     key = (id(ts), ts._version, dkey)
     hit = _SCHEDULES.get(key)
     if hit is not None and hit[0]() is ts:
