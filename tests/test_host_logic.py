@@ -291,3 +291,33 @@ def test_schedule_cache_is_keyed_by_the_value_of_dt():
     a = schedule.get_schedule(ts, torch.tensor(0.1, dtype=torch.float32))
     b = schedule.get_schedule(ts, torch.tensor(0.1, dtype=torch.float64))
     assert a is not b
+
+
+def test_graph_plan_key_follows_the_sde_tensors():
+    """A captured graph bakes in the addresses of the SDE's parameters: the plan key must change when they are
+    replaced (`.double()`, re-assignment) and stay put under in-place updates (optimiser steps)."""
+    from torchsde_b200._core.graph import _tensor_signature
+    sde = problems.GBMDiagonal(4, 'ito', dtype=torch.float32)
+    s0 = _tensor_signature(sde)
+    assert len(s0) == len(list(sde.parameters())) > 0
+    with torch.no_grad():
+        for p in sde.parameters():
+            p.add_(0.5)                                   # what an optimiser step does
+    sde.load_state_dict(sde.state_dict())
+    assert _tensor_signature(sde) == s0
+    sde.mu = torch.nn.Parameter(sde.mu.detach().clone())  # new storage
+    assert _tensor_signature(sde) != s0
+    assert _tensor_signature(sde.double()) != s0
+
+    class Plain:                                          # SDEs need not be nn.Modules (sdeint.py:124-243)
+        noise_type, sde_type = 'diagonal', 'ito'
+
+        def __init__(self):
+            self.c = torch.ones(3)
+            self.name = 'x'
+    obj = Plain()
+    s1 = _tensor_signature(obj)
+    assert len(s1) == 1
+    obj.c = torch.ones(3)
+    assert _tensor_signature(obj) != s1 or obj.c.data_ptr() == s1[0][0]
+    assert _tensor_signature(object()) == ()

@@ -41,9 +41,21 @@ class _Plan:
     pass
 
 
+def _tensor_signature(obj):
+    """Addresses (and shapes / dtypes) of the tensors an SDE object owns.  A captured graph has them baked in, so a
+    plan must not be replayed after `sde.to(...)`, `sde.double()` or `sde.mu = nn.Parameter(...)` replaced them;
+    in-place updates (optimiser steps, `load_state_dict`) keep the addresses and keep the plan valid."""
+    if isinstance(obj, torch.nn.Module):
+        tensors = list(obj.parameters()) + list(obj.buffers())
+    else:
+        tensors = [v for v in vars(obj).values() if torch.is_tensor(v)] if hasattr(obj, '__dict__') else []
+    return tuple((t.data_ptr(), tuple(t.shape), t.dtype) for t in tensors)
+
+
 def _plan_key(solver, y0, ts, extra0, binding):
     node = binding.node
-    return (type(solver).__name__, tuple(y0.shape), y0.dtype, str(y0.device),
+    return (type(solver).__name__, _tensor_signature(solver.sde._base_sde),
+            tuple(y0.shape), y0.dtype, str(y0.device),
             schedule_lib.ts_values(ts), str(ts.dtype),
             float(solver.dt) if not torch.is_tensor(solver.dt) else float(solver.dt),
             tuple(sorted((k, repr(v)) for k, v in solver.options.items())),
