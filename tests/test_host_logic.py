@@ -321,3 +321,21 @@ def test_graph_plan_key_follows_the_sde_tensors():
     obj.c = torch.ones(3)
     assert _tensor_signature(obj) != s1 or obj.c.data_ptr() == s1[0][0]
     assert _tensor_signature(object()) == ()
+
+
+def test_plan_cache_tolerates_unhashable_sde_objects():
+    import weakref
+    from torchsde_b200._core.graph import plans_of
+
+    class Slotted:
+        __slots__ = ('x',)
+
+    class NoHash:
+        def __eq__(self, other):
+            return True
+
+    cache = weakref.WeakKeyDictionary()
+    assert plans_of(cache, Slotted()) is None and plans_of(cache, NoHash()) is None
+    mod = problems.GBMDiagonal(2, 'ito')
+    d = plans_of(cache, mod)
+    assert d == {} and plans_of(cache, mod) is d

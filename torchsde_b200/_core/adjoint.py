@@ -207,7 +207,9 @@ def _backward_plan(engine, ys, ts, extras):
     sde_obj = engine.sde._base_sde
     key = ('bwd',) + graph_mod._plan_key(engine, ys[0], ts, tuple(extras), binding) + (
         tuple(tuple(p.shape) for p in engine.params),)
-    plans = _BWD_PLANS.setdefault(sde_obj, {})
+    plans = graph_mod.plans_of(_BWD_PLANS, sde_obj)
+    if plans is None:
+        return None
     plan = plans.get(key)
     if plan is not None:
         return plan

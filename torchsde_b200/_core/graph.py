@@ -31,6 +31,15 @@ _PLANS = weakref.WeakKeyDictionary()
 MAX_PLANS_PER_SDE = 4  # every plan owns its output series (T x B x D): keep the cache small
 
 
+def plans_of(cache, sde_obj):
+    """The per-object plan dict, or None for an SDE object that can be neither hashed nor weakly referenced
+    (a class with `__slots__`, or `__eq__` without `__hash__`): such objects run without a cached plan."""
+    try:
+        return cache.setdefault(sde_obj, {})
+    except TypeError:
+        return None
+
+
 def _remember(plans, key, plan):
     while len(plans) >= MAX_PLANS_PER_SDE:
         plans.pop(next(iter(plans)))  # oldest first (dicts keep insertion order)
@@ -78,7 +87,9 @@ def integrate_captured(solver, y0, ts, extra0):
         return solver.integrate(y0, ts, extra0)
     extra0 = tuple(base_solver._contig(e.detach()) for e in extra0)
     key = _plan_key(solver, y0, ts, extra0, binding)
-    plans = _PLANS.setdefault(sde_obj, {})
+    plans = plans_of(_PLANS, sde_obj)
+    if plans is None:
+        return solver.integrate(y0, ts, extra0)  # nothing to hang the plan on: ordinary eager loop
     plan = plans.get(key)
     if plan is None:
         plan = _capture(solver, sched, binding, y0, ts, extra0)
@@ -163,7 +174,9 @@ def _integrate_captured_split(solver, y0, ts):
         solver.options = opts
         return integrate_captured(solver, y0, ts, ())
     key = ('split', k) + _plan_key(solver, y0, ts, (), binding)
-    plans = _PLANS.setdefault(sde_obj, {})
+    plans = plans_of(_PLANS, sde_obj)
+    if plans is None:
+        return solver.integrate(y0, ts, ())
     plan = plans.get(key)
     if plan is None:
         plan = _Plan()
