@@ -224,3 +224,33 @@ def test_oracle_bridge_equals_live_reference(seed, levy):
             np.testing.assert_allclose(U, out[1].numpy(), **tol)
         if levy in ('davie', 'foster'):
             np.testing.assert_allclose(A, out[2].numpy(), **tol)
+
+
+@pytest.mark.parametrize('seed', range(40))
+def test_host_planned_grid_equals_the_grid_the_reference_walks(seed):
+    """The product plans the time grid once on the host (torchsde_b200/_core/schedule.py) instead of evaluating
+    `while curr_t < out_t` / `min(curr_t + dt, ts[-1])` on device tensors (base_solver.py:107-147).  The plan must be the
+    grid the reference actually walks — including the rounding of the accumulated `curr_t + dt` in fp32 (1001 steps
+    for dt = 1e-3 on [0, 1]) and the clipped last step: compared here, bit for bit, with the intervals the live
+    reference queries its Brownian motion on."""
+    from torchsde_b200._core import schedule
+    rng = np.random.RandomState(7000 + seed)
+    dtype = (torch.float32, torch.float64)[seed % 2]
+    n_out = int(rng.randint(2, 6))
+    t0 = float(rng.choice([0.0, 1.0, -0.3]))
+    ts = t0 + np.concatenate([[0.0], np.cumsum(rng.uniform(0.02, 0.4, size=n_out - 1))])
+    if seed % 3 == 0:
+        ts = np.array([0.0, 1.0])
+    dt = float(rng.choice([1e-3, 1e-2, 0.03, 2.0 ** -6, 0.1, 0.25])) if seed % 3 else 1e-3 * (1 + seed % 2 * 9)
+    tst = torch.tensor(ts, dtype=dtype)
+    sde = problems.make('gbm', 1, 1, 'ito', dtype=dtype, seed=0)
+    bm = torchsde.BrownianInterval(float(tst[0]), float(tst[-1]), size=(1, 1), dtype=dtype, entropy=1)
+    rec = _Recorder(bm)
+    with torch.no_grad():
+        torchsde.sdeint(sde, torch.ones(1, 1, dtype=dtype), tst, bm=rec, method='euler', dt=dt)
+    sched = schedule.build_schedule(tst, dt)
+    assert sched.n_steps == len(rec.log), (ts, dt, dtype)
+    for (a, b), (ra, rb, _, _) in zip(sched.steps, rec.log):
+        assert float(a) == ra and float(b) == rb, (ts, dt, dtype)
+    if seed % 3 == 0 and dtype == torch.float32 and dt == 1e-3:
+        assert sched.n_steps == 1001
