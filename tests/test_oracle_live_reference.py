@@ -254,3 +254,87 @@ def test_host_planned_grid_equals_the_grid_the_reference_walks(seed):
         assert float(a) == ra and float(b) == rb, (ts, dt, dtype)
     if seed % 3 == 0 and dtype == torch.float32 and dt == 1e-3:
         assert sched.n_steps == 1001
+
+
+@pytest.mark.parametrize('sde_type', ['ito', 'stratonovich'])
+@pytest.mark.parametrize('method', ['blah', None, 'euler', 'milstein', 'srk', 'euler_heun', 'heun', 'midpoint', 'log_ode',
+                                    'reversible_heun'])
+@pytest.mark.parametrize('kind', ['gbm', 'scalar', 'additive', 'general'])
+@pytest.mark.parametrize('levy', [None, 'none', 'space-time', 'davie', 'foster'])
+def test_contract_errors_equal_the_live_reference(sde_type, method, kind, levy):
+    """`sdeint` must reject exactly the (sde_type, noise_type, method, Levy-area) combinations the reference rejects,
+    with the same exception type (ValueError).  The product is given CPU tensors: a combination it accepts gets past
+    every contract check and then stops at the CUDA requirement (RuntimeError) — there is no CPU fallback."""
+    import warnings
+    import torchsde_b200 as tsde
+    d, m = 3, {'gbm': 3, 'scalar': 1}.get(kind, 2)
+    sde = problems.make(kind, d, m, sde_type, dtype=torch.float64)
+    y0 = torch.ones(4, d, dtype=torch.float64)
+    ts = [0.0, 0.1]
+
+    def outcome(mod):
+        bm = None if levy is None else mod.BrownianInterval(0.0, 0.1, size=(4, m), dtype=torch.float64,
+                                                            levy_area_approximation=levy,
+                                                            **({'device': 'cuda'} if mod is tsde else {}))
+        try:
+            with warnings.catch_warnings(), torch.no_grad():
+                warnings.simplefilter('ignore')
+                mod.sdeint(sde, y0, ts, bm=bm, method=method, dt=0.05)
+        except ValueError:
+            return 'ValueError'
+        except (RuntimeError, NotImplementedError) as e:
+            return 'accepted' if mod is tsde and ('CUDA' in str(e) or 'not implemented' in str(e)) else type(e).__name__
+        return 'accepted'
+
+    assert outcome(tsde) == outcome(torchsde), (sde_type, method, kind, levy)
+
+
+_ADJ_METHODS = [None, 'euler', 'milstein', 'srk', 'midpoint', 'heun', 'euler_heun', 'reversible_heun', 'log_ode']
+_ADJ_ADJOINTS = [None, 'euler', 'milstein', 'srk', 'midpoint', 'heun', 'euler_heun', 'adjoint_reversible_heun', 'log_ode',
+                 'blah']
+
+
+@pytest.mark.parametrize('sde_type', ['ito', 'stratonovich'])
+@pytest.mark.parametrize('kind', ['gbm', 'scalar', 'additive', 'general'])
+def test_adjoint_contract_errors_equal_the_live_reference(sde_type, kind):
+    """`sdeint_adjoint`: 90 (method, adjoint_method) pairs per (sde_type, noise type).  The reference is run forward AND
+    backward on the CPU (it builds its adjoint solver only in `backward`); the product, given CPU tensors, stops at the
+    CUDA requirement once every contract check has passed.  They must agree on ValueError vs accepted, except for two
+    documented cases:
+      * adjoint_method='adjoint_reversible_heun' with a non-reversible forward method: the reference accepts the call
+        and then dies inside `backward` with RuntimeError("Please report a bug to torchsde."); the product rejects the
+        pair up front with a ValueError;
+      * adjoint_method='milstein' on non-diagonal noise: NotImplementedError from the adjoint SDE's
+        `g_prod_and_gdg_prod` at backward time in both (adjoint_sde.py:332-377) — not reachable without a GPU here.
+    """
+    import warnings
+    import torchsde_b200 as tsde
+    d, m = 3, {'gbm': 3, 'scalar': 1}.get(kind, 2)
+    sde = problems.make(kind, d, m, sde_type, dtype=torch.float64)
+
+    def outcome(mod, method, adj):
+        y0 = torch.ones(2, d, dtype=torch.float64, requires_grad=True)
+        try:
+            with warnings.catch_warnings():
+                warnings.simplefilter('ignore')
+                ys = mod.sdeint_adjoint(sde, y0, [0.0, 0.1], method=method, adjoint_method=adj, dt=0.05)
+                ys.sum().backward()
+        except ValueError:
+            return 'ValueError'
+        except (RuntimeError, NotImplementedError) as e:
+            if mod is tsde and ('CUDA' in str(e) or 'not implemented' in str(e)):
+                return 'accepted'
+            return type(e).__name__
+        return 'accepted'
+
+    for method in _ADJ_METHODS:
+        for adj in _ADJ_ADJOINTS:
+            ours, ref = outcome(tsde, method, adj), outcome(torchsde, method, adj)
+            if ours == ref:
+                continue
+            if adj == 'adjoint_reversible_heun' and method != 'reversible_heun':
+                assert (ours, ref) == ('ValueError', 'RuntimeError'), (sde_type, kind, method, adj, ours, ref)
+            elif adj == 'milstein' and kind != 'gbm':
+                assert (ours, ref) == ('accepted', 'NotImplementedError'), (sde_type, kind, method, adj, ours, ref)
+            else:
+                raise AssertionError((sde_type, kind, method, adj, ours, ref))
