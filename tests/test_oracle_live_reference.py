@@ -338,3 +338,124 @@ def test_adjoint_contract_errors_equal_the_live_reference(sde_type, kind):
                 assert (ours, ref) == ('accepted', 'NotImplementedError'), (sde_type, kind, method, adj, ours, ref)
             else:
                 raise AssertionError((sde_type, kind, method, adj, ours, ref))
+
+
+class _BadShape(torch.nn.Module):
+    """Diagonal-noise SDE whose callables return deliberately wrong shapes."""
+    noise_type, sde_type = 'diagonal', 'ito'
+
+    def __init__(self, f_shape, g_shape):
+        super().__init__()
+        self.f_shape, self.g_shape = f_shape, g_shape
+
+    def f(self, t, y):
+        return torch.zeros(self.f_shape, dtype=y.dtype)
+
+    def g(self, t, y):
+        return torch.zeros(self.g_shape, dtype=y.dtype)
+
+
+def _malformed_calls():
+    good = problems.make('gbm', 3, 3, 'ito', dtype=torch.float64)
+    gen = problems.make('general', 3, 2, 'ito', dtype=torch.float64)
+    y0 = torch.ones(4, 3, dtype=torch.float64)
+    yield 'y0 1-d', dict(sde=good, y0=y0[0], ts=[0.0, 0.1])
+    yield 'y0 3-d', dict(sde=good, y0=y0[None], ts=[0.0, 0.1])
+    yield 'y0 not a tensor', dict(sde=good, y0=[[1.0, 1.0, 1.0]], ts=[0.0, 0.1])
+    yield 'ts decreasing', dict(sde=good, y0=y0, ts=[0.1, 0.0])
+    yield 'ts repeated', dict(sde=good, y0=y0, ts=[0.0, 0.0, 0.1])
+    yield 'ts 2-d tensor', dict(sde=good, y0=y0, ts=torch.tensor([[0.0, 0.1]], dtype=torch.float64))
+    yield 'ts of strings', dict(sde=good, y0=y0, ts=['a', 'b'])
+    yield 'ts single point', dict(sde=good, y0=y0, ts=[0.0])
+    yield 'ts requires grad', dict(sde=good, y0=y0, ts=torch.tensor([0.0, 0.1], dtype=torch.float64, requires_grad=True))
+    yield 'dt requires grad', dict(sde=good, y0=y0, ts=[0.0, 0.1], dt=torch.tensor(0.05, requires_grad=True))
+    yield 'bm batch mismatch', dict(sde=good, y0=y0, ts=[0.0, 0.1], bm=(5, 3))
+    yield 'bm channel mismatch', dict(sde=good, y0=y0, ts=[0.0, 0.1], bm=(4, 2))
+    yield 'bm rank 1', dict(sde=good, y0=y0, ts=[0.0, 0.1], bm=(4,))
+    yield 'general bm channel mismatch', dict(sde=gen, y0=y0, ts=[0.0, 0.1], bm=(4, 3))
+    yield 'f wrong batch', dict(sde=_BadShape((5, 3), (4, 3)), y0=y0, ts=[0.0, 0.1])
+    yield 'f wrong state', dict(sde=_BadShape((4, 2), (4, 3)), y0=y0, ts=[0.0, 0.1])
+    yield 'g wrong state', dict(sde=_BadShape((4, 3), (4, 2)), y0=y0, ts=[0.0, 0.1])
+    yield 'g rank 3 for diagonal', dict(sde=_BadShape((4, 3), (4, 3, 3)), y0=y0, ts=[0.0, 0.1])
+    yield 'f rank 1', dict(sde=_BadShape((3,), (4, 3)), y0=y0, ts=[0.0, 0.1])
+    yield 'unknown noise type', dict(sde=type('S', (torch.nn.Module,), dict(noise_type='weird', sde_type='ito', f=good.f, g=good.g))(), y0=y0, ts=[0.0, 0.1])
+    yield 'unknown sde type', dict(sde=type('S', (torch.nn.Module,), dict(noise_type='diagonal', sde_type='weird', f=good.f, g=good.g))(), y0=y0, ts=[0.0, 0.1])
+    yield 'no noise_type attribute', dict(sde=type('S', (torch.nn.Module,), dict(sde_type='ito', f=good.f, g=good.g))(), y0=y0, ts=[0.0, 0.1])
+    yield 'no drift', dict(sde=type('S', (torch.nn.Module,), dict(noise_type='diagonal', sde_type='ito', g=good.g))(), y0=y0, ts=[0.0, 0.1])
+    yield 'no diffusion', dict(sde=type('S', (torch.nn.Module,), dict(noise_type='diagonal', sde_type='ito', f=good.f))(), y0=y0, ts=[0.0, 0.1])
+    yield 'logqp without h', dict(sde=good, y0=y0, ts=[0.0, 0.1], logqp=True)
+    yield 'names to a missing method', dict(sde=good, y0=y0, ts=[0.0, 0.1], names={'drift': 'nope'})
+    yield 'well-formed', dict(sde=good, y0=y0, ts=[0.0, 0.1])
+
+
+@pytest.mark.parametrize('label', [lab for lab, _ in _malformed_calls()])
+def test_malformed_calls_fail_like_the_live_reference(label):
+    """Shape / type / attribute violations of the user-SDE protocol (sdeint.py:115-258): same exception type as the
+    reference (a call the reference accepts must reach the product's CUDA requirement)."""
+    import warnings
+    import torchsde_b200 as tsde
+    kwargs = dict(_malformed_calls())[label]
+
+    def outcome(mod):
+        kw = dict(kwargs)
+        if 'bm' in kw:
+            kw['bm'] = mod.BrownianInterval(0.0, 0.1, size=kw['bm'], dtype=torch.float64,
+                                            **({'device': 'cuda'} if mod is tsde else {}))
+        kw.setdefault('dt', 0.05)
+        try:
+            with warnings.catch_warnings(), torch.no_grad():
+                warnings.simplefilter('ignore')
+                mod.sdeint(**kw)
+        except (RuntimeError, NotImplementedError) as e:
+            if mod is tsde and ('CUDA' in str(e) or 'not implemented' in str(e)):
+                return 'accepted'
+            return type(e).__name__
+        except Exception as e:  # noqa: BLE001 - the exception TYPE is what is compared
+            return type(e).__name__
+        return 'accepted'
+
+    assert outcome(tsde) == outcome(torchsde), label
+
+
+_BI_BAD = {
+    'no size no W': dict(t0=0.0, t1=1.0),
+    't0 > t1': dict(t0=1.0, t1=0.0, size=(2, 3)),
+    't0 == t1': dict(t0=1.0, t1=1.0, size=(2, 3)),
+    'tensor t0 ok': dict(t0=torch.tensor(0.0), t1=torch.tensor(1.0), size=(2, 3)),
+    'non-scalar t0': dict(t0=torch.tensor([0.0, 0.5]), t1=1.0, size=(2, 3)),
+    'bad levy': dict(t0=0.0, t1=1.0, size=(2, 3), levy_area_approximation='wrong'),
+    'integer dtype': dict(t0=0.0, t1=1.0, size=(2, 3), dtype=torch.int64),
+    'W given': dict(t0=0.0, t1=1.0, W=torch.zeros(2, 3)),
+    'W of integer dtype': dict(t0=0.0, t1=1.0, W=torch.zeros(2, 3, dtype=torch.int32)),
+    'W and size disagree': dict(t0=0.0, t1=1.0, size=(2, 4), W=torch.zeros(2, 3)),
+    'W and dtype disagree': dict(t0=0.0, t1=1.0, dtype=torch.float64, W=torch.zeros(2, 3, dtype=torch.float32)),
+    'H without levy': dict(t0=0.0, t1=1.0, W=torch.zeros(2, 3), H=torch.zeros(2, 3)),
+    'H with levy': dict(t0=0.0, t1=1.0, W=torch.zeros(2, 3), H=torch.zeros(2, 3), levy_area_approximation='space-time'),
+    'H shape mismatch': dict(t0=0.0, t1=1.0, W=torch.zeros(2, 3), H=torch.zeros(2, 4), levy_area_approximation='space-time'),
+    'halfway tree': dict(t0=0.0, t1=1.0, size=(2, 3), halfway_tree=True),
+    'dt hint': dict(t0=0.0, t1=1.0, size=(2, 3), dt=0.1),
+    'scalar size': dict(t0=0.0, t1=1.0, size=()),
+    'rank-1 size': dict(t0=0.0, t1=1.0, size=(5,)),
+    'entropy given': dict(t0=0.0, t1=1.0, size=(2, 3), entropy=7),
+    'pool and cache sizes': dict(t0=0.0, t1=1.0, size=(2, 3), pool_size=4, cache_size=None),
+    'tol': dict(t0=0.0, t1=1.0, size=(2, 3), tol=1e-3),
+}
+
+
+@pytest.mark.parametrize('label', sorted(_BI_BAD))
+def test_brownian_interval_constructor_like_the_live_reference(label):
+    """Constructor contract of BrownianInterval (brownian_interval.py:394-494): accepts / rejects the same arguments
+    with the same exception type, and reports the same shape / dtype / levy / flags."""
+    import torchsde_b200 as tsde
+    kwargs = _BI_BAD[label]
+
+    def outcome(mod):
+        kw = dict(kwargs)
+        try:
+            bm = mod.BrownianInterval(**kw)
+        except Exception as e:  # noqa: BLE001
+            return type(e).__name__
+        return ('ok', tuple(bm.shape), bm.dtype, bm.levy_area_approximation, bm.halfway_tree, bm.dt, bm.tol,
+                bm.pool_size, bm.cache_size)
+
+    assert outcome(tsde) == outcome(torchsde), label

@@ -238,7 +238,6 @@ class BrownianInterval(brownian_base.BaseBrownian):
             raise ValueError(f"`levy_area_approximation` must be one of {LEVY_AREA_APPROXIMATIONS}, but got "
                              f"'{levy_area_approximation}'.")
         device = torch.device(device)
-
         self._size = size
         self._dtype = dtype
         self._device = device
@@ -288,6 +287,10 @@ class BrownianInterval(brownian_base.BaseBrownian):
             _assert_floating_tensor('W', W)
         if H is not None:
             _assert_floating_tensor('H', H)
+        if dtype not in (torch.float32, torch.float64):
+            # Integer dtypes fail in the reference's constructor as well (it draws the top-level increment eagerly and
+            # `torch.randn` has no integer kernel, brownian_interval.py:30-32); half precision is not implemented here.
+            raise NotImplementedError(f"BrownianInterval is implemented for torch.float32 and torch.float64, not {dtype}.")
         self._user_W = W
         self._user_H = H
         self._root_value = None  # (W, H) once observed
