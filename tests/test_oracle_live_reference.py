@@ -459,3 +459,66 @@ def test_brownian_interval_constructor_like_the_live_reference(label):
                 bm.pool_size, bm.cache_size)
 
     assert outcome(tsde) == outcome(torchsde), label
+
+
+def test_public_signatures_equal_the_live_reference():
+    """Drop-in boundary: same exported names, same parameter names, order, kinds and defaults."""
+    import inspect
+    import torchsde_b200 as tsde
+    names = ['sdeint', 'sdeint_adjoint', 'BrownianInterval', 'BrownianPath', 'BrownianTree', 'ReverseBrownian',
+             'brownian_interval_like', 'BaseBrownian', 'BaseSDE', 'SDEIto', 'SDEStratonovich']
+    assert set(torchsde.__all__ if hasattr(torchsde, '__all__') else names) >= set()  # reference exports by import
+    for name in names:
+        ours, ref = getattr(tsde, name), getattr(torchsde, name)
+        targets = [(ours, ref)]
+        if inspect.isclass(ref):
+            targets = [(ours.__init__, ref.__init__)]
+            if hasattr(ref, '__call__') and name != 'BaseSDE' and not name.startswith('SDE'):
+                targets.append((ours.__call__, ref.__call__))
+        for fo, fr in targets:
+            so, sr = inspect.signature(fo), inspect.signature(fr)
+            po = [(p.name, p.kind, p.default) for p in so.parameters.values()]
+            pr = [(p.name, p.kind, p.default) for p in sr.parameters.values()]
+            assert po == pr, f"{name}.{getattr(fr, '__name__', '')}: {po} != {pr}"
+    # read-only properties of a Brownian motion (brownian_interval.py:744-785)
+    for prop in ('shape', 'dtype', 'device', 'entropy', 'levy_area_approximation', 'dt', 'tol', 'pool_size', 'cache_size',
+                 'halfway_tree'):
+        assert isinstance(getattr(tsde.BrownianInterval, prop), property), prop
+    assert callable(tsde.BrownianInterval.size) and callable(tsde.BrownianInterval.display_binary_tree)
+
+
+_DERIVED = {
+    'path': ('BrownianPath', dict(t0=0.0, w0=torch.zeros(2, 3))),
+    'path window': ('BrownianPath', dict(t0=0.5, w0=torch.zeros(2, 3, dtype=torch.float64), window_size=4)),
+    'path bad t0': ('BrownianPath', dict(t0=torch.tensor([0.0, 1.0]), w0=torch.zeros(2, 3))),
+    'path int w0': ('BrownianPath', dict(t0=0.0, w0=torch.zeros(2, 3, dtype=torch.int64))),
+    'tree': ('BrownianTree', dict(t0=0.0, w0=torch.zeros(2, 3))),
+    'tree t1 w1': ('BrownianTree', dict(t0=0.0, w0=torch.zeros(2, 3), t1=2.0, w1=torch.ones(2, 3))),
+    'tree t1 before t0': ('BrownianTree', dict(t0=1.0, w0=torch.zeros(2, 3), t1=0.5)),
+    'tree w1 shape': ('BrownianTree', dict(t0=0.0, w0=torch.zeros(2, 3), t1=1.0, w1=torch.ones(2, 4))),
+    'tree options': ('BrownianTree', dict(t0=0.0, w0=torch.zeros(2, 3), entropy=3, tol=1e-4, pool_size=8, cache_depth=5,
+                                          safety=0.1)),
+    'like': ('brownian_interval_like', dict(y=torch.zeros(4, 5, dtype=torch.float64))),
+    'like overrides': ('brownian_interval_like', dict(y=torch.zeros(4, 5), t0=0.5, t1=2.0, size=(4, 2),
+                                                       levy_area_approximation='space-time')),
+}
+
+
+@pytest.mark.parametrize('label', sorted(_DERIVED))
+def test_derived_brownians_construct_like_the_live_reference(label):
+    """BrownianPath / BrownianTree / brownian_interval_like (derived.py:52-205): same acceptance, exception types and
+    reported shape / dtype / Levy-area mode."""
+    import warnings
+    import torchsde_b200 as tsde
+    name, kwargs = _DERIVED[label]
+
+    def outcome(mod):
+        try:
+            with warnings.catch_warnings():
+                warnings.simplefilter('ignore')
+                bm = getattr(mod, name)(**kwargs)
+        except Exception as e:  # noqa: BLE001
+            return type(e).__name__
+        return ('ok', tuple(bm.shape), bm.dtype, bm.levy_area_approximation)
+
+    assert outcome(tsde) == outcome(torchsde), label
