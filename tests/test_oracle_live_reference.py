@@ -522,3 +522,91 @@ def test_derived_brownians_construct_like_the_live_reference(label):
         return ('ok', tuple(bm.shape), bm.dtype, bm.levy_area_approximation)
 
     assert outcome(tsde) == outcome(torchsde), label
+
+
+@pytest.mark.parametrize('sde_type', ['ito', 'stratonovich'])
+@pytest.mark.parametrize('kind', ['gbm', 'scalar', 'additive', 'general'])
+def test_adjoint_sde_glue_equals_the_live_reference(kind, sde_type):
+    """`_core/adjoint_sde.AdjointSDE` (the augmented backward SDE of the generic adjoint, adjoint_sde.py:23-377) is
+    autograd glue around the user's f and g — pure torch ops, so it runs on the CPU: every product it hands to the
+    solvers (drift, diffusion-vector product, both at once, Milstein's pair for diagonal noise) is compared with the
+    reference's AdjointSDE on random augmented states, including the Ito corrections."""
+    from torchsde._core import base_sde as ref_base
+    from torchsde._core.adjoint_sde import AdjointSDE as RefAdjointSDE
+    from torchsde_b200._core import base_sde as our_base
+    from torchsde_b200._core.adjoint_sde import AdjointSDE as OurAdjointSDE
+    rng = torch.Generator().manual_seed(11)
+    B, d = 3, 4
+    m = {'gbm': d, 'scalar': 1}.get(kind, 2)
+    sde = problems.make(kind, d, m, sde_type, dtype=torch.float64, seed=2)
+    params = [p for p in sde.parameters() if p.requires_grad]
+    y = 0.1 + torch.rand(B, d, generator=rng, dtype=torch.float64)
+    adj_y = torch.randn(B, d, generator=rng, dtype=torch.float64)
+    aug = [y, adj_y] + [torch.randn(p.shape, generator=rng, dtype=torch.float64) for p in params]
+    shapes = [t.size() for t in aug]
+    flat = torch.cat([t.reshape(-1) for t in aug]).unsqueeze(0)
+    ref = RefAdjointSDE(ref_base.ForwardSDE(sde), params, shapes)
+    ours = OurAdjointSDE(our_base.ForwardSDE(sde), params, shapes)
+    assert ours.noise_type == ref.noise_type and ours.sde_type == ref.sde_type
+    t = torch.tensor(-0.3, dtype=torch.float64)
+    bm_m = d if kind == 'gbm' else m
+    v = torch.randn(B, bm_m, generator=rng, dtype=torch.float64)
+    tol = dict(rtol=1e-12, atol=1e-13)
+    with torch.no_grad():
+        np.testing.assert_allclose(ours.f(t, flat).numpy(), ref.f(t, flat).numpy(), **tol)
+        np.testing.assert_allclose(ours.g_prod(t, flat, v).numpy(), ref.g_prod(t, flat, v).numpy(), **tol)
+        fo, go = ours.f_and_g_prod(t, flat, v)
+        fr, gr = ref.f_and_g_prod(t, flat, v)
+        np.testing.assert_allclose(fo.numpy(), fr.numpy(), **tol)
+        np.testing.assert_allclose(go.numpy(), gr.numpy(), **tol)
+        if kind == 'gbm':
+            v2 = torch.randn(B, bm_m, generator=rng, dtype=torch.float64)
+            a1, a2 = ours.g_prod_and_gdg_prod(t, flat, v, v2)
+            b1, b2 = ref.g_prod_and_gdg_prod(t, flat, v, v2)
+            np.testing.assert_allclose(a1.numpy(), b1.numpy(), **tol)
+            np.testing.assert_allclose(a2.numpy(), b2.numpy(), **tol)
+
+
+class _WithPrior(torch.nn.Module):
+    """f, g and a prior drift h — what `logqp=True` needs (sdeint.py:141-145)."""
+
+    def __init__(self, base):
+        super().__init__()
+        self.base = base
+        self.noise_type, self.sde_type = base.noise_type, base.sde_type
+
+    def f(self, t, y):
+        return self.base.f(t, y)
+
+    def g(self, t, y):
+        return self.base.g(t, y)
+
+    def h(self, t, y):
+        return -0.5 * y + torch.sin(t)
+
+
+@pytest.mark.parametrize('kind', ['gbm', 'scalar', 'additive', 'general'])
+def test_logqp_augmentation_equals_the_live_reference(kind):
+    """SDELogqp (base_sde.py:240-306): drift / diffusion of the state augmented with the KL integrand, diagonal branch
+    (stable division) and general branch (pseudo-inverse) — pure torch, compared on the CPU."""
+    from torchsde._core import base_sde as ref_base
+    from torchsde_b200._core import base_sde as our_base
+    d, m = 4, {'gbm': 4, 'scalar': 1}.get(kind, 3)
+    sde = _WithPrior(problems.make(kind, d, m, 'ito', dtype=torch.float64, seed=4))
+    ours, ref = our_base.SDELogqp(sde), ref_base.SDELogqp(sde)
+    gen = torch.Generator().manual_seed(3)
+    y = torch.cat([0.2 + torch.rand(5, d, generator=gen, dtype=torch.float64), torch.zeros(5, 1, dtype=torch.float64)], dim=1)
+    t = torch.tensor(0.4, dtype=torch.float64)
+    tol = dict(rtol=1e-12, atol=1e-13)
+    with torch.no_grad():
+        np.testing.assert_allclose(ours.f(t, y).numpy(), ref.f(t, y).numpy(), **tol)
+        np.testing.assert_allclose(ours.g(t, y).numpy(), ref.g(t, y).numpy(), **tol)
+        fo, go = ours.f_and_g(t, y)
+        fr, gr = ref.f_and_g(t, y)
+        np.testing.assert_allclose(fo.numpy(), fr.numpy(), **tol)
+        np.testing.assert_allclose(go.numpy(), gr.numpy(), **tol)
+    assert ours.noise_type == ref.noise_type and ours.sde_type == ref.sde_type
+    with pytest.raises(AttributeError):
+        our_base.SDELogqp(problems.make(kind, d, m, 'ito'))
+    with pytest.raises(AttributeError):
+        ref_base.SDELogqp(problems.make(kind, d, m, 'ito'))

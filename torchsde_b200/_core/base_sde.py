@@ -78,101 +78,77 @@ class ForwardSDE(BaseSDE):
 
 
 class RenameMethodsSDE(BaseSDE):
+    """View of a user SDE whose callables live under other attribute names (`names=` of sdeint; reference
+    base_sde.py:212-224).  Only the names that resolve are bound, a missing one surfaces later as the usual
+    "method has not been provided" error."""
+    _STANDARD = ('f', 'g', 'h', 'g_prod', 'f_and_g', 'f_and_g_prod')
 
     def __init__(self, sde, drift='f', diffusion='g', prior_drift='h', diffusion_prod='g_prod',
                  drift_and_diffusion='f_and_g', drift_and_diffusion_prod='f_and_g_prod'):
-        super(RenameMethodsSDE, self).__init__(noise_type=sde.noise_type, sde_type=sde.sde_type)
+        BaseSDE.__init__(self, noise_type=sde.noise_type, sde_type=sde.sde_type)
         self._base_sde = sde
-        for name, value in zip(('f', 'g', 'h', 'g_prod', 'f_and_g', 'f_and_g_prod'),
-                               (drift, diffusion, prior_drift, diffusion_prod, drift_and_diffusion,
-                                drift_and_diffusion_prod)):
-            try:
-                setattr(self, name, getattr(sde, value))
-            except AttributeError:
-                pass
+        theirs = (drift, diffusion, prior_drift, diffusion_prod, drift_and_diffusion, drift_and_diffusion_prod)
+        for ours, attr in zip(self._STANDARD, theirs):
+            bound = getattr(sde, attr, None)
+            if bound is not None:
+                setattr(self, ours, bound)
 
 
 class SDEIto(BaseSDE):
+    """Convenience base class fixing sde_type='ito' (base_sde.py:227-230)."""
 
     def __init__(self, noise_type):
-        super(SDEIto, self).__init__(noise_type=noise_type, sde_type=SDE_TYPES.ito)
+        BaseSDE.__init__(self, noise_type=noise_type, sde_type=SDE_TYPES.ito)
 
 
 class SDEStratonovich(BaseSDE):
+    """Convenience base class fixing sde_type='stratonovich' (base_sde.py:233-236)."""
 
     def __init__(self, noise_type):
-        super(SDEStratonovich, self).__init__(noise_type=noise_type, sde_type=SDE_TYPES.stratonovich)
+        BaseSDE.__init__(self, noise_type=noise_type, sde_type=SDE_TYPES.stratonovich)
 
 
-def _stable_division(a, b, epsilon=1e-7):
-    # misc.py:66-68
-    b = torch.where(b.abs().detach() > epsilon, b, torch.full_like(b, fill_value=epsilon) * b.sign())
-    return a / b
+def _kl_rate(f, g, h, diagonal, epsilon=1e-7):
+    """0.5 |u|^2 with g u = f - h: the integrand of the KL divergence between the posterior SDE (drift f) and the
+    prior SDE (drift h) that share the diffusion g.  Diagonal noise divides element-wise, guarding |g| < epsilon the way
+    the reference's `stable_division` does (misc.py:66-68); otherwise u is the least-squares solution through the
+    pseudo-inverse of g (base_sde.py:266-306)."""
+    gap = f - h
+    if diagonal:
+        safe = torch.where(g.abs().detach() > epsilon, g, torch.full_like(g, fill_value=epsilon) * g.sign())
+        u = gap / safe
+    else:
+        u = torch.bmm(g.pinverse(), gap.unsqueeze(-1)).squeeze(-1)
+    return .5 * (u ** 2).sum(dim=1, keepdim=True)
 
 
 class SDELogqp(BaseSDE):
-    """Augments the state with the KL integrand (base_sde.py:240-306).  This is user-level model
-    code composed of the user's own f/g/h callables (torch ops), not part of the solver kernels."""
+    """State augmented by one channel that integrates the KL rate (`logqp=True`; base_sde.py:240-306): drift
+    (f, 0.5|u|^2), diffusion (g, 0).  User-level model code made of the user's own f / g / h (torch ops), solved by the
+    same engine as any other SDE."""
 
     def __init__(self, sde):
-        super(SDELogqp, self).__init__(noise_type=sde.noise_type, sde_type=sde.sde_type)
+        BaseSDE.__init__(self, noise_type=sde.noise_type, sde_type=sde.sde_type)
         self._base_sde = sde
-        try:
-            self._base_f = sde.f
-            self._base_g = sde.g
-            self._base_h = sde.h
-        except AttributeError as e:
-            raise AttributeError("If using logqp then drift, diffusion and prior drift must all be specified.") from e
-        if sde.noise_type == NOISE_TYPES.diagonal:
-            self.f = self.f_diagonal
-            self.g = self.g_diagonal
-            self.f_and_g = self.f_and_g_diagonal
-        else:
-            self.f = self.f_general
-            self.g = self.g_general
-            self.f_and_g = self.f_and_g_general
+        missing = [name for name in ('f', 'g', 'h') if not hasattr(sde, name)]
+        if missing:
+            raise AttributeError("If using logqp then drift, diffusion and prior drift must all be specified.")
+        self._diagonal = sde.noise_type == NOISE_TYPES.diagonal
 
-    def f_diagonal(self, t, y):
-        y = y[:, :-1]
-        f, g, h = self._base_f(t, y), self._base_g(t, y), self._base_h(t, y)
-        u = _stable_division(f - h, g)
-        f_logqp = .5 * (u ** 2).sum(dim=1, keepdim=True)
-        return torch.cat([f, f_logqp], dim=1)
+    def _pad_diffusion(self, g):
+        # the extra channel carries no noise: a zero entry (diagonal) or a zero row of the (d, m) matrix
+        zeros = g.new_zeros((g.size(0), 1) if self._diagonal else (g.size(0), 1, g.size(-1)))
+        return torch.cat([g, zeros], dim=1)
 
-    def g_diagonal(self, t, y):
-        y = y[:, :-1]
-        g = self._base_g(t, y)
-        g_logqp = y.new_zeros(size=(y.size(0), 1))
-        return torch.cat([g, g_logqp], dim=1)
+    def f_and_g(self, t, y):
+        state = y[:, :-1]
+        base = self._base_sde
+        f, g = base.f(t, state), base.g(t, state)
+        rate = _kl_rate(f, g, base.h(t, state), self._diagonal)
+        return torch.cat([f, rate], dim=1), self._pad_diffusion(g)
 
-    def f_and_g_diagonal(self, t, y):
-        y = y[:, :-1]
-        f, g, h = self._base_f(t, y), self._base_g(t, y), self._base_h(t, y)
-        u = _stable_division(f - h, g)
-        f_logqp = .5 * (u ** 2).sum(dim=1, keepdim=True)
-        g_logqp = y.new_zeros(size=(y.size(0), 1))
-        return torch.cat([f, f_logqp], dim=1), torch.cat([g, g_logqp], dim=1)
+    def f(self, t, y):
+        return self.f_and_g(t, y)[0]
 
-    def _u_general(self, f, g, h):
-        return torch.bmm(g.pinverse(), (f - h).unsqueeze(-1)).squeeze(-1)
-
-    def f_general(self, t, y):
-        y = y[:, :-1]
-        f, g, h = self._base_f(t, y), self._base_g(t, y), self._base_h(t, y)
-        u = self._u_general(f, g, h)
-        f_logqp = .5 * (u ** 2).sum(dim=1, keepdim=True)
-        return torch.cat([f, f_logqp], dim=1)
-
-    def g_general(self, t, y):
-        y = y[:, :-1]
-        g = self._base_sde.g(t, y)
-        g_logqp = y.new_zeros(size=(g.size(0), 1, g.size(-1)))
-        return torch.cat([g, g_logqp], dim=1)
-
-    def f_and_g_general(self, t, y):
-        y = y[:, :-1]
-        f, g, h = self._base_f(t, y), self._base_g(t, y), self._base_h(t, y)
-        u = self._u_general(f, g, h)
-        f_logqp = .5 * (u ** 2).sum(dim=1, keepdim=True)
-        g_logqp = y.new_zeros(size=(g.size(0), 1, g.size(-1)))
-        return torch.cat([f, f_logqp], dim=1), torch.cat([g, g_logqp], dim=1)
+    def g(self, t, y):
+        return self._pad_diffusion(self._base_sde.g(t, y[:, :-1]))
