@@ -143,53 +143,96 @@ def _tensor_from_list(values, dtype, device):
     return t
 
 
-def _is_strictly_increasing(ts):
-    return all(x < y for x, y in zip(ts[:-1], ts[1:]))
+def default_method(sde_type, noise_type):
+    """Solver used when `method` is None (reference sdeint.py:147-153): midpoint for Stratonovich SDEs, else Euler for
+    general noise and SRK for the noise types SRK supports."""
+    if sde_type == SDE_TYPES.stratonovich:
+        return METHODS.midpoint
+    return METHODS.euler if noise_type == NOISE_TYPES.general else METHODS.srk
+
+
+def default_levy_area(method):
+    """Levy-area mode of the BrownianInterval created when `bm` is None (reference sdeint.py:262-268)."""
+    return {METHODS.srk: LEVY_AREA_APPROXIMATIONS.space_time,
+            METHODS.log_ode_midpoint: LEVY_AREA_APPROXIMATIONS.foster}.get(method, LEVY_AREA_APPROXIMATIONS.none)
+
+
+def _checked_kinds(sde):
+    for attr, allowed, label in (('noise_type', NOISE_TYPES, 'noise type'), ('sde_type', SDE_TYPES, 'sde type')):
+        if not hasattr(sde, attr):
+            raise ValueError(f"sde does not have the attribute {attr}.")
+        if getattr(sde, attr) not in allowed:
+            raise ValueError(f"Expected {label} in {allowed}, but found {getattr(sde, attr)}.")
+
+
+def _time_tensor(ts, like):
+    """`ts` as a 1-D tensor in y0's dtype / device, strictly increasing (reference sdeint.py:161-166)."""
+    if not torch.is_tensor(ts):
+        floats = isinstance(ts, (tuple, list)) and all(isinstance(t, (float, int)) for t in ts)
+        if not floats:
+            raise ValueError("Evaluation times `ts` must be a 1-D Tensor or list/tuple of floats.")
+        ts = _tensor_from_list(tuple(ts), like.dtype, like.device)
+    values = schedule_lib.ts_values(ts)
+    if not all(earlier < later for earlier, later in zip(values, values[1:])):  # (a NaN time fails here too)
+        raise ValueError("Evaluation times `ts` must be strictly increasing.")
+    return ts
+
+
+def _probe(sde, t0, y0, sizes):
+    """Call every callable the SDE offers once and record the sizes it reports (reference sdeint.py:168-243).  Returns
+    (drift available, diffusion available)."""
+    have_f = have_g = False
+
+    def test_vector():
+        sizes.need_noise_size()
+        return torch.randn(sizes.batch[0], sizes.noise[0], dtype=y0.dtype, device=y0.device)
+
+    with torch.no_grad():
+        if hasattr(sde, 'f'):
+            have_f = True
+            sizes.two_d('Drift', tuple(sde.f(t0, y0).size()))
+        if hasattr(sde, 'g'):
+            have_g = True
+            sizes.diffusion('Diffusion', tuple(sde.g(t0, y0).size()))
+        if hasattr(sde, 'f_and_g'):
+            have_f = have_g = True
+            drift, diffusion = sde.f_and_g(t0, y0)
+            sizes.two_d('Drift', tuple(drift.size()))
+            sizes.diffusion('Diffusion', tuple(diffusion.size()))
+        if hasattr(sde, 'g_prod'):
+            have_g = True
+            sizes.two_d('Diffusion-vector product', tuple(sde.g_prod(t0, y0, test_vector()).size()))
+        if hasattr(sde, 'f_and_g_prod'):
+            have_f = have_g = True
+            drift, product = sde.f_and_g_prod(t0, y0, test_vector())
+            sizes.two_d('Drift', tuple(drift.size()))
+            sizes.two_d('Diffusion-vector product', tuple(product.size()))
+    return have_f, have_g
 
 
 def check_contract(sde, y0, ts, bm, method, adaptive, options, names, logqp):
-    """Validate and normalise the arguments of a solve; reference sdeint.py:115-281."""
-    rename = {}
-    if names is not None:
-        rename = {key: names[key] for key in ("drift", "diffusion", "prior_drift", "drift_and_diffusion",
-                                              "drift_and_diffusion_prod") if key in names}
-    if len(rename) > 0:
-        sde = base_sde.RenameMethodsSDE(sde, **rename)
-
-    if not hasattr(sde, "noise_type"):
-        raise ValueError("sde does not have the attribute noise_type.")
-    if sde.noise_type not in NOISE_TYPES:
-        raise ValueError(f"Expected noise type in {NOISE_TYPES}, but found {sde.noise_type}.")
-    if not hasattr(sde, "sde_type"):
-        raise ValueError("sde does not have the attribute sde_type.")
-    if sde.sde_type not in SDE_TYPES:
-        raise ValueError(f"Expected sde type in {SDE_TYPES}, but found {sde.sde_type}.")
+    """Validate and normalise the arguments of a solve; every violation is a ValueError, as in the reference
+    (sdeint.py:115-281).  Returns (ForwardSDE, y0, ts tensor, bm, method, options copy)."""
+    if names:
+        known = ("drift", "diffusion", "prior_drift", "drift_and_diffusion", "drift_and_diffusion_prod")
+        rename = {role: names[role] for role in known if role in names}
+        if rename:
+            sde = base_sde.RenameMethodsSDE(sde, **rename)
+    _checked_kinds(sde)
 
     if not torch.is_tensor(y0):
         raise ValueError("`y0` must be a torch.Tensor.")
     if y0.dim() != 2:
         raise ValueError("`y0` must be a 2-dimensional tensor of shape (batch, channels).")
-
-    if logqp:  # backwards compatibility v0.1.1, sdeint.py:141-145
+    if logqp:  # one more state channel integrates the KL rate (v0.1.1 compatibility, sdeint.py:141-145)
         sde = base_sde.SDELogqp(sde)
         y0 = torch.cat((y0, y0.new_zeros(size=(y0.size(0), 1))), dim=1)
 
     if method is None:
-        if sde.sde_type == SDE_TYPES.stratonovich:
-            method = METHODS.midpoint
-        elif sde.noise_type == NOISE_TYPES.general:
-            method = METHODS.euler
-        else:
-            method = METHODS.srk
+        method = default_method(sde.sde_type, sde.noise_type)
     if method not in METHODS:
         raise ValueError(f"Expected method in {METHODS}, but found {method}.")
-
-    if not torch.is_tensor(ts):
-        if not isinstance(ts, (tuple, list)) or not all(isinstance(t, (float, int)) for t in ts):
-            raise ValueError("Evaluation times `ts` must be a 1-D Tensor or list/tuple of floats.")
-        ts = _tensor_from_list(tuple(ts), y0.dtype, y0.device)
-    if not _is_strictly_increasing(schedule_lib.ts_values(ts)):
-        raise ValueError("Evaluation times `ts` must be strictly increasing.")
+    ts = _time_tensor(ts, y0)
 
     sizes = _Sizes(sde.noise_type)
     sizes.batch.append(y0.size(0))
@@ -199,76 +242,35 @@ def check_contract(sde, y0, ts, bm, method, adaptive, options, names, logqp):
             raise ValueError("`bm` must be of shape (batch, noise_channels).")
         sizes.batch.append(bm.shape[0])
         sizes.noise.append(bm.shape[1])
-
-    has_f = has_g = False
-    with torch.no_grad():
-        if hasattr(sde, 'f'):
-            has_f = True
-            sizes.two_d('Drift', tuple(sde.f(ts[0], y0).size()))
-        if hasattr(sde, 'g'):
-            has_g = True
-            sizes.diffusion('Diffusion', tuple(sde.g(ts[0], y0).size()))
-        if hasattr(sde, 'f_and_g'):
-            has_f = has_g = True
-            _f, _g = sde.f_and_g(ts[0], y0)
-            sizes.two_d('Drift', tuple(_f.size()))
-            sizes.diffusion('Diffusion', tuple(_g.size()))
-        if hasattr(sde, 'g_prod'):
-            has_g = True
-            sizes.need_noise_size()
-            v = torch.randn(sizes.batch[0], sizes.noise[0], dtype=y0.dtype, device=y0.device)
-            sizes.two_d('Diffusion-vector product', tuple(sde.g_prod(ts[0], y0, v).size()))
-        if hasattr(sde, 'f_and_g_prod'):
-            has_f = has_g = True
-            sizes.need_noise_size()
-            v = torch.randn(sizes.batch[0], sizes.noise[0], dtype=y0.dtype, device=y0.device)
-            _f, _g_prod = sde.f_and_g_prod(ts[0], y0, v)
-            sizes.two_d('Drift', tuple(_f.size()))
-            sizes.two_d('Diffusion-vector product', tuple(_g_prod.size()))
-
-    if not has_f:
+    have_f, have_g = _probe(sde, ts[0], y0, sizes)
+    if not have_f:
         raise ValueError("sde must define at least one of `f`, `f_and_g`, or `f_and_g_prod`. (Or possibly more "
                          "depending on the method chosen.)")
-    if not has_g:
+    if not have_g:
         raise ValueError("sde must define at least one of `g`, `f_and_g`, `g_prod` or `f_and_g_prod`. (Or possibly "
                          "more depending on the method chosen.)")
     sizes.consistent()
-
-    if sde.noise_type == NOISE_TYPES.scalar:
-        if sizes.noise[0] != 1:
-            raise ValueError(f"Scalar noise must have only one channel; the diffusion has {sizes.noise[0]} noise "
-                             f"channels.")
+    if sde.noise_type == NOISE_TYPES.scalar and sizes.noise[0] != 1:
+        raise ValueError(f"Scalar noise must have only one channel; the diffusion has {sizes.noise[0]} noise channels.")
 
     sde = base_sde.ForwardSDE(sde)
-
     if bm is None:
-        if method == METHODS.srk:
-            levy_area_approximation = LEVY_AREA_APPROXIMATIONS.space_time
-        elif method == METHODS.log_ode_midpoint:
-            levy_area_approximation = LEVY_AREA_APPROXIMATIONS.foster
-        else:
-            levy_area_approximation = LEVY_AREA_APPROXIMATIONS.none
-        vals = schedule_lib.ts_values(ts)
-        bm = BrownianInterval(t0=vals[0], t1=vals[-1], size=(sizes.batch[0], sizes.noise[0]), dtype=y0.dtype,
-                              device=y0.device, levy_area_approximation=levy_area_approximation)
-
-    options = {} if options is None else options.copy()
-
+        span = schedule_lib.ts_values(ts)
+        bm = BrownianInterval(t0=span[0], t1=span[-1], size=(sizes.batch[0], sizes.noise[0]), dtype=y0.dtype,
+                              device=y0.device, levy_area_approximation=default_levy_area(method))
     if adaptive and method == METHODS.euler and sde.noise_type != NOISE_TYPES.additive:
         warnings.warn("Numerical solution is not guaranteed to converge to the correct solution when using adaptive "
                       "time-stepping with the Euler--Maruyama method with non-additive noise.")
-
-    return sde, y0, ts, bm, method, options
+    return sde, y0, ts, bm, method, ({} if options is None else options.copy())
 
 
 def parse_return(y0, ys, extra_solver_state, extra, logqp):
-    """sdeint.py:284-300."""
+    """What `sdeint` hands back (reference sdeint.py:284-300): ys; with `logqp` the state's last channel is split off
+    and returned as per-interval increments of the log-ratio; with `extra` the solver's final extra state is appended."""
+    out = [ys]
     if logqp:
         ys, log_ratio = ys.split(split_size=(y0.size(1) - 1, 1), dim=2)
-        log_ratio_increments = (log_ratio[1:] - log_ratio[:-1]).squeeze(dim=2)
-        if extra:
-            return ys, log_ratio_increments, extra_solver_state
-        return ys, log_ratio_increments
+        out = [ys, (log_ratio[1:] - log_ratio[:-1]).squeeze(dim=2)]
     if extra:
-        return ys, extra_solver_state
-    return ys
+        out.append(extra_solver_state)
+    return out[0] if len(out) == 1 else tuple(out)
