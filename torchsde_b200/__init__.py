@@ -1,7 +1,7 @@
 """torchsde_b200 — B200 (sm_100a) native SDE-integration core behind the torchsde API.
 
 The eleven public names are the ones the reference exports (``torchsde/__init__.py:15-19``); their signatures are
-checked against the reference's in ``tests/test_oracle_live_reference.py``.
+checked against the reference's by the test suite.
 """
 from ._core.sdeint import sdeint
 from ._core.adjoint import sdeint_adjoint
