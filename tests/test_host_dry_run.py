@@ -1,0 +1,150 @@
+"""Dry run of the host side on the CPU: the solver / adjoint / Brownian control flow that normally needs a GPU is
+executed against a *recording stand-in* for the C library (every entry point checks its arity against the ctypes
+binding, returns 0 and computes nothing).  Numbers are meaningless here — parity lives in the `-m gpu` tests — but every
+Python path from `sdeint` / `sdeint_adjoint` down to the launch sites runs, so a broken call site, a wrong argument
+count or a stale attribute fails in the CPU suite instead of on the GPU box.  This is test scaffolding: the product
+itself has no CPU path (tests/test_host_logic.py::test_no_cpu_fallback)."""
+import warnings
+
+import pytest
+import torch
+
+import torchsde_b200 as tsde
+from torchsde_b200 import _cabi
+from torchsde_b200._brownian import interval as interval_mod
+from . import problems
+
+
+class _RecordingLib:
+    def __init__(self):
+        self.calls = {}
+
+    def __getattr__(self, name):
+        if name not in _cabi.SIGNATURES:
+            raise AttributeError(name)
+        arity = len(_cabi.SIGNATURES[name])
+
+        def entry(*args):
+            assert len(args) == arity, f"{name}: {len(args)} arguments, the C ABI declares {arity}"
+            self.calls[name] = self.calls.get(name, 0) + 1
+            return 0
+        return entry
+
+    def tsde_abi_version(self):
+        return 1
+
+    def tsde_kernel_launches(self, family):
+        return 0
+
+
+@pytest.fixture
+def dry(monkeypatch):
+    lib = _RecordingLib()
+    monkeypatch.setattr(_cabi, '_lib', lib)
+    monkeypatch.setattr(_cabi, 'lib', lambda: lib)
+    monkeypatch.setattr(_cabi, 'require_cuda', lambda *a, **k: None)
+    monkeypatch.setattr(interval_mod.BrownianInterval, '_require_cuda', lambda self: None)
+    monkeypatch.setattr(torch.cuda, 'current_stream', lambda *a, **k: type('S', (), {'cuda_stream': 0})())
+    monkeypatch.setattr(torch.cuda, 'synchronize', lambda *a, **k: None)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        yield lib
+
+
+CASES = [('gbm', 'ito', 'euler', 'none'), ('gbm', 'ito', 'milstein', 'none'), ('gbm', 'ito', 'srk', 'space-time'),
+         ('gbm', 'stratonovich', 'milstein', 'none'), ('scalar', 'stratonovich', 'midpoint', 'none'),
+         ('additive', 'ito', 'srk', 'space-time'), ('additive', 'ito', 'milstein', 'none'),
+         ('general', 'ito', 'euler', 'none'), ('general', 'stratonovich', 'heun', 'none'),
+         ('general', 'stratonovich', 'reversible_heun', 'none'), ('gbm', 'stratonovich', 'euler_heun', 'none'),
+         ('gbm', 'stratonovich', 'reversible_heun', 'none'), ('general', 'stratonovich', 'log_ode', 'foster'),
+         ('scalar', 'ito', 'srk', 'davie')]
+TS = [0.0, 0.12, 0.2]      # the middle output lies between two steps: exercises tsde_linear_interp
+
+
+def _setup(kind, sde_type, levy):
+    d, m = 3, {'gbm': 3, 'scalar': 1}.get(kind, 2)
+    sde = problems.make(kind, d, m, sde_type, dtype=torch.float32)
+    bm = tsde.BrownianInterval(0.0, TS[-1], size=(4, m), dtype=torch.float32, device='cpu',
+                               levy_area_approximation=levy)
+    return sde, torch.ones(4, d), bm
+
+
+@pytest.mark.parametrize('kind,sde_type,method,levy', CASES)
+def test_forward_paths(dry, kind, sde_type, method, levy):
+    sde, y0, bm = _setup(kind, sde_type, levy)
+    with torch.no_grad():
+        ys = tsde.sdeint(sde, y0, TS, bm=bm, method=method, dt=0.05)
+    assert ys.shape == (3, 4, 3) and dry.calls and 'tsde_linear_interp' in dry.calls
+    if method != 'log_ode':                      # gradients through the solver: every launch is an autograd node
+        sde, y0, bm = _setup(kind, sde_type, levy)
+        ys = tsde.sdeint(sde, y0.requires_grad_(), TS, bm=bm, method=method, dt=0.05)
+        ys.sum().backward()
+        assert y0.grad is not None and y0.grad.shape == y0.shape
+
+
+@pytest.mark.parametrize('kind,sde_type,method,levy', [c for c in CASES if c[2] not in ('log_ode',)])
+def test_adjoint_paths(dry, kind, sde_type, method, levy):
+    sde, y0, bm = _setup(kind, sde_type, levy)
+    ys = tsde.sdeint_adjoint(sde, y0.requires_grad_(), TS, bm=bm, method=method, dt=0.05)
+    ys.sum().backward()
+    assert y0.grad is not None and all(p.grad is not None for p in sde.parameters())
+    if method == 'reversible_heun':
+        assert dry.calls.get('tsde_adjoint_reversible_heun_a', 0) > 0 and dry.calls.get('tsde_adjoint_reversible_heun_b', 0) > 0
+
+
+def test_adaptive_logqp_names_extra_and_queries(dry):
+    sde, y0, bm = _setup('gbm', 'ito', 'none')
+    with torch.no_grad():
+        ys = tsde.sdeint(sde, y0, TS, bm=bm, method='euler', dt=0.05, adaptive=True)
+        assert ys.shape == (3, 4, 3) and dry.calls.get('tsde_adaptive_error_sumsq', 0) > 0
+
+        class Renamed(torch.nn.Module):
+            noise_type, sde_type = 'diagonal', 'ito'
+
+            def drift(self, t, y):
+                return -y
+
+            def diffusion(self, t, y):
+                return 0.1 + 0 * y
+
+            def prior(self, t, y):
+                return 0 * y
+
+        ys, logqp = tsde.sdeint(Renamed(), y0, TS, method='euler', dt=0.05, logqp=True,
+                                names={'drift': 'drift', 'diffusion': 'diffusion', 'prior_drift': 'prior'},
+                                bm=tsde.BrownianInterval(0., TS[-1], size=(4, 4), device='cpu'))
+        assert ys.shape == (3, 4, 3) and logqp.shape == (2, 4)
+        sde, y0, bm = _setup('gbm', 'stratonovich', 'none')
+        ys, extra = tsde.sdeint(sde, y0, TS, bm=bm, method='reversible_heun', dt=0.05, extra=True)
+        assert len(extra) == 3
+        # arbitrary queries: bridge below the bound grid, merges across cells, Levy area, derived objects
+        bm = tsde.BrownianInterval(0.0, 1.0, size=(4, 2), device='cpu', levy_area_approximation='foster')
+        w, u, a = bm(0.1, 0.7, return_U=True, return_A=True)
+        assert w.shape == u.shape == (4, 2) and a.shape == (4, 2, 2)
+        assert tsde.ReverseBrownian(bm)(-0.5, -0.25).shape == (4, 2)
+        assert tsde.BrownianPath(t0=0.0, w0=torch.zeros(4, 2))(0.5).shape == (4, 2)
+        assert tsde.BrownianTree(t0=0.0, w0=torch.zeros(4, 2), t1=1.0)(0.3).shape == (4, 2)
+        assert tsde.brownian_interval_like(y0)(0.0, 0.5).shape == y0.shape
+    for name in ('tsde_brownian_bridge', 'tsde_brownian_levy_area', 'tsde_brownian_h_to_u'):
+        assert dry.calls.get(name, 0) > 0, name
+
+
+def test_every_solver_entry_point_is_reached(dry):
+    """Between them the dry runs drive (almost) the whole C ABI from Python; what is left is listed explicitly."""
+    for kind, sde_type, method, levy in CASES:
+        sde, y0, bm = _setup(kind, sde_type, levy)
+        with torch.no_grad():
+            tsde.sdeint(sde, y0, TS, bm=bm, method=method, dt=0.05)
+    sde, y0, bm = _setup('gbm', 'ito', 'none')
+    with torch.no_grad():
+        tsde.sdeint(sde, y0, TS, bm=bm, method='milstein', dt=0.05, options={'grad_free': True})
+    sde, y0, bm = _setup('general', 'stratonovich', 'none')
+    tsde.sdeint_adjoint(sde, y0.requires_grad_(), TS, bm=bm, method='reversible_heun', dt=0.05).sum().backward()
+    sde, y0, bm = _setup('gbm', 'ito', 'none')
+    with torch.no_grad():
+        tsde.sdeint(sde, y0, TS, bm=bm, method='milstein', dt=0.05, adaptive=True)
+    bm = tsde.BrownianInterval(0.0, 1.0, size=(4, 2), device='cpu', levy_area_approximation='davie')
+    bm(0.0, 0.5, return_U=True, return_A=True)
+    bm(0.25, 0.75, return_U=True, return_A=True)      # covers pieces of two nodes: increments and areas are merged
+    not_reached = set(_cabi.SIGNATURES) - set(dry.calls)
+    assert not not_reached, sorted(not_reached)
