@@ -44,8 +44,42 @@ def dry(monkeypatch):
     monkeypatch.setattr(_cabi, 'lib', lambda: lib)
     monkeypatch.setattr(_cabi, 'require_cuda', lambda *a, **k: None)
     monkeypatch.setattr(interval_mod.BrownianInterval, '_require_cuda', lambda self: None)
-    monkeypatch.setattr(torch.cuda, 'current_stream', lambda *a, **k: type('S', (), {'cuda_stream': 0})())
+    # let CPU-resident intervals bind a solver grid (the product only binds on CUDA devices)
+    real_bind = interval_mod.BrownianInterval.bind_grid
+
+    def bind_grid(self, bounds):
+        device, self._device = self._device, torch.device('cuda')
+        try:
+            return real_bind(self, bounds)
+        finally:
+            self._device = device
+
+    monkeypatch.setattr(interval_mod.BrownianInterval, 'bind_grid', bind_grid)
     monkeypatch.setattr(torch.cuda, 'synchronize', lambda *a, **k: None)
+    # stand-ins for stream capture: the "captured" body simply runs once, replay does nothing
+    import contextlib
+
+    class _Stream:
+        cuda_stream = 0
+
+        def __init__(self, *a, **k):
+            pass
+
+        def wait_stream(self, other):
+            pass
+
+    class _Graph:
+        replays = 0
+
+        def replay(self):
+            type(self).replays += 1
+
+    monkeypatch.setattr(torch.cuda, 'current_stream', lambda *a, **k: _Stream())
+    monkeypatch.setattr(torch.cuda, 'Stream', _Stream)
+    monkeypatch.setattr(torch.cuda, 'stream', lambda s: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, 'CUDAGraph', _Graph)
+    monkeypatch.setattr(torch.cuda, 'graph', lambda g, **k: contextlib.nullcontext())
+    lib.graph_cls = _Graph
     with warnings.catch_warnings():
         warnings.simplefilter('ignore')
         yield lib
@@ -58,7 +92,8 @@ CASES = [('gbm', 'ito', 'euler', 'none'), ('gbm', 'ito', 'milstein', 'none'), ('
          ('general', 'stratonovich', 'reversible_heun', 'none'), ('gbm', 'stratonovich', 'euler_heun', 'none'),
          ('gbm', 'stratonovich', 'reversible_heun', 'none'), ('general', 'stratonovich', 'log_ode', 'foster'),
          ('scalar', 'ito', 'srk', 'davie')]
-TS = [0.0, 0.12, 0.2]      # the middle output lies between two steps: exercises tsde_linear_interp
+TS = [0.0, 0.09375, 0.25]  # dyadic (exact in fp32, so the Brownian grid binds); the middle output lies between two
+DT = 0.0625                # steps and exercises tsde_linear_interp
 
 
 def _setup(kind, sde_type, levy):
@@ -73,11 +108,11 @@ def _setup(kind, sde_type, levy):
 def test_forward_paths(dry, kind, sde_type, method, levy):
     sde, y0, bm = _setup(kind, sde_type, levy)
     with torch.no_grad():
-        ys = tsde.sdeint(sde, y0, TS, bm=bm, method=method, dt=0.05)
+        ys = tsde.sdeint(sde, y0, TS, bm=bm, method=method, dt=DT)
     assert ys.shape == (3, 4, 3) and dry.calls and 'tsde_linear_interp' in dry.calls
     if method != 'log_ode':                      # gradients through the solver: every launch is an autograd node
         sde, y0, bm = _setup(kind, sde_type, levy)
-        ys = tsde.sdeint(sde, y0.requires_grad_(), TS, bm=bm, method=method, dt=0.05)
+        ys = tsde.sdeint(sde, y0.requires_grad_(), TS, bm=bm, method=method, dt=DT)
         ys.sum().backward()
         assert y0.grad is not None and y0.grad.shape == y0.shape
 
@@ -85,7 +120,7 @@ def test_forward_paths(dry, kind, sde_type, method, levy):
 @pytest.mark.parametrize('kind,sde_type,method,levy', [c for c in CASES if c[2] not in ('log_ode',)])
 def test_adjoint_paths(dry, kind, sde_type, method, levy):
     sde, y0, bm = _setup(kind, sde_type, levy)
-    ys = tsde.sdeint_adjoint(sde, y0.requires_grad_(), TS, bm=bm, method=method, dt=0.05)
+    ys = tsde.sdeint_adjoint(sde, y0.requires_grad_(), TS, bm=bm, method=method, dt=DT)
     ys.sum().backward()
     assert y0.grad is not None and all(p.grad is not None for p in sde.parameters())
     if method == 'reversible_heun':
@@ -95,7 +130,7 @@ def test_adjoint_paths(dry, kind, sde_type, method, levy):
 def test_adaptive_logqp_names_extra_and_queries(dry):
     sde, y0, bm = _setup('gbm', 'ito', 'none')
     with torch.no_grad():
-        ys = tsde.sdeint(sde, y0, TS, bm=bm, method='euler', dt=0.05, adaptive=True)
+        ys = tsde.sdeint(sde, y0, TS, bm=bm, method='euler', dt=DT, adaptive=True)
         assert ys.shape == (3, 4, 3) and dry.calls.get('tsde_adaptive_error_sumsq', 0) > 0
 
         class Renamed(torch.nn.Module):
@@ -110,12 +145,12 @@ def test_adaptive_logqp_names_extra_and_queries(dry):
             def prior(self, t, y):
                 return 0 * y
 
-        ys, logqp = tsde.sdeint(Renamed(), y0, TS, method='euler', dt=0.05, logqp=True,
+        ys, logqp = tsde.sdeint(Renamed(), y0, TS, method='euler', dt=DT, logqp=True,
                                 names={'drift': 'drift', 'diffusion': 'diffusion', 'prior_drift': 'prior'},
                                 bm=tsde.BrownianInterval(0., TS[-1], size=(4, 4), device='cpu'))
         assert ys.shape == (3, 4, 3) and logqp.shape == (2, 4)
         sde, y0, bm = _setup('gbm', 'stratonovich', 'none')
-        ys, extra = tsde.sdeint(sde, y0, TS, bm=bm, method='reversible_heun', dt=0.05, extra=True)
+        ys, extra = tsde.sdeint(sde, y0, TS, bm=bm, method='reversible_heun', dt=DT, extra=True)
         assert len(extra) == 3
         # arbitrary queries: bridge below the bound grid, merges across cells, Levy area, derived objects
         bm = tsde.BrownianInterval(0.0, 1.0, size=(4, 2), device='cpu', levy_area_approximation='foster')
@@ -134,17 +169,57 @@ def test_every_solver_entry_point_is_reached(dry):
     for kind, sde_type, method, levy in CASES:
         sde, y0, bm = _setup(kind, sde_type, levy)
         with torch.no_grad():
-            tsde.sdeint(sde, y0, TS, bm=bm, method=method, dt=0.05)
+            tsde.sdeint(sde, y0, TS, bm=bm, method=method, dt=DT)
     sde, y0, bm = _setup('gbm', 'ito', 'none')
     with torch.no_grad():
-        tsde.sdeint(sde, y0, TS, bm=bm, method='milstein', dt=0.05, options={'grad_free': True})
+        tsde.sdeint(sde, y0, TS, bm=bm, method='milstein', dt=DT, options={'grad_free': True})
     sde, y0, bm = _setup('general', 'stratonovich', 'none')
-    tsde.sdeint_adjoint(sde, y0.requires_grad_(), TS, bm=bm, method='reversible_heun', dt=0.05).sum().backward()
+    tsde.sdeint_adjoint(sde, y0.requires_grad_(), TS, bm=bm, method='reversible_heun', dt=DT).sum().backward()
     sde, y0, bm = _setup('gbm', 'ito', 'none')
     with torch.no_grad():
-        tsde.sdeint(sde, y0, TS, bm=bm, method='milstein', dt=0.05, adaptive=True)
+        tsde.sdeint(sde, y0, TS, bm=bm, method='milstein', dt=DT, adaptive=True)
     bm = tsde.BrownianInterval(0.0, 1.0, size=(4, 2), device='cpu', levy_area_approximation='davie')
     bm(0.0, 0.5, return_U=True, return_A=True)
     bm(0.25, 0.75, return_U=True, return_A=True)      # covers pieces of two nodes: increments and areas are merged
     not_reached = set(_cabi.SIGNATURES) - set(dry.calls)
     assert not not_reached, sorted(not_reached)
+
+
+def test_graph_plans_are_cached_and_follow_the_parameters(dry):
+    """`options={'cuda_graph': True}` with stand-ins for stream capture: the plan is built once per (sde, shapes, grid,
+    Brownian structure), replayed on the next call, and rebuilt when the SDE's parameters are replaced."""
+    from torchsde_b200._core import graph
+    sde, y0, _ = _setup('gbm', 'ito', 'none')
+
+    def solve(method='milstein'):
+        bm = tsde.BrownianInterval(0.0, TS[-1], size=(4, 3), dtype=torch.float32, device='cpu')
+        with torch.no_grad():
+            return tsde.sdeint(sde, y0, TS, bm=bm, method=method, dt=DT, options={'cuda_graph': True})
+
+    ys = solve()
+    assert ys.shape == (3, 4, 3)
+    plans = graph._PLANS[sde]
+    assert len(plans) == 1 and dry.graph_cls.replays == 1
+    launches = sum(dry.calls.values())
+    assert solve() is ys                                   # same plan, same static output buffer
+    assert len(plans) == 1 and dry.graph_cls.replays == 2
+    assert sum(dry.calls.values()) == launches             # a replay issues no new launches from Python
+    solve('euler')
+    assert len(plans) == 2
+    sde.mu = torch.nn.Parameter(sde.mu.detach().clone())   # new storage: the old plan must not be replayed
+    solve()
+    assert len(plans) == 3
+    for _ in range(4):                                     # the per-object cache is bounded
+        sde.mu = torch.nn.Parameter(sde.mu.detach().clone())
+        solve()
+    assert len(plans) == graph.MAX_PLANS_PER_SDE
+    # row-split chains and the captured reversible-Heun adjoint sweep run through the same machinery
+    bm = tsde.BrownianInterval(0.0, TS[-1], size=(4, 3), dtype=torch.float32, device='cpu')
+    with torch.no_grad():
+        assert tsde.sdeint(sde, y0, TS, bm=bm, method='milstein', dt=DT,
+                           options={'cuda_graph': True, 'row_split': 2}).shape == (3, 4, 3)
+    sde2, y02, bm2 = _setup('gbm', 'stratonovich', 'none')
+    ys = tsde.sdeint_adjoint(sde2, y02.requires_grad_(), TS, bm=bm2, method='reversible_heun', dt=DT,
+                             options={'cuda_graph': True}, adjoint_options={'cuda_graph': True})
+    ys.sum().backward()
+    assert y02.grad is not None and all(p.grad is not None for p in sde2.parameters())
