@@ -610,3 +610,78 @@ def test_logqp_augmentation_equals_the_live_reference(kind):
         our_base.SDELogqp(problems.make(kind, d, m, 'ito'))
     with pytest.raises(AttributeError):
         ref_base.SDELogqp(problems.make(kind, d, m, 'ito'))
+
+
+from .test_host_dry_run import dry  # noqa: E402,F401  (fixture: recording stand-in for the C library)
+
+
+class _Partial(torch.nn.Module):
+    """General-noise SDE that exposes only a chosen subset of the five callables of the user-SDE protocol."""
+    noise_type = 'general'
+
+    def __init__(self, which, sde_type):
+        super().__init__()
+        self.sde_type = sde_type
+        self.w = torch.nn.Parameter(torch.rand(3, 2, generator=torch.Generator().manual_seed(1)))
+        self.offered = tuple(which)
+
+    def __getattr__(self, name):
+        if name in ('f', 'g', 'f_and_g', 'g_prod', 'f_and_g_prod'):
+            if name in self.__dict__.get('offered', ()):
+                return getattr(self, '_' + name)
+            raise AttributeError(name)
+        return super().__getattr__(name)
+
+    def _f(self, t, y):
+        return -y
+
+    def _g(self, t, y):
+        return torch.tanh(y).unsqueeze(-1) * self.w
+
+    def _f_and_g(self, t, y):
+        return self._f(t, y), self._g(t, y)
+
+    def _g_prod(self, t, y, v):
+        return (self._g(t, y) * v.unsqueeze(1)).sum(-1)
+
+    def _f_and_g_prod(self, t, y, v):
+        return self._f(t, y), self._g_prod(t, y, v)
+
+
+_SUBSETS = [('f', 'g'), ('f_and_g',), ('f', 'g_prod'), ('f_and_g_prod',), ('f', 'g', 'g_prod'), ('f_and_g', 'f_and_g_prod'),
+            ('g',), ('f',), ('g_prod',), ('f', 'g', 'f_and_g', 'g_prod', 'f_and_g_prod')]
+
+
+@pytest.mark.parametrize('method,sde_type', [('euler', 'ito'), ('heun', 'stratonovich'), ('midpoint', 'stratonovich'),
+                                             ('euler_heun', 'stratonovich'), ('reversible_heun', 'stratonovich')])
+@pytest.mark.parametrize('which', _SUBSETS, ids=lambda w: '+'.join(w))
+def test_partial_sde_protocols_behave_like_the_live_reference(dry, which, method, sde_type):  # noqa: F811
+    """Which subsets of {f, g, f_and_g, g_prod, f_and_g_prod} suffice for which solver, and how a missing callable
+    surfaces (ValueError from the contract check, or RuntimeError "Method `g` has not been provided…" at call time,
+    base_sde.py:78-85): the product — dry-run on the CPU — must accept, reject and word it exactly like the reference."""
+    import warnings
+    import torchsde_b200 as tsde
+    ts, dt = [0.0, 0.09375, 0.25], 0.0625
+
+    def outcome(mod):
+        sde = _Partial(which, sde_type)
+        kw = {} if mod is torchsde else {'device': 'cpu'}
+        try:
+            with warnings.catch_warnings(), torch.no_grad():
+                warnings.simplefilter('ignore')
+                ys = mod.sdeint(sde, torch.ones(4, 3), ts, method=method, dt=dt,
+                                bm=mod.BrownianInterval(0., .25, size=(4, 2), **kw))
+            return ('ok', tuple(ys.shape))
+        except (ValueError, RuntimeError) as e:
+            return (type(e).__name__, str(e))
+
+    ours, ref = outcome(tsde), outcome(torchsde)
+    if method == 'euler_heun' and 'f_and_g_prod' in which and not {'g', 'g_prod'} & set(which):
+        # One deliberate superset: Euler-Heun's second diffusion product g(t0, y').dW.  The reference asks `g_prod` for
+        # it, whose default needs `g` (RuntimeError when the SDE offers neither); the product obtains it from the user's
+        # `f_and_g_prod` — same value, so an SDE that only provides the fused callable still solves.
+        assert ours[0] == 'ok' and ref[0] == 'RuntimeError'
+        return
+    assert ours[0] == ref[0], (which, method, ours, ref)
+    if ours[0] == 'RuntimeError':
+        assert ours[1] == ref[1]
