@@ -685,3 +685,77 @@ def test_partial_sde_protocols_behave_like_the_live_reference(dry, which, method
     assert ours[0] == ref[0], (which, method, ours, ref)
     if ours[0] == 'RuntimeError':
         assert ours[1] == ref[1]
+
+
+@pytest.mark.parametrize('query', [(0.5, 0.2), (-1.0, 0.5), (0.5, 2.0), (-2.0, -1.0), (0.3, 0.3), (0.25, None), (0.0, 1.0),
+                                   (torch.tensor(0.1), torch.tensor(0.6))], ids=str)
+@pytest.mark.parametrize('levy', ['none', 'space-time', 'foster'])
+def test_query_contract_equals_the_live_reference(dry, query, levy):  # noqa: F811
+    """`BrownianInterval.__call__` (brownian_interval.py:589-687): reversed times raise RuntimeError, times outside
+    [t0, t1] warn and are clamped, `tb=None` is a point query from t0, and the tuple returned for every
+    (return_U, return_A) combination has the same arity and shapes.  (Values are a GPU matter; dry run here.)"""
+    import warnings
+    import torchsde_b200 as tsde
+    ta, tb = query
+
+    def outcome(mod):
+        kw = {} if mod is torchsde else {'device': 'cpu'}
+        bm = mod.BrownianInterval(0.0, 1.0, size=(3, 2), dtype=torch.float64, levy_area_approximation=levy, **kw)
+        results = []
+        for want_u in (False, True):
+            for want_a in (False, True):
+                if (want_u and levy == 'none') or (want_a and levy != 'foster'):
+                    continue
+                with warnings.catch_warnings(record=True) as caught:
+                    warnings.simplefilter('always')
+                    try:
+                        out = bm(ta, tb, return_U=want_u, return_A=want_a)
+                    except (RuntimeError, ValueError) as e:
+                        results.append((want_u, want_a, type(e).__name__))
+                        continue
+                out = out if isinstance(out, tuple) else (out,)
+                results.append((want_u, want_a, tuple(tuple(o.shape) for o in out),
+                                sorted({w.category.__name__ for w in caught})))
+        return results
+
+    assert outcome(tsde) == outcome(torchsde)
+
+
+def _warning_cases():
+    yield 'unused kwarg', 'sdeint', dict(method='euler', foo=1)
+    yield 'adaptive euler, non-additive noise', 'sdeint', dict(method='euler', adaptive=True)
+    yield 'plain', 'sdeint', dict(method='euler')
+    yield 'adjoint unused kwarg', 'sdeint_adjoint', dict(method='euler', bar=2)
+    yield 'reversible forward, generic adjoint', 'sdeint_adjoint', dict(method='reversible_heun', adjoint_method='midpoint')
+    yield 'reversible pair, ts off the step grid', 'sdeint_adjoint', dict(method='reversible_heun', ts=[0.0, 0.1, 0.25])
+    yield 'reversible pair, aligned', 'sdeint_adjoint', dict(method='reversible_heun')
+    yield 'reversible pair, adaptive', 'sdeint_adjoint', dict(method='reversible_heun', adaptive=True)
+
+
+@pytest.mark.parametrize('label', [c[0] for c in _warning_cases()])
+def test_warnings_equal_the_live_reference(dry, label):  # noqa: F811
+    """User-facing warnings of sdeint / sdeint_adjoint (misc.py:26-31, sdeint.py:270-274, adjoint.py:240-256): same
+    categories, same first sentence."""
+    import warnings
+    import torchsde_b200 as tsde
+    _, fn, kwargs = next(c for c in _warning_cases() if c[0] == label)
+    kwargs = dict(kwargs)
+    ts = kwargs.pop('ts', [0.0, 0.125, 0.25])
+    sde_type = 'stratonovich' if kwargs.get('method') == 'reversible_heun' else 'ito'
+
+    def collect(mod):
+        sde = problems.make('gbm', 3, 3, sde_type, dtype=torch.float32)
+        kw = {} if mod is torchsde else {'device': 'cpu'}
+        bm = mod.BrownianInterval(0.0, 0.25, size=(4, 3), dtype=torch.float32, **kw)
+        with warnings.catch_warnings(record=True) as caught:
+            warnings.simplefilter('always')
+            try:
+                getattr(mod, fn)(sde, torch.ones(4, 3), ts, bm=bm, dt=0.0625, **kwargs)
+            except NotImplementedError:
+                pass
+        return sorted((w.category.__name__, str(w.message)[:40]) for w in caught
+                      if 'torchsde' in str(w.filename) or 'sdeint' in str(w.message) or True)
+
+    ours, ref = collect(tsde), collect(torchsde)
+    assert [c for c, _ in ours] == [c for c, _ in ref], (ours, ref)
+    assert ours == ref, (ours, ref)
