@@ -759,3 +759,55 @@ def test_warnings_equal_the_live_reference(dry, label):  # noqa: F811
     ours, ref = collect(tsde), collect(torchsde)
     assert [c for c, _ in ours] == [c for c, _ in ref], (ours, ref)
     assert ours == ref, (ours, ref)
+
+
+class _LoggingBM:
+    """Duck-typed Brownian motion (the reference accepts any object with this call signature, base_solver.py:54-57):
+    returns zeros and logs how it was asked."""
+
+    def __init__(self, shape, levy, dtype=torch.float32):
+        self.shape, self.levy_area_approximation, self.dtype = shape, levy, dtype
+        self.device = torch.device('cpu')
+        self.log = []
+
+    def __call__(self, ta, tb=None, return_U=False, return_A=False):
+        self.log.append((round(float(ta), 9), None if tb is None else round(float(tb), 9), bool(return_U), bool(return_A)))
+        W = torch.zeros(self.shape, dtype=self.dtype)
+        out = [W]
+        if return_U:
+            out.append(torch.zeros_like(W))
+        if return_A:
+            out.append(torch.zeros(*self.shape, self.shape[-1], dtype=self.dtype))
+        return out[0] if len(out) == 1 else tuple(out)
+
+
+@pytest.mark.parametrize('kind,sde_type,method,levy', [
+    ('gbm', 'ito', 'euler', 'none'), ('gbm', 'ito', 'milstein', 'none'), ('gbm', 'ito', 'srk', 'space-time'),
+    ('additive', 'ito', 'srk', 'space-time'), ('general', 'stratonovich', 'heun', 'none'),
+    ('scalar', 'stratonovich', 'midpoint', 'none'), ('gbm', 'stratonovich', 'euler_heun', 'none'),
+    ('general', 'stratonovich', 'reversible_heun', 'none'), ('general', 'stratonovich', 'log_ode', 'foster')])
+def test_brownian_queries_are_made_like_the_live_reference(dry, kind, sde_type, method, levy):  # noqa: F811
+    """With a user-supplied (duck-typed) Brownian object the solver must ask for exactly the increments the reference
+    asks for — same intervals, same order, once per step, same return_U / return_A flags — in the forward pass and in
+    the backward pass of `sdeint_adjoint`."""
+    import warnings
+    import torchsde_b200 as tsde
+    d, m = 3, {'gbm': 3, 'scalar': 1}.get(kind, 2)
+    ts, dt = [0.0, 0.09375, 0.25], 0.0625
+
+    def run(mod, adjoint):
+        sde = problems.make(kind, d, m, sde_type, dtype=torch.float32)
+        bm = _LoggingBM((4, m), levy)
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            if adjoint:
+                ys = mod.sdeint_adjoint(sde, torch.ones(4, d, requires_grad=True), ts, bm=bm, method=method, dt=dt)
+                ys.sum().backward()
+            else:
+                with torch.no_grad():
+                    mod.sdeint(sde, torch.ones(4, d), ts, bm=bm, method=method, dt=dt)
+        return bm.log
+
+    assert run(tsde, False) == run(torchsde, False)
+    if method not in ('srk', 'log_ode'):
+        assert run(tsde, True) == run(torchsde, True)
