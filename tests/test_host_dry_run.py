@@ -223,3 +223,17 @@ def test_graph_plans_are_cached_and_follow_the_parameters(dry):
                              options={'cuda_graph': True}, adjoint_options={'cuda_graph': True})
     ys.sum().backward()
     assert y02.grad is not None and all(p.grad is not None for p in sde2.parameters())
+
+
+@pytest.mark.parametrize('kind,sde_type,method,levy', [('gbm', 'ito', 'euler', 'none'), ('gbm', 'ito', 'milstein', 'none'),
+                                                       ('gbm', 'ito', 'srk', 'space-time'),
+                                                       ('general', 'stratonovich', 'heun', 'none')])
+def test_empty_batch_flows_through(dry, kind, sde_type, method, levy):
+    """Zero trajectories: the host side must still produce a (T, 0, d) series (the C entry points return early on
+    empty launches; the reference itself handles B = 0 for most methods)."""
+    d, m = 3, {'gbm': 3}.get(kind, 2)
+    sde = problems.make(kind, d, m, sde_type, dtype=torch.float32)
+    for bm in (None, tsde.BrownianInterval(0., TS[-1], size=(0, m), device='cpu', levy_area_approximation=levy)):
+        with torch.no_grad():
+            ys = tsde.sdeint(sde, torch.ones(0, d), TS, method=method, dt=DT, bm=bm)
+        assert ys.shape == (3, 0, d)
