@@ -859,3 +859,49 @@ def test_user_callables_are_evaluated_like_the_live_reference(dry, noise, sde_ty
         assert set(ours) == set(ref) and len(ours) < len(ref)
     else:
         assert ours == ref
+
+
+class _PlainSDE:
+    """Not an nn.Module: parameters must be named explicitly for the adjoint (adjoint.py:228-231)."""
+    noise_type, sde_type = 'diagonal', 'ito'
+
+    def __init__(self):
+        self.c = torch.ones(3, requires_grad=True)
+        self.frozen = torch.ones(3)
+
+    def f(self, t, y):
+        return -self.c * y * self.frozen
+
+    def g(self, t, y):
+        return 0.1 * y
+
+
+@pytest.mark.parametrize('label', ['missing', 'empty tuple', 'explicit', 'with a frozen tensor', 'module default'])
+def test_adjoint_params_contract_equals_the_live_reference(dry, label):  # noqa: F811
+    import warnings
+    import torchsde_b200 as tsde
+
+    def outcome(mod):
+        plain = _PlainSDE()
+        sde, kw = plain, {}
+        if label == 'empty tuple':
+            kw = dict(adjoint_params=())
+        elif label == 'explicit':
+            kw = dict(adjoint_params=(plain.c,))
+        elif label == 'with a frozen tensor':
+            kw = dict(adjoint_params=(plain.c, plain.frozen))
+        elif label == 'module default':
+            sde = problems.make('gbm', 3, 3, 'ito', dtype=torch.float32)
+        y0 = torch.ones(4, 3, requires_grad=True)
+        bkw = {} if mod is torchsde else {'device': 'cpu'}
+        try:
+            with warnings.catch_warnings():
+                warnings.simplefilter('ignore')
+                ys = mod.sdeint_adjoint(sde, y0, [0.0, 0.125, 0.25], method='euler', dt=0.0625,
+                                        bm=mod.BrownianInterval(0., .25, size=(4, 3), **bkw), **kw)
+                ys.sum().backward()
+        except Exception as e:  # noqa: BLE001
+            return type(e).__name__
+        return ('ok', y0.grad is not None, plain.c.grad is not None, plain.frozen.grad is not None)
+
+    assert outcome(tsde) == outcome(torchsde), label
