@@ -905,3 +905,43 @@ def test_adjoint_params_contract_equals_the_live_reference(dry, label):  # noqa:
         return ('ok', y0.grad is not None, plain.c.grad is not None, plain.frozen.grad is not None)
 
     assert outcome(tsde) == outcome(torchsde), label
+
+
+@pytest.mark.parametrize('cls,kwargs', [('BrownianPath', dict(t0=0.0, w0=torch.zeros(3, 2))),
+                                        ('BrownianTree', dict(t0=0.0, w0=torch.zeros(3, 2), t1=1.0)),
+                                        ('BrownianTree', dict(t0=0.0, w0=torch.zeros(3, 2), t1=1.0, w1=torch.ones(3, 2)))],
+                         ids=['path', 'tree', 'tree with w1'])
+@pytest.mark.parametrize('query', [(0.5, None), (0.25, 0.75), (0.0, None), (1.0, None), (0.75, 0.25), (1.5, None),
+                                   (-0.5, None)], ids=str)
+def test_derived_brownian_queries_equal_the_live_reference(dry, cls, kwargs, query):  # noqa: F811
+    """BrownianPath / BrownianTree (derived.py:52-172): point queries return w0 + W(t0, t); interval queries the
+    increment; same shapes, errors and warnings as the reference (values are a GPU matter)."""
+    import warnings
+    import torchsde_b200 as tsde
+    ta, tb = query
+
+    def outcome(mod):
+        with warnings.catch_warnings(record=True) as caught:
+            warnings.simplefilter('always')
+            bm = getattr(mod, cls)(**kwargs)
+            try:
+                out = bm(ta) if tb is None else bm(ta, tb)
+            except Exception as e:  # noqa: BLE001
+                return type(e).__name__
+        return (tuple(out.shape), out.dtype, sorted({w.category.__name__ for w in caught}))
+
+    assert outcome(tsde) == outcome(torchsde)
+
+
+def test_reverse_brownian_equals_the_live_reference(dry):  # noqa: F811
+    """ReverseBrownian (derived.py:22-49): time reversal (ta, tb) -> base(-tb, -ta), attribute forwarding."""
+    import torchsde_b200 as tsde
+    outs = []
+    for mod in (tsde, torchsde):
+        kw = {} if mod is torchsde else {'device': 'cpu'}
+        base = mod.BrownianInterval(0.0, 1.0, size=(3, 2), levy_area_approximation='space-time', **kw)
+        rev = mod.ReverseBrownian(base)
+        w, u = rev(-0.75, -0.25, return_U=True)
+        outs.append((tuple(w.shape), tuple(u.shape), tuple(rev.shape), rev.dtype, rev.levy_area_approximation,
+                     rev.base_brownian is base))
+    assert outs[0] == outs[1]
