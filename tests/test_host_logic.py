@@ -339,3 +339,61 @@ def test_plan_cache_tolerates_unhashable_sde_objects():
     mod = problems.GBMDiagonal(2, 'ito')
     d = plans_of(cache, mod)
     assert d == {} and plans_of(cache, mod) is d
+
+
+def test_cabi_rejects_malformed_calls_without_touching_the_device():
+    """Contract violations are TSDE_EINVAL from every compute entry point — a null launch descriptor, a valid one with
+    null operands, negative sizes — checked before any CUDA call (so this runs on a machine without a GPU, in a child
+    process because a regression here is a segfault).  An empty launch is a no-op (0)."""
+    import subprocess
+    import sys
+    import textwrap
+    code = textwrap.dedent('''
+        import ctypes, sys
+        sys.path.insert(0, %r)
+        import torch
+        from torchsde_b200 import _cabi
+        lib = _cabi.lib()
+        EINVAL = -22
+
+        def args_for(name, launch):
+            out = []
+            for t in _cabi.SIGNATURES[name]:
+                if t is _cabi._D:
+                    out.append(0.0)
+                elif t is _cabi._L:
+                    out.append(launch)
+                elif t in (_cabi._I, ctypes.c_int64, ctypes.c_uint64):
+                    out.append(0)
+                else:
+                    out.append(None)
+            return out
+
+        ok = _cabi.make_launch(torch.float32, _cabi.NOISE_DIAGONAL, 4, 8, 8, 0)
+        negative = _cabi.make_launch(torch.float32, _cabi.NOISE_DIAGONAL, -1, 8, 8, 0)
+        no_width = _cabi.make_launch(torch.float64, _cabi.NOISE_GENERAL, 4, 8, 0, 0)
+        for name in _cabi.SIGNATURES:
+            for launch in (None, ctypes.byref(ok), ctypes.byref(negative), ctypes.byref(no_width)):
+                rc = getattr(lib, name)(*args_for(name, launch))
+                assert rc == EINVAL, (name, rc)
+        # an empty launch returns 0 before touching the device
+        empty = _cabi.make_launch(torch.float32, _cabi.NOISE_DIAGONAL, 0, 8, 8, 0)
+        buf = (ctypes.c_float * 64)()
+        p = ctypes.addressof(buf)
+        nz = _cabi.Noise()
+        nz.source, nz.w = _cabi.SRC_MEMORY, p
+        assert lib.tsde_step_euler(ctypes.byref(empty), ctypes.byref(nz), p, p, p, 0.1, p) == 0
+        assert lib.tsde_linear_interp(ctypes.byref(empty), p, p, 0.5, 0.5, p) == 0
+        # wrong dtype code, diagonal noise with m != d, Milstein on general noise
+        bad_dtype = _cabi.make_launch(torch.float32, _cabi.NOISE_DIAGONAL, 4, 8, 8, 0)
+        bad_dtype.dtype = 7
+        assert lib.tsde_step_euler(ctypes.byref(bad_dtype), ctypes.byref(nz), p, p, p, 0.1, p) == EINVAL
+        skew = _cabi.make_launch(torch.float32, _cabi.NOISE_DIAGONAL, 4, 8, 4, 0)
+        assert lib.tsde_step_euler(ctypes.byref(skew), ctypes.byref(nz), p, p, p, 0.1, p) == EINVAL
+        general = _cabi.make_launch(torch.float32, _cabi.NOISE_GENERAL, 4, 8, 4, 0)
+        assert lib.tsde_milstein_vjp_seed(ctypes.byref(general), ctypes.byref(nz), p, 0.1, 1, p) == EINVAL
+        assert b'invalid argument' in lib.tsde_error_string(EINVAL)
+        print('validated', len(_cabi.SIGNATURES))
+    ''' % ROOT)
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True)
+    assert r.returncode == 0 and f'validated {len(_cabi.SIGNATURES)}' in r.stdout, (r.returncode, r.stdout[-300:], r.stderr[-600:])

@@ -461,6 +461,7 @@ static tsde_launch as_rows_m(const tsde_launch* L) {
 
 int tsde_brownian_merge(const tsde_launch* L, void* w0, void* h0, const void* w1, const void* h1,
                         double len0, double len1, double tot) {
+  if (tsde::launch_invalid(L)) return TSDE_EINVAL;
   const tsde_launch r = as_rows_m(L);
   if (h0 && h1) {
     const void* ins[4] = {w0, h0, w1, h1};
@@ -482,6 +483,7 @@ int tsde_brownian_merge(const tsde_launch* L, void* w0, void* h0, const void* w1
 
 int tsde_brownian_h_to_u(const tsde_launch* L, const void* w, const void* hh, double h,
                          void* out_u) {
+  if (tsde::launch_invalid(L)) return TSDE_EINVAL;
   const tsde_launch r = as_rows_m(L);
   const void* ins[2] = {w, hh};
   void* outs[1] = {out_u};
@@ -493,6 +495,7 @@ int tsde_brownian_h_to_u(const tsde_launch* L, const void* w, const void* hh, do
 int tsde_brownian_levy_area(const tsde_launch* L, const void* key, int64_t row_offset,
                             uint64_t a_id, const void* w, const void* hh, double h, int32_t foster,
                             void* out_a) {
+  if (tsde::launch_invalid(L)) return TSDE_EINVAL;
   return TSDE_DISPATCH_DTYPE(
       L, levy_impl<float>(L, key, row_offset, a_id, w, hh, h, foster, out_a),
       levy_impl<double>(L, key, row_offset, a_id, w, hh, h, foster, out_a));
@@ -500,6 +503,7 @@ int tsde_brownian_levy_area(const tsde_launch* L, const void* key, int64_t row_o
 
 int tsde_brownian_merge_area(const tsde_launch* L, void* a0, const void* a1, const void* w0,
                              const void* w1) {
+  if (tsde::launch_invalid(L)) return TSDE_EINVAL;
   return TSDE_DISPATCH_DTYPE(L, merge_area_impl<float>(L, a0, a1, w0, w1),
                              merge_area_impl<double>(L, a0, a1, w0, w1));
 }

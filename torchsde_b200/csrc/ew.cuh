@@ -512,7 +512,13 @@ inline int launch_ew(const tsde_launch* L, const tsde_noise* nz, bool bcast,
   }
 }
 
-#define TSDE_DISPATCH_DTYPE(L, EXPR_F32, EXPR_F64) \
-  ((L)->dtype == TSDE_F32 ? (EXPR_F32) : (L)->dtype == TSDE_F64 ? (EXPR_F64) : TSDE_EINVAL)
+// A launch descriptor every entry point can rely on: non-null, non-negative row count, positive widths.
+inline bool launch_invalid(const tsde_launch* L) { return !L || L->rows < 0 || L->d <= 0 || L->m <= 0; }
+
+#define TSDE_DISPATCH_DTYPE(L, EXPR_F32, EXPR_F64)                                                   \
+  (::tsde::launch_invalid(L) ? TSDE_EINVAL                                                           \
+   : (L)->dtype == TSDE_F32  ? (EXPR_F32)                                                            \
+   : (L)->dtype == TSDE_F64  ? (EXPR_F64)                                                            \
+                             : TSDE_EINVAL)
 
 }  // namespace tsde
