@@ -392,6 +392,18 @@ def test_cabi_rejects_malformed_calls_without_touching_the_device():
         assert lib.tsde_step_euler(ctypes.byref(skew), ctypes.byref(nz), p, p, p, 0.1, p) == EINVAL
         general = _cabi.make_launch(torch.float32, _cabi.NOISE_GENERAL, 4, 8, 4, 0)
         assert lib.tsde_milstein_vjp_seed(ctypes.byref(general), ctypes.byref(nz), p, 0.1, 1, p) == EINVAL
+        # noise descriptor: unknown source code, counter source without a key, (W, U) requested from memory without U
+        for noise_type, m in ((_cabi.NOISE_DIAGONAL, 8), (_cabi.NOISE_GENERAL, 4)):
+            launch = _cabi.make_launch(torch.float32, noise_type, 4, 8, m, 0)
+            bad = _cabi.Noise()
+            bad.source, bad.w = 99, p
+            assert lib.tsde_step_euler(ctypes.byref(launch), ctypes.byref(bad), p, p, p, 0.1, p) == EINVAL
+            bad.source, bad.key = _cabi.SRC_COUNTER, None
+            assert lib.tsde_step_euler(ctypes.byref(launch), ctypes.byref(bad), p, p, p, 0.1, p) == EINVAL
+        need_u = _cabi.Noise()
+        need_u.source, need_u.w, need_u.want_u, need_u.u = _cabi.SRC_MEMORY, p, 1, None
+        assert lib.tsde_step_srk_diag(ctypes.byref(ok), ctypes.byref(need_u), p, p, p, p, p, p, p, p, 0.1, 10.0, 0.3, 0.3,
+                                      p) == EINVAL
         assert b'invalid argument' in lib.tsde_error_string(EINVAL)
         print('validated', len(_cabi.SIGNATURES))
     ''' % ROOT)

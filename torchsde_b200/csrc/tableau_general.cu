@@ -775,7 +775,8 @@ static int launch_gen(const tsde_launch* L, const tsde_noise* nz,
                       std::initializer_list<const void*> es, std::initializer_list<const void*> gs,
                       std::initializer_list<void*> os, const Op& op) {
   if (!nz) return TSDE_EINVAL;
-  if (nz->source == TSDE_SRC_UNIT) return TSDE_EINVAL;  // g_prod given -> diagonal entry points
+  if (nz->source != TSDE_SRC_MEMORY && nz->source != TSDE_SRC_COUNTER)
+    return TSDE_EINVAL;  // (a user-supplied product, TSDE_SRC_UNIT, goes through the element-wise entry points)
   GenP<Op::NE, Op::NG, Op::NO> p{};
   bool vec = (L->m % 4) == 0;
   int i = 0;
@@ -1010,6 +1011,7 @@ template <typename T>
 static int launch_outer(const tsde_launch* L, const tsde_noise* nz, const void* base,
                         const void* a1, double c1, const void* a2, double c2, void* out) {
   if (!nz || !a1 || !out) return TSDE_EINVAL;
+  if (nz->source != TSDE_SRC_MEMORY && nz->source != TSDE_SRC_COUNTER) return TSDE_EINVAL;
   NoiseP<T> np;
   if (int e = fill_noise<T>(L, nz, false, np)) return e;
   const int64_t total = L->rows * L->d * ((L->m + 3) / 4);
