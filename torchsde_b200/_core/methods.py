@@ -8,12 +8,22 @@ reference's ``step`` by one or two launches through the C ABI (include/torchsde_
 ``self._k(name, L, nz, inputs, scalars, outputs)`` (base_solver.py) — a direct launch on the fast path,
 an autograd node when gradients must flow through the solve.
 """
+import numpy as np
 import torch
 
 from . import base_solver
 from .base_solver import _contig
 from ..settings import SDE_TYPES, NOISE_TYPES, LEVY_AREA_APPROXIMATIONS, METHODS, METHOD_OPTIONS
 
+
+
+def _ieee_sqrt(dt):
+    """sqrt of a 0-d CPU tensor, correctly rounded in its dtype.  The reference writes `dt.sqrt()` on a tensor that lives
+    on the solve's device — on a GPU that is the IEEE square root.  PyTorch's *CPU* sqrt kernel is not correctly rounded
+    on AVX-512 builds (about 1 % of inputs come out one ulp off, e.g. sqrt(2^-5) in fp64), so evaluating the same
+    expression on the host would make SRK / derivative-free Milstein depend on the host's vector ISA; numpy's sqrt is the
+    hardware instruction."""
+    return torch.tensor(np.sqrt(dt.detach().numpy()), dtype=dt.dtype)
 
 class _ProdMixin:
     """Shared handling of the reference's `f_and_g_prod` / `g_prod` call sites (base_sde.py:51-56)."""
@@ -84,7 +94,7 @@ class BaseMilstein(_ProdMixin, base_solver.BaseSDESolver):
         self._ones = None
 
     def scalars(self, dt):
-        sqrt_dt = dt.sqrt()
+        sqrt_dt = _ieee_sqrt(dt)
         return {'sqrt_dt': float(sqrt_dt), 'two_sqrt_dt': float(2 * sqrt_dt)}
 
     def _step(self, c, y0, extra0, out):
@@ -275,7 +285,7 @@ class SRK(base_solver.BaseSDESolver):
         return [t0 + 0 * dt, t0 + 1 * dt, t0 + (1 / 4) * dt, t0 + (1 / 2) * dt]
 
     def scalars(self, dt):
-        return {'rdt': float(1 / dt), 'sqrt_dt': float(dt.sqrt()), 'three_dt': float(3 * dt)}
+        return {'rdt': float(1 / dt), 'sqrt_dt': float(_ieee_sqrt(dt)), 'three_dt': float(3 * dt)}
 
     def _step(self, c, y0, extra0, out):
         if self.sde.user_g_prod:
