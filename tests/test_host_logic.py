@@ -409,3 +409,19 @@ def test_cabi_rejects_malformed_calls_without_touching_the_device():
     ''' % ROOT)
     r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True)
     assert r.returncode == 0 and f'validated {len(_cabi.SIGNATURES)}' in r.stdout, (r.returncode, r.stdout[-300:], r.stderr[-600:])
+
+
+def test_c_client_of_the_abi(tmp_path):
+    """The boundary is usable from plain C: tests/c/abi_client.c includes the public header, dlopens the library and
+    checks version, struct sizes, diagnostics and argument validation (everything that needs no GPU)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which('gcc')
+    if gcc is None:
+        pytest.skip("no gcc")
+    _cabi.lib()  # make sure the library is built
+    exe = str(tmp_path / 'abi_client')
+    subprocess.run([gcc, '-std=c99', '-Wall', '-Wextra', '-Werror', '-I', os.path.join(ROOT, 'include'),
+                    os.path.join(ROOT, 'tests', 'c', 'abi_client.c'), '-o', exe, '-ldl'], check=True)
+    r = subprocess.run([exe, _cabi.LIB_PATH], capture_output=True, text=True)
+    assert r.returncode == 0 and 'c client ok, abi 1' in r.stdout, (r.returncode, r.stdout, r.stderr)
