@@ -59,6 +59,14 @@ enum {
   TSDE_SRC_UNIT    = 2  /* W == 1: `g` already holds the user's g_prod (base_sde.py:51-56) */
 };
 
+/* Launch flags (tsde_noise.flags).
+ * TSDE_FLAG_G_BROADCAST: every (rows,d,m) diffusion operand of this launch is ONE dense (d,m) block shared by
+ * all rows (row stride 0) — what `sigma.expand(B, d, m)` is for additive noise whose diffusion does not depend on
+ * y (the reference's own additive test problem materialises it with `repeat`, tests/problems.py:113-116; the
+ * product base_sde.py:101-102 / misc.py:62-63 only ever reads it).  Honoured by the general-noise entry points
+ * (noise_type GENERAL, m > 1); the pointer then addresses d*m elements. */
+#define TSDE_FLAG_G_BROADCAST 1
+
 /* Shape / stream descriptor shared by all launches. */
 typedef struct tsde_launch {
   int32_t dtype;      /* TSDE_F32 | TSDE_F64                       */
@@ -91,7 +99,7 @@ typedef struct tsde_noise {
   uint64_t    cell_id;    /* COUNTER: counter words 2,3 of the first cell                  */
   int64_t     row_offset; /* COUNTER: global index of local row 0 (batch sharding)         */
   int32_t     n_cells;    /* COUNTER: number of consecutive cells merged (>= 1)            */
-  int32_t     reserved;
+  int32_t     flags;      /* TSDE_FLAG_* of this launch (0 = none)                         */
   double      h;          /* COUNTER: length of each cell when cell_h == NULL              */
   const double* cell_h;   /* COUNTER: DEVICE pointer to n_cells lengths, or NULL (uniform) */
   double      h_total;    /* COUNTER: tb - ta of the whole step (U = h_total (W/2 + H))    */

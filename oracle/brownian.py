@@ -92,23 +92,23 @@ def davie_foster(W, H, h, foster, noise):
 
 
 # ---- this repository's counter-based source (spec restated; see philox.py) ----------------------
-def cell(key, cell_id, h, rows, m, dtype, have_h, row_offset=0):
+def cell(key, cell_id, h, rows, m, dtype, have_h, row_offset=0, row_ids=None):
     """Direct draw of a primary cell: W = sqrt(h) N_W, H = sqrt(h/12) N_H — the law of the top
     interval in the reference (brownian_interval.py:553-558)."""
-    W = philox.normals(key, cell_id, philox.STREAM_W, rows, m, dtype, row_offset) * _s(math.sqrt(h), dtype)
+    W = philox.normals(key, cell_id, philox.STREAM_W, rows, m, dtype, row_offset, row_ids) * _s(math.sqrt(h), dtype)
     H = None
     if have_h:
-        H = philox.normals(key, cell_id, philox.STREAM_H, rows, m, dtype, row_offset) * _s(math.sqrt(h / 12), dtype)
+        H = philox.normals(key, cell_id, philox.STREAM_H, rows, m, dtype, row_offset, row_ids) * _s(math.sqrt(h / 12), dtype)
     return W, H
 
 
-def cells(key, cell_id, lengths, rows, m, dtype, have_h, row_offset=0):
+def cells(key, cell_id, lengths, rows, m, dtype, have_h, row_offset=0, row_ids=None):
     """Merge of consecutive primary cells (ids cell_id, cell_id+1, ...), left to right with `merge`
     (elapsed time accumulated in float64, as csrc/ew.cuh counter_noise does)."""
-    W, H = cell(key, cell_id, lengths[0], rows, m, dtype, have_h, row_offset)
+    W, H = cell(key, cell_id, lengths[0], rows, m, dtype, have_h, row_offset, row_ids)
     elapsed = lengths[0]
     for c in range(1, len(lengths)):
-        Wi, Hi = cell(key, (cell_id + c) & ((1 << 64) - 1), lengths[c], rows, m, dtype, have_h, row_offset)
+        Wi, Hi = cell(key, (cell_id + c) & ((1 << 64) - 1), lengths[c], rows, m, dtype, have_h, row_offset, row_ids)
         # merge() with ta = 0, start_i = elapsed, end_i = elapsed + len  (term coefficients: len, elapsed, total)
         dt = W.dtype
         if have_h:
@@ -130,6 +130,7 @@ def bridge_chain(key, W, H, levels, row_offset=0):
     return W, H
 
 
-def levy_noise(key, a_id, rows, m, dtype, row_offset=0):
+def levy_noise(key, a_id, rows, m, dtype, row_offset=0, row_ids=None):
     """(rows, m, m) normals of the STREAM_A stream: 'channel' = i*m + j."""
-    return philox.normals(key, a_id, philox.STREAM_A, rows, m * m, dtype, row_offset).reshape(rows, m, m)
+    n = philox.normals(key, a_id, philox.STREAM_A, rows, m * m, dtype, row_offset, row_ids)
+    return n.reshape(n.shape[0], m, m)

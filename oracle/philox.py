@@ -36,8 +36,12 @@ def _box_muller(a, b):
     return r * np.cos(th), r * np.sin(th)
 
 
-def normals(key, node_id, stream, rows, m, dtype, row_offset=0):
+def normals(key, node_id, stream, rows, m, dtype, row_offset=0, row_ids=None):
     """(rows, m) normals of (key, node_id, stream).  Mirrors normal4() for every quad.
+
+    `row_ids` (optional 1-D integer array) selects arbitrary global rows instead of the contiguous block
+    row_offset .. row_offset + rows - 1: rows are independent streams, which is what lets the full-size
+    parity tests check a random sample of trajectories of a 65536-row solve.
 
     fp32: computed in float64 from the float32 uniforms, rounded to float32 at the end (the device
     uses float32 libm: agreement to a few ulp, tests use rtol 2e-6 / atol 2e-6).
@@ -46,17 +50,29 @@ def normals(key, node_id, stream, rows, m, dtype, row_offset=0):
     node_id = int(node_id)
     k0, k1 = key & 0xFFFFFFFF, (key >> 32) & 0xFFFFFFFF
     qpr = (m + 3) // 4
-    row = (np.arange(rows, dtype=np.uint64) + np.uint64(row_offset)).astype(np.uint32)[:, None]
+    if row_ids is not None:
+        row_ids = np.asarray(row_ids, dtype=np.uint64)
+        rows = int(row_ids.shape[0])
+        row = (row_ids + np.uint64(row_offset)).astype(np.uint32)[:, None]
+    else:
+        row = (np.arange(rows, dtype=np.uint64) + np.uint64(row_offset)).astype(np.uint32)[:, None]
     q = np.arange(qpr, dtype=np.uint32)[None, :]
     id_lo, id_hi = node_id & 0xFFFFFFFF, (node_id >> 32) & 0xFFFFFFFF
     out = np.empty((rows, qpr * 4), dtype=np.float64)
     if np.dtype(dtype) == np.float32:
         x = philox4x32_10(q | np.uint32(stream << 24), row, id_lo, id_hi, k0, k1)
-        u = [np.float32(np.float32(xi) * np.float32(2.3283064365386963e-10) + np.float32(1.1641532182693481e-10))
-             for xi in x]
-        # float32(x)*2^-32 is exact; + 2^-33 rounds once: identical to the device fmaf
-        n0, n1 = _box_muller(u[0].astype(np.float64), 2.0 * 0 + u[1].astype(np.float64))
-        n2, n3 = _box_muller(u[2].astype(np.float64), u[3].astype(np.float64))
+        # radius uniform a = fmaf(uint2float_rn(x), 2^-32, 2^-33): x is rounded to float32 by the conversion, the
+        # product with 2^-32 is exact, the sum rounds once more — the device's two instructions, bit for bit
+        def radius_uniform(xi):
+            a = np.float32(np.float32(xi) * np.float32(2.3283064365386963e-10) + np.float32(1.1641532182693481e-10))
+            return a.astype(np.float64)
+
+        # angle fraction b = (x >> 9) * 2^-23 in [0, 1) (the device builds it into a float's mantissa)
+        def angle_fraction(xi):
+            return (xi >> np.uint32(9)).astype(np.float64) * 2.0 ** -23
+
+        n0, n1 = _box_muller(radius_uniform(x[0]), angle_fraction(x[1]))
+        n2, n3 = _box_muller(radius_uniform(x[2]), angle_fraction(x[3]))
         out[:, 0::4], out[:, 1::4], out[:, 2::4], out[:, 3::4] = n0, n1, n2, n3
     else:
         for call in (0, 1):

@@ -98,6 +98,15 @@ class TimeAdditive(nn.Module):
         return val.unsqueeze(0).repeat(y.size(0), 1, 1)
 
 
+class TimeAdditiveExpand(TimeAdditive):
+    """Same SDE; g returns a stride-0 (batch-broadcast) view instead of a dense copy — what a user who knows that the
+    diffusion does not depend on y writes.  The tile kernels read the shared (d, m) block without densifying it."""
+
+    def g(self, t, y):
+        val = self.a * (self.b / torch.sqrt(1. + t)).unsqueeze(-1)
+        return val.unsqueeze(0).expand(y.size(0), -1, -1)
+
+
 class TanhGeneral(nn.Module):
     """General noise: g = tanh(y)[:, :, None] * S, f = mu * y."""
     noise_type = 'general'
@@ -154,7 +163,8 @@ class LatentLike(nn.Module):
         return self.f_net(ty), 0.1 * torch.sigmoid(self.w * y + self.b)
 
 
-PROBLEMS = {'gbm': GBMDiagonal, 'scalar': CosScalar, 'additive': TimeAdditive, 'general': TanhGeneral}
+PROBLEMS = {'gbm': GBMDiagonal, 'scalar': CosScalar, 'additive': TimeAdditive, 'general': TanhGeneral,
+            'additive_expand': TimeAdditiveExpand}
 
 
 def make(kind, d, m, sde_type, dtype=torch.float64, seed=0):

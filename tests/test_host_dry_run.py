@@ -70,6 +70,10 @@ def dry(monkeypatch):
 
     class _Graph:
         replays = 0
+        captures = 0
+
+        def __init__(self):
+            type(self).captures += 1
 
         def replay(self):
             type(self).replays += 1
@@ -191,10 +195,11 @@ def test_graph_plans_are_cached_and_follow_the_parameters(dry):
     from torchsde_b200._core import graph
     sde, y0, _ = _setup('gbm', 'ito', 'none')
 
-    def solve(method='milstein'):
+    def solve(method='milstein', static=True):
         bm = tsde.BrownianInterval(0.0, TS[-1], size=(4, 3), dtype=torch.float32, device='cpu')
         with torch.no_grad():
-            return tsde.sdeint(sde, y0, TS, bm=bm, method=method, dt=DT, options={'cuda_graph': True})
+            return tsde.sdeint(sde, y0, TS, bm=bm, method=method, dt=DT,
+                               options={'cuda_graph': True, 'static_output': static})
 
     ys = solve()
     assert ys.shape == (3, 4, 3)
@@ -203,6 +208,9 @@ def test_graph_plans_are_cached_and_follow_the_parameters(dry):
     launches = sum(dry.calls.values())
     assert solve() is ys                                   # same plan, same static output buffer
     assert len(plans) == 1 and dry.graph_cls.replays == 2
+    fresh = solve(static=False)                            # the default hands out a copy (results never alias)
+    assert fresh is not ys and fresh.data_ptr() != ys.data_ptr() and len(plans) == 1
+    dry.graph_cls.replays -= 1
     assert sum(dry.calls.values()) == launches             # a replay issues no new launches from Python
     solve('euler')
     assert len(plans) == 2
@@ -223,6 +231,65 @@ def test_graph_plans_are_cached_and_follow_the_parameters(dry):
                              options={'cuda_graph': True}, adjoint_options={'cuda_graph': True})
     ys.sum().backward()
     assert y02.grad is not None and all(p.grad is not None for p in sde2.parameters())
+
+
+def test_graph_plans_die_with_their_sde(dry):
+    """a plan pins a whole output series, so it must not outlive the SDE it was captured for, and the
+    wrappers `sdeint` creates per call (logqp=True, names=...) must not defeat the cache."""
+    import gc
+    import weakref
+    from torchsde_b200._core import graph
+    from torchsde_b200._core import adjoint
+
+    class Latent(torch.nn.Module):
+        noise_type, sde_type = 'diagonal', 'stratonovich'
+
+        def __init__(self):
+            super().__init__()
+            self.a = torch.nn.Parameter(torch.tensor([0.3, 0.2, 0.1]))
+
+        def f(self, t, y):
+            return -self.a * y
+
+        def h(self, t, y):
+            return -y
+
+        def g(self, t, y):
+            return 0.2 + 0.1 * torch.sigmoid(y)
+
+    def bm_for(rows, m):
+        return tsde.BrownianInterval(0.0, TS[-1], size=(rows, m), dtype=torch.float32, device='cpu')
+
+    refs = []
+    for _ in range(5):
+        sde, y0, _ = _setup('gbm', 'ito', 'none')
+        with torch.no_grad():
+            tsde.sdeint(sde, y0, TS, bm=bm_for(4, 3), method='milstein', dt=DT, options={'cuda_graph': True})
+        assert len(graph._PLANS[sde]) == 1
+        refs.append(weakref.ref(sde))
+        del sde
+    gc.collect()
+    assert all(r() is None for r in refs) and len(graph._PLANS) == 0
+    # logqp=True wraps the user's SDE in a fresh SDELogqp per call: one capture, then replays
+    sde = Latent()
+    y0 = torch.full((4, 3), 0.1)
+    captures = dry.graph_cls.captures
+    for _ in range(4):
+        with torch.no_grad():
+            ys, logqp = tsde.sdeint(sde, y0, TS, bm=bm_for(4, 4), method='midpoint', dt=DT, logqp=True,
+                                    options={'cuda_graph': True})
+    assert dry.graph_cls.captures == captures + 1 and len(graph._PLANS[sde]) == 1
+    for _ in range(3):
+        # (output times on the step grid: only then can the backward sweep bind the forward pass's cells)
+        out = tsde.sdeint_adjoint(sde, y0.clone().requires_grad_(), [0.0, 0.125, 0.25], bm=bm_for(4, 4),
+                                  method='reversible_heun', dt=DT,
+                                  logqp=True, options={'cuda_graph': True}, adjoint_options={'cuda_graph': True})
+        out[0].sum().backward()
+    assert len(adjoint._BWD_PLANS[sde]) == 1 and len(graph._PLANS[sde]) == 2
+    ref = weakref.ref(sde)
+    del sde, out, ys, logqp
+    gc.collect()
+    assert ref() is None and len(graph._PLANS) == 0 and len(adjoint._BWD_PLANS) == 0
 
 
 @pytest.mark.parametrize('kind,sde_type,method,levy', [('gbm', 'ito', 'euler', 'none'), ('gbm', 'ito', 'milstein', 'none'),

@@ -242,7 +242,7 @@ def test_bench_reference_arm_prints_one_contract_line():
     import json
     import subprocess
     import sys
-    env = dict(os.environ, TSDE_BENCH_B='2048')
+    env = dict(os.environ, TSDE_BENCH_B='2048', TSDE_BENCH_REF_BUDGET_S='2')
     out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1',
                           '--warmup', '0'], check=True, cwd=ROOT, env=env, capture_output=True, text=True).stdout
     lines = [ln for ln in out.splitlines() if ln.strip()]
@@ -253,7 +253,11 @@ def test_bench_reference_arm_prints_one_contract_line():
         assert key in d, key
     assert d['value'] > 0 and d['e2e']['value'] == d['value'] and d['e2e']['h2d_bytes_per_step'] == 0
     cb = d['cpu_baseline']
-    assert cb['kind'] == 'port' and cb['cores'] >= 1 and str(cb['cores']) in cb['threads_tried']
+    # the reference itself where build() has staged it under baseline/_ref (git-ignored, travels with the snapshot);
+    # the numpy port only where that directory is absent
+    staged = os.path.isdir(os.path.join(ROOT, 'baseline', '_ref', 'torchsde'))
+    assert cb['kind'] == ('reference' if staged else 'port') and cb['cores'] >= 1
+    assert d['config']['workload'] == 'cfg2' and d['config']['method'] == 'milstein' 
 
 
 def test_header_is_plain_c():
@@ -404,6 +408,16 @@ def test_cabi_rejects_malformed_calls_without_touching_the_device():
         need_u.source, need_u.w, need_u.want_u, need_u.u = _cabi.SRC_MEMORY, p, 1, None
         assert lib.tsde_step_srk_diag(ctypes.byref(ok), ctypes.byref(need_u), p, p, p, p, p, p, p, p, 0.1, 10.0, 0.3, 0.3,
                                       p) == EINVAL
+        # launch flags: unknown bits; a batch-broadcast g on a row-wise (diagonal / m == 1) launch or on the
+        # reversible-Heun pair, whose g operands are saved and differentiated
+        flagged = _cabi.Noise()
+        flagged.source, flagged.w, flagged.flags = _cabi.SRC_MEMORY, p, 2
+        assert lib.tsde_step_euler(ctypes.byref(general), ctypes.byref(flagged), p, p, p, 0.1, p) == EINVAL
+        flagged.flags = _cabi.FLAG_G_BROADCAST
+        assert lib.tsde_step_euler(ctypes.byref(ok), ctypes.byref(flagged), p, p, p, 0.1, p) == EINVAL
+        scalar = _cabi.make_launch(torch.float32, _cabi.NOISE_GENERAL, 4, 8, 1, 0)
+        assert lib.tsde_step_euler(ctypes.byref(scalar), ctypes.byref(flagged), p, p, p, 0.1, p) == EINVAL
+        assert lib.tsde_reversible_heun_z(ctypes.byref(general), ctypes.byref(flagged), p, p, p, p, 0.1, p) == EINVAL
         assert b'invalid argument' in lib.tsde_error_string(EINVAL)
         print('validated', len(_cabi.SIGNATURES))
     ''' % ROOT)

@@ -312,7 +312,7 @@ class BrownianInterval(brownian_base.BaseBrownian):
         return self._key_dev
 
     def _launch(self):
-        return _cabi.make_launch(self._dtype, _cabi.NOISE_DIAGONAL, self._rows, self._m, self._m)
+        return _cabi.make_launch(self._dtype, _cabi.NOISE_DIAGONAL, self._rows, self._m, self._m, device=self._device)
 
     def _new(self, *extra):
         return torch.empty((self._rows, self._m, *extra), dtype=self._dtype, device=self._device)
@@ -523,6 +523,10 @@ class BrownianInterval(brownian_base.BaseBrownian):
     # queries (:589-687)
     # ------------------------------------------------------------------------------------------
     def __call__(self, ta, tb=None, return_U=False, return_A=False):
+        with _cabi.device_guard(self._device):
+            return self._call(ta, tb, return_U, return_A)
+
+    def _call(self, ta, tb, return_U, return_A):
         if tb is None:
             warnings.warn(f"{self.__class__.__name__} is optimised for interval-based queries, not point evaluation.")
             ta, tb = self._root.start, ta

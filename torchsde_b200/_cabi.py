@@ -13,12 +13,14 @@ import os
 import torch
 
 _LIB_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib')
-LIB_PATH = os.path.join(_LIB_DIR, 'libtorchsde_b200.so')
+# TORCHSDE_B200_LIB: load another build of the same ABI instead (A/B measurements of kernel changes on one box)
+LIB_PATH = os.environ.get('TORCHSDE_B200_LIB') or os.path.join(_LIB_DIR, 'libtorchsde_b200.so')
 
 F32, F64 = 0, 1
 NOISE_DIAGONAL, NOISE_GENERAL = 0, 1
 SRC_MEMORY, SRC_COUNTER, SRC_UNIT = 0, 1, 2
 EINVAL = -22
+FLAG_G_BROADCAST = 1
 
 
 class LibraryNotBuilt(RuntimeError):
@@ -33,7 +35,7 @@ class Launch(ctypes.Structure):
 class Noise(ctypes.Structure):
     _fields_ = [('source', ctypes.c_int32), ('want_u', ctypes.c_int32), ('w', ctypes.c_void_p),
                 ('u', ctypes.c_void_p), ('key', ctypes.c_void_p), ('cell_id', ctypes.c_uint64),
-                ('row_offset', ctypes.c_int64), ('n_cells', ctypes.c_int32), ('reserved', ctypes.c_int32),
+                ('row_offset', ctypes.c_int64), ('n_cells', ctypes.c_int32), ('flags', ctypes.c_int32),
                 ('h', ctypes.c_double), ('cell_h', ctypes.c_void_p), ('h_total', ctypes.c_double)]
 
 
@@ -131,10 +133,21 @@ def require_cuda(*tensors):
                 "There is no CPU path; use the reference torchsde for CPU solves.")
 
 
-def make_launch(dtype, noise_type, rows, d, m, stream=None):
+def make_launch(dtype, noise_type, rows, d, m, stream=None, device=None):
     if stream is None:
-        stream = torch.cuda.current_stream().cuda_stream
+        stream = torch.cuda.current_stream(device).cuda_stream  # the stream of the tensors' device, not of the current one
     return Launch(dtype_code(dtype), noise_type, rows, d, m, stream)
+
+
+def device_guard(device):
+    """Make `device` the current CUDA device for the duration of a solve / query: the C ABI launches on the stream
+    it is handed and never calls cudaSetDevice, and a launch on a stream of another device than the current one
+    is an invalid resource handle.  No-op for non-CUDA devices (the host-side dry runs of the test-suite)."""
+    import contextlib
+    device = torch.device(device) if device is not None else None
+    if device is None or device.type != 'cuda':
+        return contextlib.nullcontext()
+    return torch.cuda.device(device)
 
 
 def ptr(t):

@@ -193,6 +193,16 @@ class _BackwardEngine(base_solver.BaseSDESolver):
 _BWD_PLANS = __import__('weakref').WeakKeyDictionary()
 
 
+def drop_plans(sde):
+    """Release every cached backward-sweep plan of `sde`."""
+    from . import graph as graph_mod
+    owner, _ = graph_mod.cache_owner(sde)
+    try:
+        _BWD_PLANS.pop(owner, None)
+    except TypeError:
+        pass
+
+
 def _backward_plan(engine, ys, ts, extras):
     """Capture (once) the backward sweep as a CUDA graph.  Called from the *forward* pass, i.e. from
     the user's thread: stream capture cannot be started from inside the autograd engine's worker
@@ -204,7 +214,7 @@ def _backward_plan(engine, ys, ts, extras):
     names = engine.param_names()
     if binding is None or names is None:
         return None
-    sde_obj = engine.sde._base_sde
+    sde_obj, _ = graph_mod.cache_owner(engine.sde)
     key = ('bwd',) + graph_mod._plan_key(engine, ys[0], ts, tuple(extras), binding) + (
         tuple(tuple(p.shape) for p in engine.params),)
     plans = graph_mod.plans_of(_BWD_PLANS, sde_obj)
@@ -214,7 +224,7 @@ def _backward_plan(engine, ys, ts, extras):
     if plan is not None:
         return plan
     plan = graph_mod._Plan()
-    plan.engine, plan.binding = engine, binding
+    plan.binding = binding  # (no reference to the engine / the SDE: plans must not keep their cache key alive)
     plan.ys = ys.detach().clone()
     plan.grad_ys = torch.zeros_like(plan.ys)
     plan.extras = tuple(_contig(e.detach()).clone() for e in extras)
@@ -234,6 +244,7 @@ def _backward_plan(engine, ys, ts, extras):
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
         plan.out = engine.sweep(plan.ys, plan.grad_ys, plan.extras, plan.grad_extras, alias_names=names)
+    plan.time_table = getattr(engine, '_time_table', None)
     plan.graph = g
     graph_mod._remember(plans, key, plan)
     return plan
@@ -301,11 +312,9 @@ class _SdeintAdjointMethod(torch.autograd.Function):
         ctx.adjoint_options = adjoint_options
         extras = tuple(x.detach() for x in extras_and_params[:n_extras])
         params = extras_and_params[n_extras:]
+        # (with cuda_graph the engine hands out copies of the plan's static buffers: what autograd saves here must
+        # not be overwritten by the next solve)
         ys, extras_out = sdeint_mod._integrate(solver, y0.detach(), ts, extras, options)
-        if options.get('cuda_graph', False):
-            # the graph's static output buffers are reused by the next solve; what autograd saves must not be
-            ys = ys.clone()
-            extras_out = tuple(e.clone() for e in extras_out)
         ctx.bwd_plan = None
         if adjoint_options.get('cuda_graph', False) and isinstance(bm, BrownianInterval) \
                 and adjoint_options_reversible(adjoint_options):
@@ -316,6 +325,11 @@ class _SdeintAdjointMethod(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_ys, *grad_extras):
+        with _cabi.device_guard(grad_ys.device):
+            return _SdeintAdjointMethod._backward(ctx, grad_ys, *grad_extras)
+
+    @staticmethod
+    def _backward(ctx, grad_ys, *grad_extras):
         ys, ts, *rest = ctx.saved_tensors
         extras = rest[:ctx.n_extras]
         params = rest[ctx.n_extras:]
@@ -400,9 +414,10 @@ def sdeint_adjoint(sde, y0, ts, bm=None, method=None, adjoint_method=None, dt=1e
         # backward() flow on to y0 and the parameters through these ordinary torch ops
         extra_solver_state = solver.init_extra_solver_state(ts[0], y0)
 
-    ys, *extra_solver_state = _SdeintAdjointMethod.apply(
-        sde, ts, dt, bm, solver, options, adjoint_options, len(extra_solver_state), y0, *extra_solver_state,
-        *adjoint_params)
+    with _cabi.device_guard(y0.device):
+        ys, *extra_solver_state = _SdeintAdjointMethod.apply(
+            sde, ts, dt, bm, solver, options, adjoint_options, len(extra_solver_state), y0, *extra_solver_state,
+            *adjoint_params)
     return sdeint_mod.parse_return(y0, ys, extra_solver_state, extra, logqp)
 
 

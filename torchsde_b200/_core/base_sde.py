@@ -88,6 +88,7 @@ class RenameMethodsSDE(BaseSDE):
         BaseSDE.__init__(self, noise_type=sde.noise_type, sde_type=sde.sde_type)
         self._base_sde = sde
         theirs = (drift, diffusion, prior_drift, diffusion_prod, drift_and_diffusion, drift_and_diffusion_prod)
+        self._plan_tag = ('rename',) + theirs  # part of the CUDA-graph plan key (graph.cache_owner)
         for ours, attr in zip(self._STANDARD, theirs):
             bound = getattr(sde, attr, None)
             if bound is not None:
@@ -130,6 +131,7 @@ class SDELogqp(BaseSDE):
     def __init__(self, sde):
         BaseSDE.__init__(self, noise_type=sde.noise_type, sde_type=sde.sde_type)
         self._base_sde = sde
+        self._plan_tag = 'logqp'
         missing = [name for name in ('f', 'g', 'h') if not hasattr(sde, name)]
         if missing:
             raise AttributeError("If using logqp then drift, diffusion and prior drift must all be specified.")

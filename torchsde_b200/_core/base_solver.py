@@ -33,6 +33,22 @@ def _contig(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
+def _is_row_broadcast(t):
+    """A (rows, d, m) diffusion that is one dense (d, m) block shared by all rows (`sigma.expand(B, d, m)`)."""
+    return t.dim() == 3 and t.size(0) > 1 and t.stride(0) == 0 and t.stride(2) == 1 and t.stride(1) == t.size(2) \
+        and t.size(2) > 1
+
+
+def _gop(g):
+    """Diffusion operand of a tableau launch: dense, or left as the batch-broadcast view it is (additive noise
+    written as `sigma.expand(B, d, m)`): the tile kernels read the shared (d, m) block (TSDE_FLAG_G_BROADCAST)
+    instead of a densified copy (at the cfg3 size a 16 MiB write + read per evaluation that the reference pays in
+    `repeat` / `bmm`, tests/problems.py:113-116, misc.py:62-63)."""
+    if g.is_contiguous() or _is_row_broadcast(g):
+        return g
+    return g.contiguous()
+
+
 class StepContext:
     """Everything one step needs besides tensors; built once per solve for every step."""
     __slots__ = ('k', 't0', 't1', 'ft0', 'ft1', 'dt', 'scalars', 'aux_t', 'solver')
@@ -199,6 +215,19 @@ class BaseSDESolver(metaclass=abc.ABCMeta):
         return torch.empty((self.rows, self.d), dtype=self.dtype, device=self.device)
 
     def _launch(self, name, L, nz, ins, scalars, outs):
+        flags = 0
+        g3 = [t for t in ins if t.dim() == 3 and not t.is_contiguous()]
+        if g3:
+            every = [t for t in ins if t.dim() == 3]
+            # the flag describes ALL (rows, d, m) operands of the launch, and only the general-noise tile kernels
+            # fed by the step's own noise descriptor understand it
+            if len(g3) == len(every) and L is self._L and self.m > 1 and nz is self._feed._nz_ref \
+                    and all(_is_row_broadcast(t) for t in g3):
+                flags = _cabi.FLAG_G_BROADCAST
+            else:
+                ins = [_contig(t) for t in ins]
+        if nz is self._feed._nz_ref:
+            self._feed._nz.flags = flags
         args = [L] if nz is None else [L, nz]
         args += [t.data_ptr() for t in ins]
         args += list(scalars)
@@ -380,7 +409,7 @@ class BaseSDESolver(metaclass=abc.ABCMeta):
         """compute_error of adaptive_stepping.py:42-69: RMS of (y11 - y12) / tol, reduced on the GPU."""
         eps = 1e-7
         if self._err_buf is None:
-            self._err_buf = torch.empty(1024, dtype=torch.float64, device=self.device)
+            self._err_buf = torch.zeros(1024, dtype=torch.float64, device=self.device)
         buf = self._err_buf
         _cabi.check(self._lib.tsde_adaptive_error_sumsq(self._LU, y_full.data_ptr(), y_half.data_ptr(),
                                                         float(self.rtol), float(self.atol), eps,
@@ -414,8 +443,11 @@ class BaseSDESolver(metaclass=abc.ABCMeta):
         """One full step vs two half steps per proposal; accept / reject on the host.  Step sizes are
         data dependent, so this branch is an eager loop (one device->host scalar per proposal, exactly
         the reference's sync count) and the Brownian motion is queried at arbitrary times through
-        ``bm(ta, tb)``; every step still runs the fused tableau kernels."""
-        y0 = _contig(y0.detach())
+        ``bm(ta, tb)``; every step still runs the fused tableau kernels.  When gradients flow through the solve
+        (`self._autograd`) every launch is an autograd node, as in the fixed-step loop; the error estimate
+        never carries gradient (the reference turns it into a Python float, base_solver.py:127-134)."""
+        track = self._autograd
+        y0 = _contig(y0 if track else y0.detach())
         self._prepare(y0)
         self._err_buf = None
         ts_cpu = ts.detach().to('cpu')
@@ -424,10 +456,13 @@ class BaseSDESolver(metaclass=abc.ABCMeta):
         prev_y = curr_y = y0
         curr_extra = tuple(extra0)
         T = ts.numel()
-        ys = torch.empty((T, self.rows, self.d), dtype=self.dtype, device=self.device)
-        ys[0].copy_(y0)
+        if track:
+            rows = [y0]
+        else:
+            ys = torch.empty((T, self.rows, self.d), dtype=self.dtype, device=self.device)
+            ys[0].copy_(y0)
         prev_error_ratio = None
-        with torch.no_grad():
+        with (torch.enable_grad() if track else torch.no_grad()):
             for i in range(1, T):
                 out_t = ts_cpu[i]
                 while curr_t < out_t:
@@ -436,7 +471,7 @@ class BaseSDESolver(metaclass=abc.ABCMeta):
                     midpoint_t = 0.5 * (curr_t + next_t)
                     midpoint_y, midpoint_extra = self.step(curr_t, midpoint_t, curr_y, curr_extra)
                     next_y, next_extra = self.step(midpoint_t, next_t, midpoint_y, midpoint_extra)
-                    error_estimate = self._error_estimate(next_y_full, next_y)
+                    error_estimate = self._error_estimate(_contig(next_y_full.detach()), _contig(next_y.detach()))
                     step_size, prev_error_ratio = self._update_step_size(
                         error_estimate=error_estimate, prev_step_size=step_size, prev_error_ratio=prev_error_ratio)
                     if step_size < self.dt_min:
@@ -448,12 +483,21 @@ class BaseSDESolver(metaclass=abc.ABCMeta):
                         curr_t, curr_y, curr_extra = next_t, next_y, next_extra
                 # interp.py:15-18
                 if bool(curr_t == out_t):
-                    ys[i].copy_(curr_y)
+                    out = curr_y
+                    w0 = w1 = None
                 else:
                     w0 = float((curr_t - out_t) / (curr_t - prev_t))
                     w1 = float((out_t - prev_t) / (curr_t - prev_t))
+                if track:
+                    rows.append(curr_y if w0 is None else
+                                self._k('tsde_linear_interp', self._LU, None, (prev_y, curr_y), (w0, w1), None))
+                elif w0 is None:
+                    ys[i].copy_(curr_y)
+                else:
                     _cabi.check(self._lib.tsde_linear_interp(self._LU, prev_y.data_ptr(), curr_y.data_ptr(), w0, w1,
                                                              ys[i].data_ptr()), "tsde_linear_interp")
+        if track:
+            return torch.stack(rows, dim=0), curr_extra
         return ys, curr_extra
 
     def _run(self, sched, ctxs, ys, extra):

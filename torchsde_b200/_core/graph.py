@@ -16,9 +16,20 @@ What makes this possible (and what it requires):
   tensor values (`.item()`, `float(t)`) inside f/g cannot be captured; such SDEs run with the
   default eager loop.
 
-Enable with ``options={'cuda_graph': True}``.  The returned `ys` is the plan's static output buffer:
-it is overwritten by the next solve that reuses the plan (standard CUDA-graph output semantics).
-Plans are cached per (sde object, method, shapes, dtype, grid, dt, Brownian structure).
+Enable with ``options={'cuda_graph': True}``.
+
+Ownership of the result.  A captured graph writes into buffers whose addresses are baked in, so the plan owns
+one output series `ys` (T x B x D).  By default `sdeint` returns a *copy* of it (a fresh tensor, the reference's
+semantics: results of successive solves never alias).  ``options={'cuda_graph': True, 'static_output': True}``
+returns the plan's buffer itself — no copy (for cfg2 the copy would move 2 x 16.8 GB, ~10 % of the solve) — and
+the caller must consume it before the next solve that reuses the plan overwrites it (the usual contract of
+CUDA-graph inference engines).  `bench.py` uses the static output and says so in its JSON line.
+
+Plan cache.  Plans are cached per *user SDE object* (the innermost object behind ForwardSDE / SDELogqp /
+RenameMethodsSDE wrappers, which are re-created on every call) and keyed by (wrapper kinds, method, parameter
+addresses, shapes, dtype, grid, dt, Brownian structure).  The cache is a WeakKeyDictionary and a plan keeps NO
+reference to the SDE (only tensors and the graph), so dropping the SDE frees its plans — each of which pins a
+full output series, hence also the small bound MAX_PLANS_PER_SDE.
 """
 import weakref
 
@@ -50,6 +61,15 @@ class _Plan:
     pass
 
 
+def drop_plans(sde):
+    """Release every cached forward plan of `sde` (each pins a full output series in device memory)."""
+    owner, _ = cache_owner(sde)
+    try:
+        _PLANS.pop(owner, None)
+    except TypeError:
+        pass
+
+
 def _tensor_signature(obj):
     """Addresses (and shapes / dtypes) of the tensors an SDE object owns.  A captured graph has them baked in, so a
     plan must not be replayed after `sde.to(...)`, `sde.double()` or `sde.mu = nn.Parameter(...)` replaced them;
@@ -61,23 +81,47 @@ def _tensor_signature(obj):
     return tuple((t.data_ptr(), tuple(t.shape), t.dtype) for t in tensors)
 
 
+def cache_owner(sde):
+    """(innermost user object, tags of the wrappers around it).  `sdeint` wraps the user's SDE afresh on every call
+    (ForwardSDE always; SDELogqp for logqp=True; RenameMethodsSDE for names=...), so the wrapper objects cannot
+    key a cache: plans hang on the user's own object, and the wrapper chain is part of the plan key."""
+    tags = []
+    obj = sde
+    while hasattr(obj, '_base_sde'):
+        tags.append(getattr(obj, '_plan_tag', type(obj).__name__))
+        obj = obj._base_sde
+    return obj, tuple(tags)
+
+
 def _plan_key(solver, y0, ts, extra0, binding):
     node = binding.node
-    return (type(solver).__name__, _tensor_signature(solver.sde._base_sde),
+    owner, tags = cache_owner(solver.sde)
+    return (type(solver).__name__, tags, _tensor_signature(owner),
             tuple(y0.shape), y0.dtype, str(y0.device),
             schedule_lib.ts_values(ts), str(ts.dtype),
             float(solver.dt) if not torch.is_tensor(solver.dt) else float(solver.dt),
-            tuple(sorted((k, repr(v)) for k, v in solver.options.items())),
+            tuple(sorted((k, repr(v)) for k, v in solver.options.items() if k != 'static_output')),
             solver.bm.levy_area_approximation, tuple(solver.bm.shape),
             node.cell_base, tuple(binding.first), tuple(binding.count), binding.reverse,
             binding.interval._row_offset,
             tuple((tuple(e.shape), e.dtype) for e in extra0))
 
 
-def integrate_captured(solver, y0, ts, extra0):
+def _hand_out(plan, solver, static_ok):
+    """The plan's output series, or a copy of it (see the module docstring)."""
+    if static_ok or solver.options.get('static_output', False):
+        return plan.ys, plan.extra_out
+    return plan.ys.clone(), tuple(e.clone() for e in plan.extra_out)
+
+
+LAST_PLAN = None  # the plan replayed most recently (bench.py reads its launch count)
+
+
+def integrate_captured(solver, y0, ts, extra0, static_ok=False):
+    global LAST_PLAN
     if int(solver.options.get('row_split', 1)) > 1 and not extra0:
-        return _integrate_captured_split(solver, y0, ts)
-    sde_obj = solver.sde._base_sde
+        return _integrate_captured_split(solver, y0, ts, static_ok)
+    sde_obj, _ = cache_owner(solver.sde)
     sched = schedule_lib.get_schedule(ts, solver.dt)
     y0 = base_solver._contig(y0.detach())
     solver._prepare(y0)
@@ -99,13 +143,14 @@ def integrate_captured(solver, y0, ts, extra0):
     for dst, src in zip(plan.extra_in, extra0):
         dst.copy_(src)
     plan.graph.replay()
-    return plan.ys, plan.extra_out
+    LAST_PLAN = plan
+    return _hand_out(plan, solver, static_ok)
 
 
 def _capture(solver, sched, binding, y0, ts, extra0):
+    from .. import _cabi
     plan = _Plan()
     dev = y0.device
-    plan.solver = solver  # keeps launch descriptors / time table alive
     plan.binding = binding  # keeps the grid node (and its device-side cell lengths) alive
     plan.y0 = torch.empty_like(y0)
     plan.key = torch.empty(1, dtype=torch.int64, device=dev)
@@ -121,8 +166,10 @@ def _capture(solver, sched, binding, y0, ts, extra0):
     feed._key_ptr = plan.key.data_ptr()  # kernels read the key from the static buffer
     solver._feed = feed
     ctxs = solver._contexts(sched, ts)
-    plan.ctxs = ctxs
-    plan.sched = sched
+    # the 0-d time tensors handed to the user's f/g are views of this table: it must outlive the graph.  Nothing
+    # else of the solver is kept (launch descriptors and scalars were copied into the kernel nodes at capture
+    # time), in particular no reference to the SDE: see the module docstring.
+    plan.time_table = getattr(solver, '_time_table', None)
 
     def body():
         plan.ys[0].copy_(plan.y0)
@@ -146,8 +193,10 @@ def _capture(solver, sched, binding, y0, ts, extra0):
     torch.cuda.synchronize(dev)
 
     graph = torch.cuda.CUDAGraph()
+    launches0 = _cabi.LAUNCHES
     with torch.no_grad(), torch.cuda.graph(graph):
         extra_out = body()
+    plan.abi_launches = _cabi.LAUNCHES - launches0  # kernels of THIS library captured in the graph (per replay)
     plan.graph = graph
     plan.extra_out = tuple(extra_out)
     return plan
@@ -160,10 +209,12 @@ def _capture(solver, sched, binding, y0, ts, extra0):
 # global index, so the result is bit-identical; what changes is that while one chain's kernel drains or the
 # next one ramps up, the other chain's kernel keeps the SMs busy (per-kernel fixed cost ~3 us on 16 MiB tensors).
 # Requires f/g to act row-wise on (t, y) — true for any SDE whose trajectories are independent.
-def _integrate_captured_split(solver, y0, ts):
+def _integrate_captured_split(solver, y0, ts, static_ok=False):
     import copy
+    global LAST_PLAN
+    from .. import _cabi
     k = int(solver.options['row_split'])
-    sde_obj = solver.sde._base_sde
+    sde_obj, _ = cache_owner(solver.sde)
     sched = schedule_lib.get_schedule(ts, solver.dt)
     y0 = base_solver._contig(y0.detach())
     solver._prepare(y0)
@@ -172,7 +223,7 @@ def _integrate_captured_split(solver, y0, ts):
         opts = dict(solver.options)
         opts.pop('row_split')
         solver.options = opts
-        return integrate_captured(solver, y0, ts, ())
+        return integrate_captured(solver, y0, ts, (), static_ok)
     key = ('split', k) + _plan_key(solver, y0, ts, (), binding)
     plans = plans_of(_PLANS, sde_obj)
     if plans is None:
@@ -202,7 +253,7 @@ def _integrate_captured_split(solver, y0, ts):
             sub._feed = feed
             sub_ctxs = sub._contexts(sched, ts)
             subs.append((sub, sub_ctxs, lo, hi))
-        plan.subs = subs
+        plan.time_table = [getattr(sub, '_time_table', None) for sub, _, _, _ in subs]  # (no reference to the sub-solvers / the SDE)
         streams = [torch.cuda.Stream(device=dev) for _ in range(k - 1)]
 
         def body(n_steps=None):
@@ -231,11 +282,15 @@ def _integrate_captured_split(solver, y0, ts):
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
+        launches0 = _cabi.LAUNCHES
         with torch.no_grad(), torch.cuda.graph(graph):
             body()
+        plan.abi_launches = _cabi.LAUNCHES - launches0
         plan.graph = graph
+        plan.extra_out = ()
         _remember(plans, key, plan)
     plan.y0.copy_(y0)
     plan.key.copy_(binding.interval.key_tensor())
     plan.graph.replay()
-    return plan.ys, ()
+    LAST_PLAN = plan
+    return _hand_out(plan, solver, static_ok)

@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import base_solver
-from .base_solver import _contig
+from .base_solver import _contig, _gop
 from ..settings import SDE_TYPES, NOISE_TYPES, LEVY_AREA_APPROXIMATIONS, METHODS, METHOD_OPTIONS
 
 
@@ -36,7 +36,7 @@ class _ProdMixin:
         mode = sde.f_and_g_prod_mode
         if mode == 'fused':
             f, g = sde.f_and_g(t, y)
-            return self._L, self._feed.get(c, self.want_u), _contig(f), _contig(g)
+            return self._L, self._feed.get(c, self.want_u), _contig(f), _gop(g)
         w, _ = self._feed.tensors(c)
         w = w.reshape(self.bm.shape)
         if mode == 'f_and_g_prod':
@@ -48,7 +48,7 @@ class _ProdMixin:
     def _g_prod(self, c, t, y):
         sde = self.sde
         if sde.g_prod_mode == 'fused':
-            return self._L, self._feed.get(c, self.want_u), _contig(sde.g(t, y))
+            return self._L, self._feed.get(c, self.want_u), _gop(sde.g(t, y))
         w, _ = self._feed.tensors(c)
         return self._LU, self._feed.unit(), _contig(sde.g_prod(t, y, w.reshape(self.bm.shape)))
 
@@ -322,11 +322,11 @@ class SRK(base_solver.BaseSDESolver):
             raise NotImplementedError("torchsde_b200: additive srk needs m > 1 (use noise_type='scalar' for m == 1).")
         t_1, t_34, t_00 = c.aux_t
         f0 = _contig(sde.f(t_00, y0))
-        ga = _contig(sde.g(t_1, y0))
+        ga = _gop(sde.g(t_1, y0))
         h0_1 = self._k('tsde_srk_additive_stage', self._L, self._feed.get(c, True), (y0, f0, ga), (c.dt, s['rdt']),
                        None)
         f1 = _contig(sde.f(t_34, h0_1))
-        gb = _contig(sde.g(t_00, y0))
+        gb = _gop(sde.g(t_00, y0))
         return self._k('tsde_step_srk_additive', self._L, self._feed.get(c, True), (y0, f0, f1, ga, gb),
                        (c.dt, s['rdt']), out)
 

@@ -57,9 +57,15 @@ def sdeint(sde, y0, ts, bm=None, method=None, dt=1e-3, adaptive=False, rtol=1e-5
     solver = solver_fn(sde=sde, bm=bm, dt=dt, adaptive=adaptive, rtol=rtol, atol=atol, dt_min=dt_min,
                        options=options)
     _cabi.require_cuda(y0)
-    if _needs_autograd(sde, y0, extra_solver_state) and not adaptive:
+    with _cabi.device_guard(y0.device):  # launches go to y0's device whatever the caller's current device is
+        return _solve(sde, solver, y0, ts, adaptive, options, logqp, extra, extra_solver_state)
+
+
+def _solve(sde, solver, y0, ts, adaptive, options, logqp, extra, extra_solver_state):
+    if _needs_autograd(sde, y0, extra_solver_state):
         # gradients must flow through the solve: every tableau launch becomes an autograd node
-        # (autograd_ops.py); eager loop, increments materialised (memory O(T), like the reference).
+        # (autograd_ops.py); eager loop, increments materialised (memory O(T), like the reference).  Adaptive
+        # solves take the same route: their accepted steps are ordinary (differentiable) steps.
         solver._autograd = True
         if extra_solver_state is None:
             extra_solver_state = solver.init_extra_solver_state(ts[0], y0)
@@ -73,17 +79,22 @@ def sdeint(sde, y0, ts, bm=None, method=None, dt=1e-3, adaptive=False, rtol=1e-5
 
 
 def _needs_autograd(sde, y0, extra_solver_state):
+    """Do gradients have to flow through this solve?  Yes if autograd is on and y0, a parameter of the SDE, the given
+    solver state, or — for SDEs that are not Modules, or that close over foreign tensors such as an encoder's context
+    (`contextualize`) — anything f / g returned while the contract was probed requires grad."""
     if not torch.is_grad_enabled():
         return False
     if y0.requires_grad or any(p.requires_grad for p in sde.parameters()):
         return True
+    if getattr(sde, 'probe_requires_grad', False):
+        return True
     return any(torch.is_tensor(e) and e.requires_grad for e in (extra_solver_state or ()))
 
 
-def _integrate(solver, y0, ts, extra_solver_state, options):
+def _integrate(solver, y0, ts, extra_solver_state, options, static_ok=False):
     if options.get('cuda_graph', False) and not solver.adaptive:
         from . import graph
-        return graph.integrate_captured(solver, y0, ts, extra_solver_state)
+        return graph.integrate_captured(solver, y0, ts, extra_solver_state, static_ok)
     return solver.integrate(y0, ts, extra_solver_state)
 
 
@@ -93,6 +104,11 @@ class _Sizes:
     def __init__(self, noise_type):
         self.noise_type = noise_type
         self.batch, self.state, self.noise = [], [], []
+        self.requires_grad = False  # did any probed output carry gradient (see _needs_autograd)?
+
+    def seen(self, *tensors):
+        self.requires_grad = self.requires_grad or any(torch.is_tensor(t) and t.requires_grad for t in tensors)
+        return tensors[0] if len(tensors) == 1 else tensors
 
     def two_d(self, name, shape):
         if len(shape) != 2:
@@ -187,26 +203,27 @@ def _probe(sde, t0, y0, sizes):
         sizes.need_noise_size()
         return torch.randn(sizes.batch[0], sizes.noise[0], dtype=y0.dtype, device=y0.device)
 
-    with torch.no_grad():
-        if hasattr(sde, 'f'):
-            have_f = True
-            sizes.two_d('Drift', tuple(sde.f(t0, y0).size()))
-        if hasattr(sde, 'g'):
-            have_g = True
-            sizes.diffusion('Diffusion', tuple(sde.g(t0, y0).size()))
-        if hasattr(sde, 'f_and_g'):
-            have_f = have_g = True
-            drift, diffusion = sde.f_and_g(t0, y0)
-            sizes.two_d('Drift', tuple(drift.size()))
-            sizes.diffusion('Diffusion', tuple(diffusion.size()))
-        if hasattr(sde, 'g_prod'):
-            have_g = True
-            sizes.two_d('Diffusion-vector product', tuple(sde.g_prod(t0, y0, test_vector()).size()))
-        if hasattr(sde, 'f_and_g_prod'):
-            have_f = have_g = True
-            drift, product = sde.f_and_g_prod(t0, y0, test_vector())
-            sizes.two_d('Drift', tuple(drift.size()))
-            sizes.two_d('Diffusion-vector product', tuple(product.size()))
+    # (the reference probes under no_grad; here the probe also records whether the SDE's outputs carry gradient,
+    # so it runs in the caller's grad mode — the outputs are dropped immediately either way)
+    if hasattr(sde, 'f'):
+        have_f = True
+        sizes.two_d('Drift', tuple(sizes.seen(sde.f(t0, y0)).size()))
+    if hasattr(sde, 'g'):
+        have_g = True
+        sizes.diffusion('Diffusion', tuple(sizes.seen(sde.g(t0, y0)).size()))
+    if hasattr(sde, 'f_and_g'):
+        have_f = have_g = True
+        drift, diffusion = sizes.seen(*sde.f_and_g(t0, y0))
+        sizes.two_d('Drift', tuple(drift.size()))
+        sizes.diffusion('Diffusion', tuple(diffusion.size()))
+    if hasattr(sde, 'g_prod'):
+        have_g = True
+        sizes.two_d('Diffusion-vector product', tuple(sizes.seen(sde.g_prod(t0, y0, test_vector())).size()))
+    if hasattr(sde, 'f_and_g_prod'):
+        have_f = have_g = True
+        drift, product = sizes.seen(*sde.f_and_g_prod(t0, y0, test_vector()))
+        sizes.two_d('Drift', tuple(drift.size()))
+        sizes.two_d('Diffusion-vector product', tuple(product.size()))
     return have_f, have_g
 
 
@@ -254,6 +271,7 @@ def check_contract(sde, y0, ts, bm, method, adaptive, options, names, logqp):
         raise ValueError(f"Scalar noise must have only one channel; the diffusion has {sizes.noise[0]} noise channels.")
 
     sde = base_sde.ForwardSDE(sde)
+    sde.probe_requires_grad = sizes.requires_grad
     if bm is None:
         span = schedule_lib.ts_values(ts)
         bm = BrownianInterval(t0=span[0], t1=span[-1], size=(sizes.batch[0], sizes.noise[0]), dtype=y0.dtype,

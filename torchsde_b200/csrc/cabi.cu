@@ -40,6 +40,14 @@ static inline bool bad(const tsde_launch* L) {
          (L->noise_type == TSDE_NOISE_DIAGONAL && L->m != L->d);
 }
 
+// Launch flags: unknown bits are a contract violation; a batch-broadcast g is only understood by the (rows,d,m)
+// tile kernels (the row-wise kernels address g per row).
+static inline bool bad_flags(const tsde_launch* L, const tsde_noise* nz) {
+  if (!nz) return false;
+  if (nz->flags & ~TSDE_FLAG_G_BROADCAST) return true;
+  return (nz->flags & TSDE_FLAG_G_BROADCAST) && rowwise(L);
+}
+
 extern "C" {
 
 int tsde_abi_version(void) { return TSDE_ABI_VERSION; }
@@ -53,54 +61,54 @@ const char* tsde_error_string(int code) {
 
 int tsde_step_euler(const tsde_launch* L, const tsde_noise* nz, const void* y0, const void* f,
                     const void* g, double dt, void* y1) {
-  if (bad(L)) return TSDE_EINVAL;
+  if (bad(L) || bad_flags(L, nz)) return TSDE_EINVAL;
   return rowwise(L) ? tsde_diag_step_euler(L, nz, y0, f, g, dt, y1)
                     : tsde_general_step_euler(L, nz, y0, f, g, dt, y1);
 }
 
 int tsde_milstein_vjp_seed(const tsde_launch* L, const tsde_noise* nz, const void* g, double dt,
                            int32_t ito, void* go) {
-  if (bad(L) || !rowwise(L)) return TSDE_EINVAL;  // milstein.py:25: additive/diagonal/scalar only
+  if (bad(L) || !rowwise(L) || bad_flags(L, nz)) return TSDE_EINVAL;  // milstein.py:25: additive/diagonal/scalar only
   return tsde_diag_milstein_vjp_seed(L, nz, g, dt, ito, go);
 }
 
 int tsde_step_milstein(const tsde_launch* L, const tsde_noise* nz, const void* y0, const void* f,
                        const void* g, const void* gdg, double dt, void* y1) {
-  if (bad(L) || !rowwise(L)) return TSDE_EINVAL;
+  if (bad(L) || !rowwise(L) || bad_flags(L, nz)) return TSDE_EINVAL;
   return tsde_diag_step_milstein(L, nz, y0, f, g, gdg, dt, y1);
 }
 
 int tsde_step_heun(const tsde_launch* L, const tsde_noise* nz, const void* y0, const void* f,
                    const void* fp, const void* g, const void* gp, double dt, void* y1) {
-  if (bad(L)) return TSDE_EINVAL;
+  if (bad(L) || bad_flags(L, nz)) return TSDE_EINVAL;
   return rowwise(L) ? tsde_diag_step_heun(L, nz, y0, f, fp, g, gp, dt, y1)
                     : tsde_general_step_heun(L, nz, y0, f, fp, g, gp, dt, y1);
 }
 
 int tsde_midpoint_predict(const tsde_launch* L, const tsde_noise* nz, const void* y0,
                           const void* f, const void* g, double half_dt, void* yp) {
-  if (bad(L)) return TSDE_EINVAL;
+  if (bad(L) || bad_flags(L, nz)) return TSDE_EINVAL;
   return rowwise(L) ? tsde_diag_midpoint_predict(L, nz, y0, f, g, half_dt, yp)
                     : tsde_general_midpoint_predict(L, nz, y0, f, g, half_dt, yp);
 }
 
 int tsde_euler_heun_predict(const tsde_launch* L, const tsde_noise* nz, const void* y0,
                             const void* g, void* yp) {
-  if (bad(L)) return TSDE_EINVAL;
+  if (bad(L) || bad_flags(L, nz)) return TSDE_EINVAL;
   return rowwise(L) ? tsde_diag_euler_heun_predict(L, nz, y0, g, yp)
                     : tsde_general_euler_heun_predict(L, nz, y0, g, yp);
 }
 
 int tsde_step_euler_heun(const tsde_launch* L, const tsde_noise* nz, const void* y0, const void* f,
                          const void* g, const void* gp, double dt, void* y1) {
-  if (bad(L)) return TSDE_EINVAL;
+  if (bad(L) || bad_flags(L, nz)) return TSDE_EINVAL;
   return rowwise(L) ? tsde_diag_step_euler_heun(L, nz, y0, f, g, gp, dt, y1)
                     : tsde_general_step_euler_heun(L, nz, y0, f, g, gp, dt, y1);
 }
 
 int tsde_reversible_heun_z(const tsde_launch* L, const tsde_noise* nz, const void* y0,
                            const void* z0, const void* f0, const void* g0, double dt, void* z1) {
-  if (bad(L)) return TSDE_EINVAL;
+  if (bad(L) || bad_flags(L, nz)) return TSDE_EINVAL;
   return rowwise(L) ? tsde_diag_reversible_heun_z(L, nz, y0, z0, f0, g0, dt, z1)
                     : tsde_general_reversible_heun_z(L, nz, y0, z0, f0, g0, dt, z1);
 }
@@ -108,7 +116,7 @@ int tsde_reversible_heun_z(const tsde_launch* L, const tsde_noise* nz, const voi
 int tsde_step_reversible_heun(const tsde_launch* L, const tsde_noise* nz, const void* y0,
                               const void* f0, const void* f1, const void* g0, const void* g1,
                               double half_dt, void* y1) {
-  if (bad(L)) return TSDE_EINVAL;
+  if (bad(L) || bad_flags(L, nz)) return TSDE_EINVAL;
   return rowwise(L) ? tsde_diag_step_reversible_heun(L, nz, y0, f0, f1, g0, g1, half_dt, y1)
                     : tsde_general_step_reversible_heun(L, nz, y0, f0, f1, g0, g1, half_dt, y1);
 }
@@ -118,7 +126,7 @@ int tsde_adjoint_reversible_heun_a(const tsde_launch* L, const tsde_noise* nz, c
                                    const void* adj_y0, const void* adj_f0, const void* adj_g0,
                                    double dt, double half_dt, void* z1, void* adj_f0_out,
                                    void* adj_g0_out) {
-  if (bad(L)) return TSDE_EINVAL;
+  if (bad(L) || bad_flags(L, nz)) return TSDE_EINVAL;
   return rowwise(L) ? tsde_diag_adjoint_reversible_heun_a(L, nz, y0, z0, f0, g0, adj_y0, adj_f0,
                                                           adj_g0, dt, half_dt, z1, adj_f0_out,
                                                           adj_g0_out)
@@ -132,7 +140,7 @@ int tsde_adjoint_reversible_heun_b(const tsde_launch* L, const tsde_noise* nz, c
                                    const void* adj_y0, const void* adj_z0, const void* vjp_z,
                                    double dt, double half_dt, void* y1, void* adj_y1, void* adj_z1,
                                    void* adj_f1, void* adj_g1) {
-  if (bad(L)) return TSDE_EINVAL;
+  if (bad(L) || bad_flags(L, nz)) return TSDE_EINVAL;
   return rowwise(L) ? tsde_diag_adjoint_reversible_heun_b(L, nz, y0, f0, f1, g0, g1, adj_y0,
                                                           adj_z0, vjp_z, dt, half_dt, y1, adj_y1,
                                                           adj_z1, adj_f1, adj_g1)

@@ -14,6 +14,7 @@
 #include <stdlib.h>
 
 #include <mutex>
+#include <type_traits>
 #include <unordered_map>
 
 #include "../../include/torchsde_b200.h"
@@ -320,78 +321,137 @@ ew_kernel(const EwP<Op::NIN, Op::NOUT> p, const NoiseP<T> nz, const Op op) {
 
 // ---- fast variant: the shapes the headline path uses -------------------------------------------
 // Preconditions checked on the host: 128-bit aligned tensors with d % 4 == 0 (vector path), noise not
-// broadcast, quads-per-row a power of two, fewer than 2^31 quads.  Everything is 32-bit index
-// arithmetic and there is no per-quad branching, which removes ~1/3 of the instructions of the generic
-// kernel (the Brownian kernels are issue-bound, so instructions are time).
-template <typename T, typename Op, int SRC>
-__global__ void __launch_bounds__(kThreads, 4)
-ew_fast_kernel(const EwP<Op::NIN, Op::NOUT> p, const NoiseP<T> nz, const Op op) {
-  constexpr int NIN = Op::NIN, NOUT = Op::NOUT;
-  Key key{0u, 0u};
-  if (Op::USES_NOISE && SRC == TSDE_SRC_COUNTER) key = load_key(nz.key);
-  const uint32_t nquads = (uint32_t)p.nquads;
-  const uint32_t q_begin = (uint32_t)(((uint64_t)nquads * blockIdx.x) / gridDim.x);
-  const uint32_t q_end = (uint32_t)(((uint64_t)nquads * (blockIdx.x + 1)) / gridDim.x);
-  const bool pow2 = p.qshift >= 0;
-  const uint32_t qshift = pow2 ? (uint32_t)p.qshift : 0u, qmask = (1u << qshift) - 1u;
-  const uint32_t qpr32 = (uint32_t)p.qpr;
-  const uint64_t qmagic = p.qmagic;
-  const uint32_t row_off = (uint32_t)nz.row_offset;
-  const bool stream_hint = p.vec > 1;  // host sets vec = 2 to enable evict-first loads
-  auto row_of = [&](uint32_t Q) -> uint32_t { return pow2 ? (Q >> qshift) : (uint32_t)(((uint64_t)Q * qmagic) >> 40); };
-  auto quad_of = [&](uint32_t Q, uint32_t row) -> uint32_t { return pow2 ? (Q & qmask) : (Q - row * qpr32); };
-  // Programmatic dependent launch: this grid may start while its predecessor in the stream/graph is
-  // still draining.  Everything that does not touch the predecessor's outputs — the Philox/Box-Muller
-  // work of the thread's first quad — runs before `griddepcontrol.wait`; all loads and stores come after.
-  T w0[4], u0[4];
-  const uint32_t Q0 = q_begin + threadIdx.x;
-  if (Op::USES_NOISE && SRC == TSDE_SRC_COUNTER && Q0 < q_end) {
-    const uint32_t r0 = row_of(Q0);
-    counter_noise<T, Op::WANT_U, false>(nz, key, r0 + row_off, quad_of(Q0, r0), w0, u0);
+// broadcast, quads-per-row a power of two (or divisible by multiply-shift), fewer than 2^31 quads.
+// Everything is 32-bit index arithmetic and there is no per-quad branching.
+//
+// Light ops (at most 3 tensors per quad: the Milstein vjp seed, the Brownian materialisation, the
+// predictor stages) are NOT HBM-bound per thread: the Philox + Box-Muller chain (~150 dependent-ish
+// instructions per quad) dominates and one 128-bit load per thread does not cover the HBM latency-bandwidth
+// product (ncu r02: issue active 57 %, 6 eligible warps per scheduler, every pipe below 40 %).  Those ops
+// process U = 2 quads per thread per iteration: both loads are issued first, the two independent Philox
+// chains interleave (2x ILP, 2x bytes in flight per thread).  Heavy ops (>= 4 tensors) keep U = 1: their
+// loads already cover the latency and the extra registers would cost occupancy.
+template <typename T, typename Op>
+struct quads_per_iter { static constexpr int value = (sizeof(T) == 4 && Op::NIN + Op::NOUT <= 3) ? 2 : 1; };
+
+template <typename T, typename Op>
+struct FastCtx {
+  const EwP<Op::NIN, Op::NOUT>& p;
+  const NoiseP<T>& nz;
+  const Op& op;
+  Key key;
+  uint32_t q_end, qshift, qmask, qpr32, row_off;
+  uint64_t qmagic;
+  bool pow2, stream_hint;
+  __device__ __forceinline__ uint32_t row_of(uint32_t Q) const {
+    return pow2 ? (Q >> qshift) : (uint32_t)(((uint64_t)Q * qmagic) >> 40);
   }
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  for (uint32_t Q = Q0; Q < q_end; Q += kThreads) {
-    const size_t base = (size_t)Q * 4;  // d == 4 * qpr: quads are laid out contiguously
-    T in[NIN > 0 ? NIN : 1][4];
+  __device__ __forceinline__ uint32_t quad_of(uint32_t Q, uint32_t row) const {
+    return pow2 ? (Q & qmask) : (Q - row * qpr32);
+  }
+  __device__ __forceinline__ void rng(uint32_t Q, T (&w)[4], T (&u)[4]) const {
+    const uint32_t r = row_of(Q);
+    counter_noise<T, Op::WANT_U, false>(nz, key, r + row_off, quad_of(Q, r), w, u);
+  }
+};
+
+// One iteration: U quads Q, Q + kThreads, ... (each warp access stays one contiguous 512-byte run).
+// FIRST: the counter noise was produced ahead of the dependency wait and is passed in (w0, u0).
+template <typename T, typename Op, int SRC, int U, bool FIRST>
+__device__ __forceinline__ void ew_fast_body(const FastCtx<T, Op>& c, uint32_t Q, const T (&w0)[U][4],
+                                             const T (&u0)[U][4]) {
+  constexpr int NIN = Op::NIN, NOUT = Op::NOUT;
+  bool ok[U];
+  T in[U][NIN > 0 ? NIN : 1][4];
 #pragma unroll
-    for (int i = 0; i < NIN; ++i) {
-      if (streams_inputs<Op>::value && stream_hint) ld4cs(reinterpret_cast<const T*>(p.in[i]) + base, in[i]);
-      else ld4(reinterpret_cast<const T*>(p.in[i]) + base, in[i]);
+  for (int k = 0; k < U; ++k) {
+    const uint32_t Qk = Q + (uint32_t)k * kThreads;
+    ok[k] = k == 0 || Qk < c.q_end;
+    const size_t base = (size_t)Qk * 4;  // d == 4 * qpr: quads are laid out contiguously
+    if (ok[k]) {
+#pragma unroll
+      for (int i = 0; i < NIN; ++i) {
+        if (streams_inputs<Op>::value && c.stream_hint)
+          ld4cs(reinterpret_cast<const T*>(c.p.in[i]) + base, in[k][i]);
+        else
+          ld4(reinterpret_cast<const T*>(c.p.in[i]) + base, in[k][i]);
+      }
     }
-    T w[4], u[4];
+  }
+  T w[U][4], u[U][4];
+#pragma unroll
+  for (int k = 0; k < U; ++k) {
+    const uint32_t Qk = Q + (uint32_t)k * kThreads;
+    const size_t base = (size_t)Qk * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { w[k][j] = T(0); u[k][j] = T(0); }
     if (Op::USES_NOISE) {
       if (SRC == TSDE_SRC_COUNTER) {
-        if (Q == Q0) {
+        if (FIRST) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) { w[j] = w0[j]; u[j] = Op::WANT_U ? u0[j] : T(0); }
+          for (int j = 0; j < 4; ++j) { w[k][j] = w0[k][j]; u[k][j] = Op::WANT_U ? u0[k][j] : T(0); }
         } else {
-          const uint32_t r = row_of(Q);
-          counter_noise<T, Op::WANT_U, false>(nz, key, r + row_off, quad_of(Q, r), w, u);
+          c.rng(Qk, w[k], u[k]);  // unconditional (a quad past the slice end costs nothing observable): the U
+                                  // Philox chains must stay in one basic block to interleave
         }
       } else if (SRC == TSDE_SRC_MEMORY) {
-        ld4(nz.w + base, w);
-        if (Op::WANT_U) ld4(nz.u + base, u);
+        if (ok[k]) {
+          ld4(c.nz.w + base, w[k]);
+          if (Op::WANT_U) ld4(c.nz.u + base, u[k]);
+        }
       } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { w[j] = T(1); u[j] = T(0); }
+        for (int j = 0; j < 4; ++j) { w[k][j] = T(1); u[k][j] = T(0); }
       }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { w[j] = T(0); u[j] = T(0); }
     }
+  }
+#pragma unroll
+  for (int k = 0; k < U; ++k) {
+    if (!ok[k]) continue;
+    const size_t base = (size_t)(Q + (uint32_t)k * kThreads) * 4;
     T out[NOUT][4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       T a[NIN > 0 ? NIN : 1], b[NOUT];
 #pragma unroll
-      for (int i = 0; i < NIN; ++i) a[i] = in[i][j];
-      op(a, w[j], u[j], b);
+      for (int i = 0; i < NIN; ++i) a[i] = in[k][i][j];
+      c.op(a, w[k][j], u[k][j], b);
 #pragma unroll
       for (int i = 0; i < NOUT; ++i) out[i][j] = b[i];
     }
 #pragma unroll
-    for (int i = 0; i < NOUT; ++i) st4(reinterpret_cast<T*>(p.out[i]) + base, out[i]);
+    for (int i = 0; i < NOUT; ++i) st4(reinterpret_cast<T*>(c.p.out[i]) + base, out[i]);
   }
+}
+
+template <typename T, typename Op, int SRC>
+__global__ void __launch_bounds__(kThreads, 4)
+ew_fast_kernel(const EwP<Op::NIN, Op::NOUT> p, const NoiseP<T> nz, const Op op) {
+  constexpr int U = quads_per_iter<T, Op>::value;
+  constexpr bool COUNTER = Op::USES_NOISE && SRC == TSDE_SRC_COUNTER;
+  const uint32_t nquads = (uint32_t)p.nquads;
+  const uint32_t q_begin = (uint32_t)(((uint64_t)nquads * blockIdx.x) / gridDim.x);
+  const uint32_t q_end = (uint32_t)(((uint64_t)nquads * (blockIdx.x + 1)) / gridDim.x);
+  const bool pow2 = p.qshift >= 0;
+  const uint32_t qshift = pow2 ? (uint32_t)p.qshift : 0u;
+  const FastCtx<T, Op> c{p, nz, op, COUNTER ? load_key(nz.key) : Key{0u, 0u}, q_end, qshift, (1u << qshift) - 1u,
+                         (uint32_t)p.qpr, (uint32_t)nz.row_offset, p.qmagic, pow2,
+                         p.vec > 1 /* host sets vec = 2 to enable evict-first loads */};
+  // Programmatic dependent launch: this grid may start while its predecessor in the stream/graph is
+  // still draining.  Everything that does not touch the predecessor's outputs — the Philox/Box-Muller
+  // work of the thread's first U quads — runs before `griddepcontrol.wait`; all loads and stores come after.
+  T w0[U][4], u0[U][4];
+  const uint32_t Q0 = q_begin + threadIdx.x;
+  if (COUNTER) {
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      c.rng(Q0 + (uint32_t)k * kThreads, w0[k], u0[k]);
+    }
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (Q0 >= q_end) return;
+  ew_fast_body<T, Op, SRC, U, true>(c, Q0, w0, u0);
+  for (uint32_t Q = Q0 + U * kThreads; Q < q_end; Q += U * kThreads) ew_fast_body<T, Op, SRC, U, false>(c, Q, w0, u0);
 }
 
 // ---- host-side launcher -----------------------------------------------------------------------

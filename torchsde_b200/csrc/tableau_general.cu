@@ -33,6 +33,9 @@ struct GenP {
   int32_t mq;    // m / 4 (vector path)
   int32_t rb;    // rows per block
   int32_t vec;   // vector path usable
+  int32_t gbcast;  // every g operand is ONE (d, m) block shared by all rows (row stride 0): additive noise whose
+                   // diffusion does not depend on y, returned as `sigma.expand(B, d, m)`.  Nothing of size
+                   // (rows, d, m) exists then; the block (d*m*s bytes, KiBs) is served from L1/L2.
 };
 
 // Op interface:
@@ -95,7 +98,7 @@ gen_kernel(const GenP<Op::NE, Op::NG, Op::NO> p, const NoiseP<T> nz, const Op op
       const int64_t rem = cc - (int64_t)r * per_row;
       const int64_t dd = rem / mq;
       const int mc = (int)(rem - dd * mq);
-      const int64_t goff = ((row0 + r) * d + dd) * m + 4 * mc;
+      const int64_t goff = ((p.gbcast ? 0 : (row0 + r) * d) + dd) * m + 4 * mc;
       T gv[NG][4];
 #pragma unroll
       for (int i = 0; i < NG; ++i) {
@@ -138,7 +141,7 @@ gen_kernel(const GenP<Op::NE, Op::NG, Op::NO> p, const NoiseP<T> nz, const Op op
     for (int64_t c = threadIdx.x; c < total; c += kThreads) {
       const int r = (int)(c / d);
       const int64_t dd = c - (int64_t)r * d;
-      const int64_t goff = ((row0 + r) * d + dd) * m;
+      const int64_t goff = ((p.gbcast ? 0 : (row0 + r) * d) + dd) * m;
       T part[NP];
 #pragma unroll
       for (int k = 0; k < NP; ++k) part[k] = T(0);
@@ -230,6 +233,9 @@ gen_cta_kernel(const GenP<Op::NE, Op::NG, Op::NO> p, const NoiseP<T> nz, const O
       valid[un] = c < total;
       rr[un] = r;
       slots[un] = slot;
+      // element offset of this chunk inside a g operand: contiguous tile, or — batch-broadcast g — the chunk's
+      // position inside the one shared (d, m) block
+      const int64_t goff = p.gbcast ? (int64_t)4 * (dd * mq + mc) : tile0 + 4 * (int64_t)c;
       if (valid[un] && mc == 0) {
 #pragma unroll
         for (int i = 0; i < NE; ++i) ev[un][i] = reinterpret_cast<const T*>(p.e[i])[slot0 + slot];
@@ -237,8 +243,8 @@ gen_cta_kernel(const GenP<Op::NE, Op::NG, Op::NO> p, const NoiseP<T> nz, const O
 #pragma unroll
       for (int i = 0; i < NG; ++i) {
         if (valid[un]) {
-          if (streams_inputs<Op>::value) ld4cs(reinterpret_cast<const T*>(p.g[i]) + tile0 + 4 * (int64_t)c, gv[un][i]);
-          else ld4(reinterpret_cast<const T*>(p.g[i]) + tile0 + 4 * (int64_t)c, gv[un][i]);
+          if (streams_inputs<Op>::value && !p.gbcast) ld4cs(reinterpret_cast<const T*>(p.g[i]) + goff, gv[un][i]);
+          else ld4(reinterpret_cast<const T*>(p.g[i]) + goff, gv[un][i]);
         } else {
 #pragma unroll
           for (int j = 0; j < 4; ++j) gv[un][i][j] = T(0);
@@ -793,11 +799,12 @@ static int launch_gen(const tsde_launch* L, const tsde_noise* nz,
   p.rows = L->rows; p.d = L->d; p.m = L->m;
   p.mq = (int32_t)mq;
   p.vec = vec ? 1 : 0;
+  p.gbcast = (nz->flags & TSDE_FLAG_G_BROADCAST) ? 1 : 0;
   if (L->rows == 0) return 0;
   if (L->rows + nz->row_offset > 0xFFFFFFFFll) return TSDE_EINVAL;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(L->stream);
   if (vec) {
-    if (int mode = gen_tma_mode(mq)) {
+    if (int mode = p.gbcast ? 0 : gen_tma_mode(mq)) {  // (a broadcast g has no tile stream to stage)
       int rc = launch_gen_tma<T, Op>(L, nz, p, np, op, mode, st);
       if (rc != kTmaNotEligible) return rc;
     }
@@ -1112,6 +1119,7 @@ int tsde_general_step_euler_heun(const tsde_launch* L, const tsde_noise* nz, con
 int tsde_general_reversible_heun_z(const tsde_launch* L, const tsde_noise* nz, const void* y0,
                                    const void* z0, const void* f0, const void* g0, double dt,
                                    void* z1) {
+  if (nz && nz->flags) return TSDE_EINVAL;  // (saved / differentiated g operands are always dense)
   return TSDE_DISPATCH_DTYPE(
       L,
       (launch_gen<float, GRevHeunZOp<float>>(L, nz, {y0, z0, f0}, {g0}, {z1},
@@ -1123,6 +1131,7 @@ int tsde_general_reversible_heun_z(const tsde_launch* L, const tsde_noise* nz, c
 int tsde_general_step_reversible_heun(const tsde_launch* L, const tsde_noise* nz, const void* y0,
                                       const void* f0, const void* f1, const void* g0,
                                       const void* g1, double half_dt, void* y1) {
+  if (nz && nz->flags) return TSDE_EINVAL;  // (saved / differentiated g operands are always dense)
   return TSDE_DISPATCH_DTYPE(
       L,
       (launch_gen<float, GRevHeunOp<float>>(L, nz, {y0, f0, f1}, {g0, g1}, {y1},
@@ -1161,6 +1170,7 @@ int tsde_general_adjoint_reversible_heun_a(const tsde_launch* L, const tsde_nois
                                            const void* g0, const void* adj_y0, const void* adj_f0,
                                            const void* adj_g0, double dt, double half_dt, void* z1,
                                            void* adj_f0_out, void* adj_g0_out) {
+  if (nz && nz->flags) return TSDE_EINVAL;  // (saved / differentiated g operands are always dense)
   // z1 = 2*y0 - z0 - f0*dt - g0.dW                                              :109
   int e = TSDE_DISPATCH_DTYPE(
       L,
@@ -1196,6 +1206,7 @@ int tsde_general_adjoint_reversible_heun_b(const tsde_launch* L, const tsde_nois
                                            const void* adj_z0, const void* vjp_z, double dt,
                                            double half_dt, void* y1, void* adj_y1, void* adj_z1,
                                            void* adj_f1, void* adj_g1) {
+  if (nz && nz->flags) return TSDE_EINVAL;  // (saved / differentiated g operands are always dense)
   // y1 = y0 - (f0+f1)*half_dt - (g0+g1).half_dW                                   :134-135
   int e = TSDE_DISPATCH_DTYPE(
       L,
