@@ -151,13 +151,22 @@ int tsde_brownian_bridge(const tsde_launch* L, const void* key, int64_t row_offs
 int tsde_brownian_merge(const tsde_launch* L, void* w0, void* h0, const void* w1,
                         const void* h1, double len0, double len1, double tot);
 
+/*
+ * GA = g A for the log-ODE correction (base_sde.py:170,191: `ga = torch.bmm(g, a)` inside
+ * dg_ga_jvp_column_sum_v1/_v2; used by methods/log_ode.py:39-56).  g is (rows,d,m), a is (rows,m,m) (the Levy
+ * area of the step), out_t is (m, rows, d): column l of g A as a contiguous (rows,d) slab, which is what the
+ * column-wise jvp's through the user's g consume (base_sde.py:173-184).  noise_type must be GENERAL.
+ */
+int tsde_bmm_ga(const tsde_launch* L, const void* g, const void* a, void* out_t);
+
 /* U = h (W/2 + H)   brownian_interval.py:102-103 */
 int tsde_brownian_h_to_u(const tsde_launch* L, const void* w, const void* hh, double h, void* out_u);
 
 /*
  * Davie / Foster Levy-area approximation of one interval
- * (brownian_interval.py:78-99): A = H (x) W - W (x) H + std * (N - N^T),
- * N ~ Philox normals with counter id `a_id`; foster != 0 selects Foster's std.
+ * (brownian_interval.py:78-99): A = H (x) W - W (x) H + std * (N - N^T); foster != 0 selects Foster's std.
+ * The antisymmetric noise N - N^T is drawn as one Philox normal per pair i < j of counter id `a_id`
+ * (N_ij = z_ij / sqrt 2 = -N_ji: the law of the reference's antisymmetrised iid matrix, half the draws).
  * out_a is (rows, m, m).
  */
 int tsde_brownian_levy_area(const tsde_launch* L, const void* key, int64_t row_offset,

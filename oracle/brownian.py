@@ -131,6 +131,16 @@ def bridge_chain(key, W, H, levels, row_offset=0):
 
 
 def levy_noise(key, a_id, rows, m, dtype, row_offset=0, row_ids=None):
-    """(rows, m, m) normals of the STREAM_A stream: 'channel' = i*m + j."""
-    n = philox.normals(key, a_id, philox.STREAM_A, rows, m * m, dtype, row_offset, row_ids)
-    return n.reshape(n.shape[0], m, m)
+    """(rows, m, m) matrix N whose antisymmetric part N - N^T is the Levy-area noise of `davie_foster` (the reference
+    draws m^2 iid normals and antisymmetrises, brownian_interval.py:88-90; only N - N^T enters, with independent
+    N(0, 2) entries per pair).  This repository's source draws one normal z per pair i < j — channel p of stream
+    STREAM_A, p counting the pairs in row-major upper-triangular order — and sets N_ij = z / sqrt(2), N_ji = -N_ij,
+    N_ii = 0 (csrc/brownian.cu)."""
+    npairs = m * (m - 1) // 2
+    z = philox.normals(key, a_id, philox.STREAM_A, rows, max(npairs, 1), dtype, row_offset, row_ids)
+    n = np.zeros((z.shape[0], m, m), dtype=dtype)
+    iu, ju = np.triu_indices(m, k=1)
+    half = (z[:, :npairs] * _s(0.70710678118654752440, dtype)).astype(dtype)
+    n[:, iu, ju] = half
+    n[:, ju, iu] = -half
+    return n

@@ -392,7 +392,128 @@ def adaptive_cases():
         print('wrote adaptive', name, len(rec.log) // 3, 'proposals')
 
 
+def _rec_save(rec, save):
+    save['ta'] = np.array([r[0] for r in rec.log])
+    save['tb'] = np.array([r[1] for r in rec.log])
+    save['W'] = np.stack([r[2] for r in rec.log])
+    if rec.log[0][3] is not None:
+        save['U'] = np.stack([r[3] for r in rec.log])
+    return save
+
+
+def variant_cases():
+    """User-callable subsets the reference accepts beyond plain f/g (VERDICT r01 missing #5): SRK calling the user's
+    g_prod (srk.py:87,102,109), additive SRK with a single Brownian channel, Euler-Heun with f_and_g_prod + g but no
+    g_prod (euler_heun.py:38)."""
+    cases = [('gbm_srk_f+g+g_prod', 'gbm', 'srk', 'ito', 6, 6, ('f', 'g', 'g_prod')),
+             ('scalar_srk_f+g+g_prod', 'scalar', 'srk', 'ito', 5, 1, ('f', 'g', 'g_prod')),
+             ('additive_srk_f+g_prod', 'additive', 'srk', 'ito', 4, 3, ('f', 'g_prod')),
+             ('additive3x1_srk_f+g', 'additive', 'srk', 'ito', 3, 1, ('f', 'g')),
+             ('additive3x1_euler_f+g', 'additive', 'euler', 'ito', 3, 1, ('f', 'g')),
+             ('additive3x1_heun_f+g', 'additive', 'heun', 'stratonovich', 3, 1, ('f', 'g')),
+             ('general_euler_heun_f_and_g_prod+g', 'general', 'euler_heun', 'stratonovich', 4, 3, ('f_and_g_prod', 'g')),
+             ('gbm_euler_heun_f_and_g_prod+g', 'gbm', 'euler_heun', 'stratonovich', 6, 6, ('f_and_g_prod', 'g')),
+             ('gbm_euler_heun_f_and_g_prod+f_and_g', 'gbm', 'euler_heun', 'stratonovich', 6, 6,
+              ('f_and_g_prod', 'f_and_g', 'g')),
+             ('gbm_milstein_f+g+g_prod', 'gbm', 'milstein', 'ito', 6, 6, ('f', 'g', 'g_prod')),
+             ('general_heun_f+g_prod', 'general', 'heun', 'stratonovich', 4, 3, ('f', 'g_prod'))]
+    for i, (name, kind, method, sde_type, d, m, offered) in enumerate(cases):
+        torch.manual_seed(777 + i)
+        tdt = torch.float64
+        sde = problems.WithProds(problems.make(kind, d, m, sde_type, dtype=tdt, seed=i), offered)
+        B = 4
+        y0 = 0.1 + 0.5 * torch.rand(B, d, dtype=tdt)
+        ts = torch.tensor([0.0, 0.1, 0.2, 0.3], dtype=tdt)
+        levy = 'space-time' if method == 'srk' else 'none'
+        bm_m = d if kind == 'gbm' else m
+        bm = torchsde.BrownianInterval(0.0, 0.3, size=(B, bm_m), dtype=tdt, entropy=900 + i, levy_area_approximation=levy)
+        rec = Recorder(bm)
+        with torch.no_grad():
+            ys = torchsde.sdeint(sde, y0, ts, bm=rec, method=method, dt=0.05)
+        save = _rec_save(rec, dict(y0=y0.numpy(), ts=ts.numpy(), dt=np.float64(0.05), ys=ys.numpy(), kind=kind,
+                                   method=method, sde_type=sde_type, d=d, m=m, dtype='f64', seed=i,
+                                   offered=','.join(offered)))
+        np.savez_compressed(os.path.join(HERE, f'variant_{name}.npz'), **save)
+        print('wrote variant', name)
+
+
+def logqp_cases():
+    """`logqp=True` (sdeint.py:141-145,284-295; base_sde.py:240-306): ys and the per-interval log-ratio, forward
+    solves and the gradient of a loss of both through sdeint_adjoint."""
+    cases = [('diag_ito_euler', 'diagonal', 'ito', 'euler', False), ('diag_ito_srk', 'diagonal', 'ito', 'srk', False),
+             ('diag_strat_midpoint', 'diagonal', 'stratonovich', 'midpoint', False),
+             ('general_strat_heun', 'general', 'stratonovich', 'heun', False),
+             ('general_ito_euler', 'general', 'ito', 'euler', False),
+             ('diag_strat_reversible_heun_adjoint', 'diagonal', 'stratonovich', 'reversible_heun', True),
+             ('general_strat_reversible_heun_adjoint', 'general', 'stratonovich', 'reversible_heun', True),
+             ('diag_ito_milstein_adjoint', 'diagonal', 'ito', 'milstein', True)]
+    for i, (name, noise, sde_type, method, adjoint) in enumerate(cases):
+        torch.manual_seed(4100 + i)
+        tdt = torch.float64
+        d, m = 4, (4 if noise == 'diagonal' else 3)
+        sde = problems.LatentPrior(d, m, noise, sde_type, seed=i, dtype=tdt)
+        B = 5
+        y0 = (0.1 + 0.5 * torch.rand(B, d, dtype=tdt)).requires_grad_(adjoint)
+        ts = torch.tensor([0.0, 0.1, 0.2, 0.3], dtype=tdt)
+        levy = 'space-time' if method == 'srk' else 'none'
+        # (diagonal noise: the augmented state has d + 1 channels, so does the Brownian motion)
+        bm_m = d + 1 if noise == 'diagonal' else m
+        bm = torchsde.BrownianInterval(0.0, 0.3, size=(B, bm_m), dtype=tdt, entropy=1300 + i, levy_area_approximation=levy)
+        rec = Recorder(bm)
+        save = dict(ts=ts.numpy(), dt=np.float64(0.05), noise=noise, sde_type=sde_type, method=method, d=d, m=m,
+                    seed=i, adjoint=adjoint)
+        if adjoint:
+            ys, logqp = torchsde.sdeint_adjoint(sde, y0, ts, bm=rec, method=method, dt=0.05, logqp=True)
+            wy = torch.linspace(0.5, 1.5, ys.numel(), dtype=tdt).reshape(ys.shape)
+            wl = torch.linspace(1.0, 2.0, logqp.numel(), dtype=tdt).reshape(logqp.shape)
+            ((ys * wy).sum() + (logqp * wl).sum()).backward()
+            save.update(wy=wy.numpy(), wl=wl.numpy(), grad_y0=y0.grad.numpy())
+            for n, p in sde.named_parameters():
+                save['grad.' + n] = (torch.zeros_like(p) if p.grad is None else p.grad).numpy()
+        else:
+            with torch.no_grad():
+                ys, logqp = torchsde.sdeint(sde, y0, ts, bm=rec, method=method, dt=0.05, logqp=True)
+        save.update(y0=y0.detach().numpy(), ys=ys.detach().numpy(), logqp=logqp.detach().numpy())
+        np.savez_compressed(os.path.join(HERE, f'logqp_{name}.npz'), **_rec_save(rec, save))
+        print('wrote logqp', name)
+
+
+def bpadaptive_cases():
+    """Backpropagation through an ADAPTIVE solve (the product used to detach silently)."""
+    import warnings
+    for i, (name, kind, method, sde_type, d, m) in enumerate([('gbm_ito_milstein', 'gbm', 'milstein', 'ito', 5, 5),
+                                                             ('general_strat_heun', 'general', 'heun', 'stratonovich', 4, 3),
+                                                             ('gbm_ito_srk', 'gbm', 'srk', 'ito', 4, 4)]):
+        torch.manual_seed(8100 + i)
+        tdt = torch.float64
+        sde = problems.make(kind, d, m, sde_type, dtype=tdt, seed=i + 1)
+        B = 3
+        y0 = (0.1 + 0.5 * torch.rand(B, d, dtype=tdt)).requires_grad_(True)
+        ts = torch.tensor([0.0, 0.4, 1.0], dtype=tdt)
+        levy = 'space-time' if method == 'srk' else 'none'
+        bm_m = d if kind == 'gbm' else m
+        bm = torchsde.BrownianInterval(0.0, 1.0, size=(B, bm_m), dtype=tdt, entropy=1500 + i, levy_area_approximation=levy)
+        rec = Recorder(bm)
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            ys = torchsde.sdeint(sde, y0, ts, bm=rec, method=method, dt=0.2, adaptive=True, rtol=1e-3, atol=1e-3,
+                                 dt_min=1e-4)
+        weights = torch.linspace(0.5, 1.5, ys.numel(), dtype=tdt).reshape(ys.shape)
+        (ys * weights).sum().backward()
+        save = dict(y0=y0.detach().numpy(), ts=ts.numpy(), dt=np.float64(0.2), ys=ys.detach().numpy(), rtol=1e-3,
+                    atol=1e-3, dt_min=1e-4, weights=weights.numpy(), grad_y0=y0.grad.numpy(), kind=kind, method=method,
+                    sde_type=sde_type, d=d, m=m, seed=i + 1)
+        for n, p in sde.named_parameters():
+            save['grad.' + n] = p.grad.numpy()
+        np.savez_compressed(os.path.join(HERE, f'bpadaptive_{name}.npz'), **_rec_save(rec, save))
+        print('wrote bpadaptive', name, len(rec.log) // 3, 'proposals')
+
+
 if __name__ == '__main__':
+    for only in ('variant', 'logqp', 'bpadaptive'):
+        if only in sys.argv:
+            {'variant': variant_cases, 'logqp': logqp_cases, 'bpadaptive': bpadaptive_cases}[only]()
+            sys.exit(0)
     if 'adaptive' in sys.argv:
         adaptive_cases()
         sys.exit(0)
@@ -413,3 +534,6 @@ if __name__ == '__main__':
     generic_adjoint_cases()
     log_ode_cases()
     backprop_cases()
+    variant_cases()
+    logqp_cases()
+    bpadaptive_cases()

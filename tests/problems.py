@@ -163,6 +163,68 @@ class LatentLike(nn.Module):
         return self.f_net(ty), 0.1 * torch.sigmoid(self.w * y + self.b)
 
 
+class WithProds(nn.Module):
+    """View of a problem that offers a chosen subset of the user-SDE protocol (reference sdeint.py:168-243):
+    `g_prod` / `f_and_g_prod` are built from the base problem's g with the reference's own product (g * v for
+    diagonal noise, batched matrix-vector product otherwise; base_sde.py:98-102, misc.py:62-63)."""
+
+    def __init__(self, base, offered):
+        super().__init__()
+        self.base = base
+        self.noise_type, self.sde_type = base.noise_type, base.sde_type
+        self.offered = tuple(offered)
+
+    def __getattr__(self, name):
+        if name in ('f', 'g', 'f_and_g', 'g_prod', 'f_and_g_prod'):
+            if name in self.__dict__.get('offered', ()):
+                return getattr(self, '_' + name)
+            raise AttributeError(name)
+        return super().__getattr__(name)
+
+    def _f(self, t, y):
+        return self.base.f(t, y)
+
+    def _g(self, t, y):
+        return self.base.g(t, y)
+
+    def _f_and_g(self, t, y):
+        return self.base.f(t, y), self.base.g(t, y)
+
+    def _g_prod(self, t, y, v):
+        g = self.base.g(t, y)
+        if self.noise_type == 'diagonal':
+            return g * v
+        return torch.bmm(g, v.unsqueeze(-1)).squeeze(-1)
+
+    def _f_and_g_prod(self, t, y, v):
+        return self.base.f(t, y), self._g_prod(t, y, v)
+
+
+class LatentPrior(nn.Module):
+    """Posterior / prior pair for `logqp=True` (reference base_sde.py:240-306, examples/latent_sde.py): drift f,
+    prior drift h, shared diffusion g; diagonal or general noise."""
+
+    def __init__(self, d, m, noise_type='diagonal', sde_type='ito', seed=0, dtype=torch.float64):
+        super().__init__()
+        self.noise_type, self.sde_type = noise_type, sde_type
+        g = _gen(seed)
+        self.a = nn.Parameter((0.5 * torch.rand(d, generator=g, dtype=torch.float64)).to(dtype))
+        self.c = nn.Parameter((0.3 * torch.rand(d, generator=g, dtype=torch.float64)).to(dtype))
+        self.s = nn.Parameter((0.2 + 0.3 * torch.rand(d, generator=g, dtype=torch.float64)).to(dtype))
+        self.S = nn.Parameter((0.2 + 0.5 * torch.rand(d, m, generator=g, dtype=torch.float64)).to(dtype))
+
+    def f(self, t, y):
+        return self.c - self.a * y + 0.1 * torch.sin(y)
+
+    def h(self, t, y):
+        return -0.5 * y
+
+    def g(self, t, y):
+        if self.noise_type == 'diagonal':
+            return self.s * (1.0 + 0.2 * torch.cos(y))
+        return (1.0 + 0.2 * torch.cos(y)).unsqueeze(-1) * self.S
+
+
 PROBLEMS = {'gbm': GBMDiagonal, 'scalar': CosScalar, 'additive': TimeAdditive, 'general': TanhGeneral,
             'additive_expand': TimeAdditiveExpand}
 

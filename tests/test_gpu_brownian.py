@@ -293,3 +293,52 @@ def test_interval_properties_and_cache_sizes():
     assert not torch.equal(e1, e2)
     r = tsde.BrownianInterval(0.0, 1.0, size=(8, 2), device=DEV)  # entropy from numpy's global RNG (:489-490)
     assert isinstance(r.entropy, int)
+
+
+@pytest.mark.parametrize('levy', ['davie', 'foster'])
+@pytest.mark.parametrize('m', [2, 3, 16, 24])
+def test_levy_area_noise_law(levy, m):
+    """The Levy-area noise is drawn as ONE normal per pair i < j (csrc/brownian.cu): (A_ij - (H_i W_j - W_i H_j)) /
+    std_ij must be N(0, 2) like the reference's antisymmetrised iid matrix N - N^T (brownian_interval.py:88-90),
+    independent across pairs, and A exactly antisymmetric with a zero diagonal."""
+    tsde = _tsde()
+    n = 32768
+    h = 0.5
+    bm = tsde.BrownianInterval(0.0, h, size=(n, m), dtype=torch.float64, device=DEV, entropy=17,
+                               levy_area_approximation=levy)
+    W, U, A = bm(0.0, h, return_U=True, return_A=True)
+    H = U / h - 0.5 * W
+    assert torch.equal(A, -A.transpose(1, 2)) and float(A.diagonal(dim1=1, dim2=2).abs().max()) == 0.0
+    base = H.unsqueeze(2) * W.unsqueeze(1) - W.unsqueeze(2) * H.unsqueeze(1)
+    if levy == 'foster':
+        H2 = H ** 2
+        std = torch.sqrt(0.1 * h * (0.1 * h + H2.unsqueeze(2) + H2.unsqueeze(1)))
+    else:
+        std = torch.full_like(base, math.sqrt(h * h / 12))
+    z = (A - base) / std
+    iu = torch.triu_indices(m, m, offset=1)
+    zu = z[:, iu[0], iu[1]]                                   # (n, npairs)
+    assert _ks(zu[:, 0], math.sqrt(2.0)) > 1e-5 and _ks(zu[:, -1], math.sqrt(2.0)) > 1e-5
+    assert _ks(zu.reshape(-1)[:262144], math.sqrt(2.0)) > 1e-5
+    if zu.shape[1] >= 2:
+        corr = torch.corrcoef(zu[:, :min(8, zu.shape[1])].T)
+        off = corr - torch.diag(torch.diag(corr))
+        assert float(off.abs().max()) < 0.03
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float64])
+@pytest.mark.parametrize('B,d,m', [(8192, 32, 16), (257, 5, 3), (64, 7, 8), (33, 4, 2), (100, 40, 32), (50, 6, 5), (3, 2, 20)])
+def test_bmm_ga_kernel_vs_torch(dtype, B, d, m):
+    """tsde_bmm_ga (log-ODE: ga = bmm(g, A), base_sde.py:170,191) against torch.bmm; the kernel writes the product
+    transposed, (m, rows, d)."""
+    import ctypes
+    from torchsde_b200 import _cabi
+    g = torch.randn(B, d, m, dtype=dtype, device=DEV)
+    a = torch.randn(B, m, m, dtype=dtype, device=DEV)
+    a = a - a.transpose(1, 2)
+    out = torch.empty(m, B, d, dtype=dtype, device=DEV)
+    L = _cabi.make_launch(dtype, _cabi.NOISE_GENERAL, B, d, m)
+    _cabi.check(_cabi.lib().tsde_bmm_ga(ctypes.byref(L), g.data_ptr(), a.data_ptr(), out.data_ptr()), 'tsde_bmm_ga')
+    ref = torch.bmm(g.double(), a.double()).permute(2, 0, 1)
+    tol = dict(rtol=1e-5, atol=1e-5) if dtype == torch.float32 else dict(rtol=1e-12, atol=1e-12)
+    torch.testing.assert_close(out.double(), ref, **tol)

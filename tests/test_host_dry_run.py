@@ -68,6 +68,12 @@ def dry(monkeypatch):
         def wait_stream(self, other):
             pass
 
+        def record_event(self):
+            return object()
+
+        def wait_event(self, event):
+            pass
+
     class _Graph:
         replays = 0
         captures = 0

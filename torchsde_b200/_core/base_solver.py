@@ -19,6 +19,7 @@ What changed underneath:
 """
 import abc
 import ctypes
+import os
 import warnings
 
 import torch
@@ -180,7 +181,7 @@ class BaseSDESolver(metaclass=abc.ABCMeta):
         self.dt_min = dt_min
         self.options = options
         self._prepared = False
-        self._side_stream = None
+        self._side_streams = []
         self._err_buf = None
         self._autograd = False
         self._cur_c = None
@@ -292,31 +293,62 @@ class BaseSDESolver(metaclass=abc.ABCMeta):
         self._lib = _cabi.lib()
         self._prepared = True
 
-    # -- drift on a parallel branch (options={'overlap_drift': True}; off by default) --------------
-    # f(t, y) and the diffusion chain g -> (vjp) are independent given y.  Issuing the drift on a
-    # side stream makes them parallel branches of the captured graph (fork/join).  Measured on cfg2 the
-    # gain is within noise (each of PyTorch's element-wise kernels already fills every SM slot), so the
-    # default keeps a single stream; evaluation *order* of f and g is not observable for pure callables.
-    def _drift_async(self, fn):
-        if self._autograd or not self.options.get('overlap_drift', False):
-            return fn(), None  # (under autograd keep one stream: AccumulateGrad nodes remember theirs)
-        main = torch.cuda.current_stream(self.device)
-        side = self._side_stream
-        if side is None:
-            side = self._side_stream = torch.cuda.Stream(device=self.device)
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
-            out = fn()
-        return out, side
+    # -- independent user callables as parallel branches -------------------------------------------------------
+    # Within a step f(t, y) and g(t, y) (and the stage evaluations of SRK that share their inputs) are independent
+    # given y.  Issued on different streams they become parallel branches of the captured graph (fork / join), so
+    # their kernels' launch latencies overlap instead of adding up.  That is what limits small-state workloads: at
+    # the cfg3 size (1 MiB states) a step is a chain of 4-30 tiny PyTorch kernels of the user's f / g at ~2.5 us of
+    # dependent-launch latency each, while the solver's own kernels take ~6 us.  Measured on a B200 (r02, ms per solve
+    # off -> on): cfg3 SRK additive 39.3 -> 32.5 (expand-g variant 28.5 -> 22.8), Heun general 20.8 -> 18.8, and even at
+    # the cfg2 size, where every kernel fills the machine and the branches mostly interleave: SRK 28.3 -> 27.4, Euler
+    # 5.75 -> 5.45, Milstein 47.67 -> 47.55.  On by default; `options={'overlap': False}` (or TSDE_OVERLAP=0) turns it off.
+    # Memory discipline: a branch's results are allocated on its side stream and consumed on the main stream after
+    # the join; they are freed (returned to the side stream's pool) only after that consumer has been enqueued, and
+    # the side stream reuses the block only after its next fork, i.e. after waiting for the main stream — so no
+    # `record_stream` is needed (under graph capture it would defer every free to the end of the capture).
+    # Evaluation order of f and g is not observable for pure callables; SDEs whose callables have side effects can
+    # set options={'overlap': False}.
+    def _overlap_now(self):
+        if self._autograd:
+            return False  # (AccumulateGrad nodes remember the stream they were created on: keep one stream)
+        opt = self.options.get('overlap', self.options.get('overlap_drift', None))
+        env = os.environ.get('TSDE_OVERLAP')
+        if env is not None and opt is None:
+            opt = env not in ('0', '')
+        return True if opt is None else bool(opt)
 
-    def _drift_join(self, out, side):
-        if side is not None:
-            main = torch.cuda.current_stream(self.device)
-            main.wait_stream(side)
-            for t in (out if isinstance(out, (tuple, list)) else (out,)):
-                if torch.is_tensor(t):
-                    t.record_stream(main)
-        return out
+    def _fork(self, *thunks, main=0):
+        """Results of independent thunks, called in the order given (the reference's call order).  thunks[main] runs
+        on the current stream (it may contain this library's launches, which go to that stream), the others on side
+        streams."""
+        if len(thunks) == 1 or not self._overlap_now():
+            return [t() for t in thunks]
+        cur = torch.cuda.current_stream(self.device)
+        while len(self._side_streams) < len(thunks) - 1:
+            self._side_streams.append(torch.cuda.Stream(device=self.device))
+        sides = iter(self._side_streams)
+        used = []
+        outs = []
+        fork_point = cur.record_event()  # every branch depends on what precedes the fork, not on its siblings
+        for i, thunk in enumerate(thunks):
+            if i == main:
+                outs.append(thunk())
+                continue
+            side = next(sides)
+            side.wait_event(fork_point)
+            with torch.cuda.stream(side):
+                outs.append(thunk())
+            used.append(side)
+        for side in used:
+            cur.wait_stream(side)
+        return outs
+
+    def _f_and_g(self, t, y):
+        """sde.f_and_g(t, y); when the user did not fuse them, f and g are evaluated as parallel branches."""
+        sde = self.sde
+        if getattr(sde, 'user_f_and_g', True) or getattr(sde, 'is_adjoint_sde', False):
+            return sde.f_and_g(t, y)
+        return self._fork(lambda: sde.f(t, y), lambda: sde.g(t, y))
 
     def _refresh_stream(self):
         stream = torch.cuda.current_stream(self.device).cuda_stream

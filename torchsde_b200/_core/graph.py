@@ -135,9 +135,23 @@ def integrate_captured(solver, y0, ts, extra0, static_ok=False):
     if plans is None:
         return solver.integrate(y0, ts, extra0)  # nothing to hang the plan on: ordinary eager loop
     plan = plans.get(key)
-    if plan is None:
-        plan = _capture(solver, sched, binding, y0, ts, extra0)
+    if plan is None and key not in plans:
+        try:
+            plan = _capture(solver, sched, binding, y0, ts, extra0)
+        except RuntimeError as e:
+            # f / g did something a stream capture cannot record (a host sync or a host<->device copy — e.g.
+            # `pinverse` in the general-noise KL rate of logqp=True, or `.item()` in user code).  Such SDEs run
+            # with the ordinary eager loop; remember it so that the capture is not attempted on every call.
+            if 'captur' not in str(e).lower():
+                raise
+            import warnings
+            warnings.warn("torchsde_b200: this SDE's f/g cannot be captured into a CUDA graph "
+                          f"({str(e).splitlines()[0][:160]}); falling back to the eager time loop.")
+            torch.cuda.synchronize(y0.device)
+            plan = None
         _remember(plans, key, plan)
+    if plan is None:
+        return solver.integrate(y0, ts, extra0)
     plan.y0.copy_(y0)
     plan.key.copy_(binding.interval.key_tensor())
     for dst, src in zip(plan.extra_in, extra0):
@@ -243,7 +257,7 @@ def _integrate_captured_split(solver, y0, ts, static_ok=False):
         subs = []
         for i in range(k):
             sub = copy.copy(solver)
-            sub._side_stream = None
+            sub._side_streams = []
             sub._err_buf = None
             lo, hi = bounds[i], bounds[i + 1]
             sub._prepare(plan.y0[lo:hi])

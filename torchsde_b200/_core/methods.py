@@ -13,6 +13,7 @@ import torch
 
 from . import base_solver
 from .base_solver import _contig, _gop
+from .. import _cabi
 from ..settings import SDE_TYPES, NOISE_TYPES, LEVY_AREA_APPROXIMATIONS, METHODS, METHOD_OPTIONS
 
 
@@ -35,7 +36,7 @@ class _ProdMixin:
         sde = self.sde
         mode = sde.f_and_g_prod_mode
         if mode == 'fused':
-            f, g = sde.f_and_g(t, y)
+            f, g = self._f_and_g(t, y)
             return self._L, self._feed.get(c, self.want_u), _contig(f), _gop(g)
         w, _ = self._feed.tensors(c)
         w = w.reshape(self.bm.shape)
@@ -102,7 +103,7 @@ class BaseMilstein(_ProdMixin, base_solver.BaseSDESolver):
         ito = 1 if self.ito else 0
         if self.options[METHOD_OPTIONS.grad_free]:
             # milstein.py:58-67
-            f, g = sde.f_and_g(c.t0, y0)
+            f, g = self._f_and_g(c.t0, y0)
             f, g = _contig(f), _contig(g)
             yp = self._k('tsde_milstein_gf_predict', self._LU, None, (y0, f, g), (c.dt, c.scalars['sqrt_dt'], ito),
                          None)
@@ -129,21 +130,23 @@ class BaseMilstein(_ProdMixin, base_solver.BaseSDESolver):
         # g_prod_and_gdg_prod_{diagonal,default}: vjp of g wrt y with grad_outputs g * (0.5 v)
         # base_sde.py:127-155 (always calls self.g, never g_prod)
         track = self._autograd
-        f, side = self._drift_async(lambda: _contig(sde.f(c.t0, y0)))  # reference order: f first (milstein.py:68)
-        with torch.enable_grad():
-            y = y0 if (track and y0.requires_grad) else y0.detach().requires_grad_(True)
-            g = sde.g(c.t0, y)
-            gd = _contig(g if track else g.detach())
-            go = self._k('tsde_milstein_vjp_seed', self._L, self._feed.get(c), (gd,), (c.dt, ito), None)
-            if g.requires_grad:
-                gdg, = torch.autograd.grad(g, y, grad_outputs=go.view_as(g), allow_unused=True,
-                                           retain_graph=track, create_graph=track)
-            else:
-                gdg = None
-        if gdg is None:
-            gdg = torch.zeros_like(y0)
-        self._drift_join(f, side)
-        return self._k('tsde_step_milstein', self._L, self._feed.get(c), (y0, f, gd, _contig(gdg)), (c.dt,), out), ()
+
+        def diffusion_chain():
+            with torch.enable_grad():
+                y = y0 if (track and y0.requires_grad) else y0.detach().requires_grad_(True)
+                g = sde.g(c.t0, y)
+                gd = _contig(g if track else g.detach())
+                go = self._k('tsde_milstein_vjp_seed', self._L, self._feed.get(c), (gd,), (c.dt, ito), None)
+                if g.requires_grad:
+                    gdg, = torch.autograd.grad(g, y, grad_outputs=go.view_as(g), allow_unused=True,
+                                               retain_graph=track, create_graph=track)
+                else:
+                    gdg = None
+            return gd, (torch.zeros_like(y0) if gdg is None else _contig(gdg))
+
+        # f and the chain g -> seed -> vjp are independent given y0 (reference order: f first, milstein.py:68)
+        f, (gd, gdg) = self._fork(lambda: _contig(sde.f(c.t0, y0)), diffusion_chain, main=1)
+        return self._k('tsde_step_milstein', self._L, self._feed.get(c), (y0, f, gd, gdg), (c.dt,), out), ()
 
 
 class MilsteinIto(BaseMilstein):
@@ -221,10 +224,17 @@ class EulerHeun(_ProdMixin, base_solver.BaseSDESolver):
             if sde.user_g_prod:
                 gp = sde.g_prod(c.t1, yp, w)
             elif not hasattr(sde._base_sde, 'g'):
+                # (deliberate superset of the reference, which raises "Method `g` has not been provided" here: an SDE
+                # that only offers the fused callable still solves — same value)
                 gp = sde.f_and_g_prod(c.t1, yp, w)[1]
             else:
-                raise RuntimeError("torchsde_b200: euler_heun with f_and_g_prod and g but no g_prod is "
-                                   "not supported; provide g_prod or only f/g.")
+                # f_and_g_prod and g, no g_prod: the reference's second product is g_prod_default =
+                # prod(g(t1, y'), dW) (euler_heun.py:38, base_sde.py:108-109).  The first product is already a tensor,
+                # so form the second one as a tensor too: 0 + g(t1, y').dW in the predictor kernel (adding to an
+                # exact zero does not round).
+                g1 = _contig(sde.g(c.t1, yp))
+                gp = self._k('tsde_euler_heun_predict', self._L, self._feed.get(c), (torch.zeros_like(y0), g1), (),
+                             None)
             L2, nz2, gp = self._LU, self._feed.unit(), _contig(gp)
         else:
             L2, nz2, gp = self._g_prod(c, c.t1, yp)
@@ -251,7 +261,7 @@ class ReversibleHeun(base_solver.BaseSDESolver):
     def _step(self, c, y0, extra0, out):
         f0, g0, z0 = (_contig(x) for x in extra0)
         z1 = self._k('tsde_reversible_heun_z', self._L, self._feed.get(c), (y0, z0, f0, g0), (c.dt,), None)
-        f1, g1 = self.sde.f_and_g(c.t1, z1)
+        f1, g1 = self._f_and_g(c.t1, z1)
         f1, g1 = _contig(f1), _contig(g1)
         y1 = self._k('tsde_step_reversible_heun', self._L, self._feed.get(c), (y0, f0, f1, g0, g1),
                      (c.scalars['half_dt'],), out)
@@ -289,11 +299,62 @@ class SRK(base_solver.BaseSDESolver):
 
     def _step(self, c, y0, extra0, out):
         if self.sde.user_g_prod:
-            raise NotImplementedError("torchsde_b200: srk with a user-supplied g_prod is not supported; "
-                                      "provide g (the fused kernel performs the product).")
+            y1 = self._additive_step_user_prod(c, y0) if self._additive else self._diagonal_step_user_prod(c, y0)
+            if out is not None and not self._autograd:
+                out.copy_(y1)
+                return out, ()
+            return y1, ()
         if self._additive:
             return self._additive_step(c, y0, out), ()
         return self._diagonal_or_scalar_step(c, y0, out), ()
+
+    # -- user-supplied g_prod (srk.py:87,102,109 call sde.g_prod) -----------------------------------------------
+    # The products are the user's own code, so the weights they are applied to have to exist as tensors: W and U are
+    # materialised and the tableau arithmetic around the user's calls is a handful of element-wise torch ops in the
+    # order of the fused kernels (csrc/tableau_diag.cu SrkDiagFinalOp, tableau_general.cu GSra*Op).  Not a fast
+    # path — SDEs that want the fused one provide g — but the reference accepts it, so it has to work.
+    def _weights(self, c):
+        w, u = self._feed.tensors(c, True)
+        shape = self.bm.shape
+        return w.reshape(shape), u.reshape(shape)
+
+    def _diagonal_step_user_prod(self, c, y0):
+        sde, s = self.sde, c.scalars
+        t_00, t_1, t_q, t_h = c.aux_t
+        dt, rdt, sqrt_dt, three_dt = c.dt, s['rdt'], s['sqrt_dt'], s['three_dt']
+        w, u = self._weights(c)
+        ikk = (w * w - dt) * 0.5                                  # srk.py:63
+        ikkk = ((w * w) * w - three_dt * w) * (1.0 / 6.0)         # srk.py:64
+        b1, b2, b3, b4 = (-1, 4 / 3, 2 / 3, 0), (1, -4 / 3, 1 / 3, 0), (2, -4 / 3, -2 / 3, 0), (-2, 5 / 3, -2 / 3, 1)
+        gw = [((b1[i] * w + (b2[i] * ikk) / sqrt_dt) + (b3[i] * u) * rdt) + (b4[i] * ikkk) * rdt for i in range(4)]
+        LU = self._LU
+        f0, g0 = _contig(sde.f(t_00, y0)), _contig(sde.g(t_00, y0))
+        h0_1, h1_1 = self._k('tsde_srk_diag_stage1', LU, None, (y0, f0, g0), (dt, sqrt_dt), None, n_out=2)
+        f1, g1 = _contig(sde.f(t_1, h0_1)), _contig(sde.g(t_q, h1_1))
+        # stage 2 needs U inside the kernel: hand it the materialised increments
+        nz = self._feed.from_tensors(*self._feed.tensors(c, True))
+        h0_2, h1_2 = self._k('tsde_srk_diag_stage2', self._L, nz, (y0, f0, g0, f1, g1), (dt, rdt, sqrt_dt), None,
+                             n_out=2)
+        f2, g2 = _contig(sde.f(t_h, h0_2)), _contig(sde.g(t_1, h1_2))
+        h1_3 = self._k('tsde_srk_diag_stage3', LU, None, (y0, g0, g1, f2, g2), (dt, sqrt_dt), None)
+        y1 = y0
+        for f, alpha, (t, h1), weight in zip((f0, f1, f2, None), (1 / 6, 1 / 6, 2 / 3, 0.0),
+                                             ((t_00, y0), (t_q, h1_1), (t_1, h1_2), (t_q, h1_3)), gw):
+            gp = sde.g_prod(t, h1, weight)
+            y1 = (y1 + (alpha * f) * dt) + gp if f is not None else y1 + gp   # alpha[3] = 0: an exact zero
+        return y1
+
+    def _additive_step_user_prod(self, c, y0):
+        sde, s = self.sde, c.scalars
+        t_1, t_34, t_00 = c.aux_t
+        dt, rdt = c.dt, s['rdt']
+        w, u = self._weights(c)
+        f0 = sde.f(t_00, y0)
+        h0_1 = (y0 + (0.75 * f0) * dt) + sde.g_prod(t_1, y0, (1.5 * u) * rdt)          # srk.py:99-104
+        f1 = sde.f(t_34, h0_1)
+        y1 = (y0 + ((1 / 3) * f0) * dt) + sde.g_prod(t_1, y0, 1 * w + (-1 * u) * rdt)   # srk.py:107-110, i = 0
+        y1 = (y1 + ((2 / 3) * f1) * dt) + sde.g_prod(t_00, y0, 0 * w + (1 * u) * rdt)   # i = 1
+        return y1
 
     def _diagonal_or_scalar_step(self, c, y0, out):
         """srk.py:57-88.  Distinct evaluations only: f0,g0 at (t0,y0); f1 at (t0+dt, H0_1);
@@ -301,15 +362,12 @@ class SRK(base_solver.BaseSDESolver):
         sde, s = self.sde, c.scalars
         t_00, t_1, t_q, t_h = c.aux_t  # t0 + 0*dt, t0 + dt, t0 + dt/4, t0 + dt/2
         LU, L = self._LU, self._L
-        f0 = _contig(sde.f(t_00, y0))
-        g0 = _contig(sde.g(t_00, y0))
+        f0, g0 = self._fork(lambda: _contig(sde.f(t_00, y0)), lambda: _contig(sde.g(t_00, y0)))
         h0_1, h1_1 = self._k('tsde_srk_diag_stage1', LU, None, (y0, f0, g0), (c.dt, s['sqrt_dt']), None, n_out=2)
-        f1 = _contig(sde.f(t_1, h0_1))
-        g1 = _contig(sde.g(t_q, h1_1))
+        f1, g1 = self._fork(lambda: _contig(sde.f(t_1, h0_1)), lambda: _contig(sde.g(t_q, h1_1)))
         h0_2, h1_2 = self._k('tsde_srk_diag_stage2', L, self._feed.get(c, True), (y0, f0, g0, f1, g1),
                              (c.dt, s['rdt'], s['sqrt_dt']), None, n_out=2)
-        f2 = _contig(sde.f(t_h, h0_2))
-        g2 = _contig(sde.g(t_1, h1_2))
+        f2, g2 = self._fork(lambda: _contig(sde.f(t_h, h0_2)), lambda: _contig(sde.g(t_1, h1_2)))
         h1_3 = self._k('tsde_srk_diag_stage3', LU, None, (y0, g0, g1, f2, g2), (c.dt, s['sqrt_dt']), None)
         g3 = _contig(sde.g(t_q, h1_3))
         return self._k('tsde_step_srk_diag', L, self._feed.get(c, True), (y0, f0, f1, f2, g0, g1, g2, g3),
@@ -318,15 +376,13 @@ class SRK(base_solver.BaseSDESolver):
     def _additive_step(self, c, y0, out):
         """srk.py:90-111: f0 = f(t0, y0); gA = g(t0+dt, y0); f1 = f(t0+3/4dt, H0_1); gB = g(t0, y0)."""
         sde, s = self.sde, c.scalars
-        if self.m == 1:
-            raise NotImplementedError("torchsde_b200: additive srk needs m > 1 (use noise_type='scalar' for m == 1).")
         t_1, t_34, t_00 = c.aux_t
-        f0 = _contig(sde.f(t_00, y0))
-        ga = _gop(sde.g(t_1, y0))
+        # f0, g(t1, y0) and g(t0, y0) share their inputs: three parallel branches
+        f0, ga, gb = self._fork(lambda: _contig(sde.f(t_00, y0)), lambda: _gop(sde.g(t_1, y0)),
+                                lambda: _gop(sde.g(t_00, y0)))
         h0_1 = self._k('tsde_srk_additive_stage', self._L, self._feed.get(c, True), (y0, f0, ga), (c.dt, s['rdt']),
                        None)
         f1 = _contig(sde.f(t_34, h0_1))
-        gb = _gop(sde.g(t_00, y0))
         return self._k('tsde_step_srk_additive', self._L, self._feed.get(c, True), (y0, f0, f1, ga, gb),
                        (c.dt, s['rdt']), out)
 
@@ -362,10 +418,18 @@ class LogODEMidpoint(_ProdMixin, base_solver.BaseSDESolver):
         with torch.enable_grad():
             y = y if (track and y.requires_grad) else y.detach().requires_grad_(True)
             g = self.sde.g(t, y)
-            ga = torch.bmm(g, a)
+            if track:
+                # gradients flow through the tangents as well (create_graph): keep the product in autograd
+                ga_cols = torch.bmm(g, a).unbind(-1)
+            else:
+                # fused fp32 kernel, result transposed to (m, rows, d): one contiguous tangent per column
+                ga_t = torch.empty((g.size(-1), g.size(0), g.size(1)), dtype=g.dtype, device=g.device)
+                _cabi.check(self._lib.tsde_bmm_ga(self._L, _contig(g.detach()).data_ptr(), _contig(a).data_ptr(),
+                                                  ga_t.data_ptr()), "tsde_bmm_ga")
+                ga_cols = ga_t.unbind(0)
             total = None
             for col in range(g.size(-1)):
-                term = _jvp(g[..., col], y, ga[..., col], create_graph=track)
+                term = _jvp(g[..., col], y, ga_cols[col], create_graph=track)
                 total = term if total is None else total + term
         return total if track else total.detach()
 

@@ -281,6 +281,90 @@ struct HToUOp {
 };
 
 // ---- Davie / Foster Levy area                                   brownian_interval.py:78-99
+// A = H (x) W - W (x) H + std * (N - N^T).  The reference draws a full (m x m) matrix N of iid normals and
+// antisymmetrises it (:88-90); only the antisymmetric part enters, and N_ij - N_ji ~ N(0, 2) independently for
+// every pair i < j.  The counter-based source therefore draws ONE normal z per pair (m(m-1)/2 instead of m^2:
+// for m = 16, 30 Philox calls per row instead of 64) and defines
+//     N_ij = z_ij / sqrt(2),  N_ji = -N_ij  (i < j),  N_ii = 0        =>   N - N^T has the reference's law;
+// pair p = (i, j), i < j, in row-major upper-triangular order, is channel p of stream STREAM_A of node `a_id`
+// (oracle/brownian.py levy_noise restates this).  The kernel is a write-bound stream of (m x m) tiles:
+// one warp per row — lanes draw the row's pair normals (one Philox quad = 4 pairs per lane), form the upper
+// triangle, mirror it (A is antisymmetric, exactly: this translation unit is compiled without FMA contraction)
+// into a warp-private shared tile, and the warp stores the tile with fully coalesced 128-bit writes.
+template <typename T>
+__device__ __forceinline__ T levy_pair_value(T wi, T wj, T hi, T hj, T z, T tenth_h, T davie_std, int foster) {
+  const T a = hi * wj - wi * hj;
+  const T n = z * T(0.70710678118654752440);   // N_ij
+  const T noise = n - (-n);                      // N_ij - N_ji
+  const T std_ = foster ? sqrt(tenth_h * ((tenth_h + hi * hi) + hj * hj)) : davie_std;
+  return a + std_ * noise;
+}
+
+constexpr int kLevyWarps = 8;
+
+template <typename T>
+__global__ void __launch_bounds__(kLevyWarps * 32)
+levy_tile_kernel(const void* keyp, int64_t row_offset, uint64_t a_id, int64_t rows, int m, int npairs, int warps,
+                 const T* __restrict__ w, const T* __restrict__ hh, T tenth_h, T davie_std, int foster,
+                 T* __restrict__ out, int vec) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int mm = m * m;
+  const int tile = (mm + 2 * m + 3) & ~3;                  // floats per warp: A tile | W | H (16-byte multiple)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char* pairs_i = smem_raw;                       // [npairs] row index of pair p
+  unsigned char* pairs_j = pairs_i + npairs;               // [npairs] column index
+  T* tiles = reinterpret_cast<T*>(smem_raw + (((size_t)2 * npairs + 15) & ~(size_t)15));
+  T* sA = tiles + (size_t)warp * tile;
+  T* sW = sA + mm;
+  T* sH = sW + m;
+  // pair table (shared by the CTA) and the tile's zero diagonal (written once: rows never touch it)
+  for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    int p = i * m - (i * (i + 1)) / 2;                     // first pair of row i
+    for (int j = i + 1; j < m; ++j, ++p) { pairs_i[p] = (unsigned char)i; pairs_j[p] = (unsigned char)j; }
+  }
+  if (warp < warps) for (int i = lane; i < m; i += 32) sA[i * m + i] = T(0);
+  __syncthreads();
+  if (warp >= warps) return;
+  const Key key = load_key(keyp);
+  const int nq = (npairs + 3) >> 2;
+  const int64_t row_stride = (int64_t)gridDim.x * warps;
+  for (int64_t row = (int64_t)blockIdx.x * warps + warp; row < rows; row += row_stride) {
+    for (int c = lane; c < m; c += 32) {
+      sW[c] = w[row * m + c];
+      sH[c] = hh[row * m + c];
+    }
+    __syncwarp();
+    const uint32_t grow = (uint32_t)(row + row_offset);
+    for (int q = lane; q < nq; q += 32) {
+      T z[4];
+      normal4(key, a_id, STREAM_A, grow, (uint32_t)q, z);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int p = 4 * q + k;
+        if (p < npairs) {
+          const int i = pairs_i[p], j = pairs_j[p];
+          const T v = levy_pair_value(sW[i], sW[j], sH[i], sH[j], z[k], tenth_h, davie_std, foster);
+          sA[i * m + j] = v;
+          sA[j * m + i] = -v;
+        }
+      }
+    }
+    __syncwarp();
+    T* dst = out + row * (int64_t)mm;
+    if (vec) {
+      for (int e = 4 * lane; e < mm; e += 128) {
+        T v4[4];
+        ld4(sA + e, v4);
+        st4(dst + e, v4);
+      }
+    } else {
+      for (int e = lane; e < mm; e += 32) dst[e] = sA[e];
+    }
+    __syncwarp();
+  }
+}
+
+// Fallback for Brownian motions with more than 64 channels (the tile would not fit): one thread per element.
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 levy_area_kernel(const void* keyp, int64_t row_offset, uint64_t a_id, int64_t rows, int64_t m,
@@ -292,80 +376,14 @@ levy_area_kernel(const void* keyp, int64_t row_offset, uint64_t a_id, int64_t ro
     const int64_t row = e / mm;
     const int64_t ij = e - row * mm;
     const int64_t i = ij / m, j = ij - i * m;
-    const uint32_t grow = (uint32_t)(row + row_offset);
-    const int64_t ji = j * m + i;
+    if (i == j) { out[e] = T(0); continue; }
+    const int64_t lo = i < j ? i : j, hi_ = i < j ? j : i;
+    const int64_t p = lo * m - (lo * (lo + 1)) / 2 + (hi_ - lo - 1);
     T n4[4];
-    normal4(key, a_id, STREAM_A, grow, (uint32_t)(ij >> 2), n4);
-    const T nij = n4[ij & 3];
-    normal4(key, a_id, STREAM_A, grow, (uint32_t)(ji >> 2), n4);
-    const T nji = n4[ji & 3];
-    const T wi = w[row * m + i], wj = w[row * m + j];
-    const T hi = hh[row * m + i], hj = hh[row * m + j];
-    T a = hi * wj - wi * hj;
-    const T noise = nij - nji;
-    T std_;
-    if (foster) {
-      std_ = sqrt(tenth_h * ((tenth_h + hi * hi) + hj * hj));
-    } else {
-      std_ = davie_std;
-    }
-    out[e] = a + std_ * noise;
-  }
-}
-
-// Block-cooperative variant: the (m x m) normal matrix of each row is generated once (m*m/4 Philox
-// calls per row, the minimum) into shared memory with row stride m+1 (conflict-free transposed reads),
-// then A_ij = H_i W_j - W_i H_j + std_ij (N_ij - N_ji) is written with fully coalesced stores.
-template <typename T>
-__global__ void __launch_bounds__(kThreads)
-levy_area_smem_kernel(const void* keyp, int64_t row_offset, uint64_t a_id, int64_t rows, int m, int rb,
-                      const T* __restrict__ w, const T* __restrict__ hh, T tenth_h, T davie_std, int foster,
-                      T* __restrict__ out, int mshift /* log2(m) or -1 */) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int mm = m * m, ld = m + 1, per_row = m * ld;
-  T* sn = reinterpret_cast<T*>(smem_raw);          // [rb][m][m+1]
-  T* sw = sn + (size_t)rb * per_row;                // [rb][m]
-  T* sh = sw + (size_t)rb * m;                      // [rb][m]
-  const Key key = load_key(keyp);
-  const int64_t row0 = (int64_t)blockIdx.x * rb;
-  const int nrows = (int)((rows - row0) < rb ? (rows - row0) : rb);
-  const int qpm = (mm + 3) / 4;
-  for (int i = threadIdx.x; i < nrows * qpm; i += kThreads) {
-    const int r = i / qpm, q = i - r * qpm;
-    T n4[4];
-    normal4(key, a_id, STREAM_A, (uint32_t)(row0 + r + row_offset), (uint32_t)q, n4);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int ij = 4 * q + k;
-      const int i2 = mshift >= 0 ? (ij >> mshift) : (ij / m);
-      const int j2 = mshift >= 0 ? (ij & (m - 1)) : (ij - i2 * m);
-      if (ij < mm) sn[r * per_row + i2 * ld + j2] = n4[k];
-    }
-  }
-  for (int i = threadIdx.x; i < nrows * m; i += kThreads) {
-    sw[i] = w[row0 * m + i];
-    sh[i] = hh[row0 * m + i];
-  }
-  __syncthreads();
-  const int total = nrows * mm;
-  for (int e = threadIdx.x; e < total; e += kThreads) {
-    int r, ij, i, j;
-    if (mshift >= 0) {
-      r = e >> (2 * mshift);
-      ij = e & (mm - 1);
-      i = ij >> mshift;
-      j = ij & (m - 1);
-    } else {
-      r = e / mm;
-      ij = e - r * mm;
-      i = ij / m;
-      j = ij - i * m;
-    }
-    const T wi = sw[r * m + i], wj = sw[r * m + j], hi = sh[r * m + i], hj = sh[r * m + j];
-    const T noise = sn[r * per_row + i * ld + j] - sn[r * per_row + j * ld + i];
-    const T a = hi * wj - wi * hj;
-    const T std_ = foster ? sqrt(tenth_h * ((tenth_h + hi * hi) + hj * hj)) : davie_std;
-    out[row0 * mm + e] = a + std_ * noise;
+    normal4(key, a_id, STREAM_A, (uint32_t)(row + row_offset), (uint32_t)(p >> 2), n4);
+    const T v = levy_pair_value(w[row * m + lo], w[row * m + hi_], hh[row * m + lo], hh[row * m + hi_], n4[p & 3],
+                                tenth_h, davie_std, foster);
+    out[e] = i < j ? v : -v;
   }
 }
 
@@ -399,18 +417,21 @@ static int levy_impl(const tsde_launch* L, const void* key, int64_t row_offset, 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(L->stream);
   const double r12 = 1.0 / 12.0;
   const int64_t m = L->m;
-  const size_t per_row = (size_t)(m * (m + 1) + 2 * m) * sizeof(T);
-  if (per_row <= 40 * 1024) {
-    int64_t rb = (int64_t)(40 * 1024 / per_row);
-    if (rb > 32) rb = 32;
-    while (rb > 1 && (L->rows + rb - 1) / rb < 2 * (int64_t)sm_count()) rb >>= 1;
-    const int64_t blocks = (L->rows + rb - 1) / rb;
-    int mshift = -1;
-    if ((m & (m - 1)) == 0) { mshift = 0; while ((1ll << mshift) < m) ++mshift; }
-    if (blocks <= 0x7fffffffll) {
-      levy_area_smem_kernel<T><<<(unsigned)blocks, kThreads, rb * per_row, st>>>(
-          key, row_offset, a_id, L->rows, (int)m, (int)rb, (const T*)w, (const T*)hh, (T)(0.1 * h),
-          (T)sqrt(r12 * h * h), foster, (T*)out_a, mshift);
+  if (m >= 2 && m <= 64) {
+    const int npairs = (int)(m * (m - 1) / 2);
+    const size_t tile = (size_t)((m * m + 2 * m + 3) & ~3ll) * sizeof(T);
+    const size_t table = ((size_t)2 * npairs + 15) & ~(size_t)15;
+    int warps = (int)((46 * 1024 - table) / tile);
+    if (warps > kLevyWarps) warps = kLevyWarps;
+    if (warps >= 1) {
+      const size_t smem = table + (size_t)warps * tile;
+      int64_t blocks = (L->rows + warps - 1) / warps;
+      const int64_t cap = (int64_t)sm_count() * 8;   // persistent: a few CTAs per SM, rows strided over them
+      if (blocks > cap) blocks = cap;
+      const int vec = ((m * m) % 4 == 0 && aligned16(out_a)) ? 1 : 0;
+      levy_tile_kernel<T><<<(unsigned)blocks, kLevyWarps * 32, smem, st>>>(
+          key, row_offset, a_id, L->rows, (int)m, npairs, warps, (const T*)w, (const T*)hh, (T)(0.1 * h),
+          (T)sqrt(r12 * h * h), foster, (T*)out_a, vec);
       return (int)cudaGetLastError();
     }
   }
