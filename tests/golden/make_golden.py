@@ -509,10 +509,53 @@ def bpadaptive_cases():
         print('wrote bpadaptive', name, len(rec.log) // 3, 'proposals')
 
 
+def gradgrad_cases():
+    """Double backward through sdeint_adjoint (adjoint.py:97-113, adjoint_sde.py create_graph paths; the reference's
+    tests/utils.py:97-98 gradgradcheck): gradient of a functional of the first-order adjoint gradients."""
+    # (the reversible pair is absent on purpose: the reference itself cannot double-backward it — the re-entered
+    # Function finds no saved extra state and AdjointReversibleHeun.init_extra_solver_state raises,
+    # reversible_heun.py:93-96)
+    # (... and so are Ito SDEs — additive ones included, whose adjoint SDE has general noise: the re-entered
+    # adjoint's Ito correction needs `f_and_g` of the first AdjointSDE, which the reference does not define,
+    # adjoint_sde.py:267-271)
+    cases = [('general_strat_midpoint', 'general', 'stratonovich', 'midpoint', None, 3, 2),
+             ('gbm_strat_midpoint', 'gbm', 'stratonovich', 'midpoint', None, 4, 4),
+             ('scalar_strat_heun', 'scalar', 'stratonovich', 'heun', 'heun', 3, 1)]
+    for i, (name, kind, sde_type, method, adjoint_method, d, m) in enumerate(cases):
+        torch.manual_seed(5200 + i)
+        tdt = torch.float64
+        sde = problems.make(kind, d, m, sde_type, dtype=tdt, seed=i + 4)
+        params = list(sde.parameters())
+        B = 3
+        y0 = (0.1 + 0.5 * torch.rand(B, d, dtype=tdt)).requires_grad_(True)
+        ts = torch.tensor([0.0, 0.1, 0.2], dtype=tdt)
+        bm_m = d if kind == 'gbm' else m
+        bm = torchsde.BrownianInterval(0.0, 0.2, size=(B, bm_m), dtype=tdt, entropy=1700 + i)
+        rec = Recorder(bm)
+        ys = torchsde.sdeint_adjoint(sde, y0, ts, bm=rec, method=method, adjoint_method=adjoint_method, dt=0.05)
+        w1 = torch.linspace(0.5, 1.5, ys.numel(), dtype=tdt).reshape(ys.shape)
+        loss = (ys * w1).sum()
+        first = torch.autograd.grad(loss, [y0] + params, create_graph=True, allow_unused=True)
+        first = [torch.zeros_like(x) if g is None else g for g, x in zip(first, [y0] + params)]
+        w2 = [torch.linspace(1.0, 2.0, g.numel(), dtype=tdt).reshape(g.shape) for g in first]
+        second = sum((g * w).sum() for g, w in zip(first, w2))
+        gg = torch.autograd.grad(second, [y0] + params, allow_unused=True)
+        gg = [torch.zeros_like(x) if g is None else g for g, x in zip(gg, [y0] + params)]
+        save = dict(y0=y0.detach().numpy(), ts=ts.numpy(), dt=np.float64(0.05), ys=ys.detach().numpy(), kind=kind,
+                    sde_type=sde_type, method=method, adjoint_method=adjoint_method or '', d=d, m=m, seed=i + 4,
+                    w1=w1.numpy(), first_y0=first[0].detach().numpy(), second_y0=gg[0].numpy())
+        for (n, _), g1, g2, w in zip(sde.named_parameters(), first[1:], gg[1:], w2[1:]):
+            save['first.' + n] = g1.detach().numpy()
+            save['second.' + n] = g2.numpy()
+        np.savez_compressed(os.path.join(HERE, f'gradgrad_{name}.npz'), **_rec_save(rec, save))
+        print('wrote gradgrad', name, len(rec.log), 'queries')
+
+
 if __name__ == '__main__':
-    for only in ('variant', 'logqp', 'bpadaptive'):
+    for only in ('variant', 'logqp', 'bpadaptive', 'gradgrad'):
         if only in sys.argv:
-            {'variant': variant_cases, 'logqp': logqp_cases, 'bpadaptive': bpadaptive_cases}[only]()
+            {'variant': variant_cases, 'logqp': logqp_cases, 'bpadaptive': bpadaptive_cases,
+             'gradgrad': gradgrad_cases}[only]()
             sys.exit(0)
     if 'adaptive' in sys.argv:
         adaptive_cases()
@@ -537,3 +580,4 @@ if __name__ == '__main__':
     variant_cases()
     logqp_cases()
     bpadaptive_cases()
+    gradgrad_cases()

@@ -182,3 +182,67 @@ def test_backprop_counter_path_matches_adjoint():
         grads.append([y0.grad.clone()] + [p.grad.clone() for p in sde.parameters()])
     for a, b in zip(*grads):
         torch.testing.assert_close(a, b, rtol=1e-9, atol=1e-11)
+
+
+@pytest.mark.parametrize('path', helpers.golden_files('gradgrad_'), ids=helpers.case_id)
+def test_double_backward_golden_replay(path):
+    """Double backward through sdeint_adjoint (reference adjoint.py:97-113: the backward pass re-enters the Function,
+    so the second-order gradient is the continuous adjoint of the adjoint solve): first- and second-order gradients
+    against the reference's on identical increments."""
+    tsde = _tsde()
+    case = helpers.load(path)
+    dev = torch.device('cuda')
+    kind, d, m = str(case['kind']), int(case['d']), int(case['m'])
+    sde = problems.make(kind, d, m, str(case['sde_type']), dtype=torch.float64, seed=int(case['seed'])).to(dev)
+    params = list(sde.parameters())
+    y0 = torch.from_numpy(case['y0']).to(dev).requires_grad_(True)
+    ts = torch.from_numpy(case['ts']).to(dev)
+    bm = helpers.replay_torch(case, dev)
+    ys = tsde.sdeint_adjoint(sde, y0, ts, bm=bm, method=str(case['method']),
+                             adjoint_method=str(case['adjoint_method']) or None, dt=float(case['dt']))
+    np.testing.assert_allclose(ys.detach().cpu().numpy(), case['ys'], rtol=1e-11, atol=1e-12)
+    loss = (ys * torch.from_numpy(case['w1']).to(dev)).sum()
+    first = torch.autograd.grad(loss, [y0] + params, create_graph=True, allow_unused=True)
+    first = [torch.zeros_like(x) if g is None else g for g, x in zip(first, [y0] + params)]
+    np.testing.assert_allclose(first[0].detach().cpu().numpy(), case['first_y0'], rtol=1e-8, atol=1e-10)
+    for (n, _), g in zip(sde.named_parameters(), first[1:]):
+        np.testing.assert_allclose(g.detach().cpu().numpy(), case['first.' + n], rtol=1e-8, atol=1e-10, err_msg=n)
+    w2 = [torch.linspace(1.0, 2.0, g.numel(), dtype=torch.float64, device=dev).reshape(g.shape) for g in first]
+    second = sum((g * w).sum() for g, w in zip(first, w2))
+    gg = torch.autograd.grad(second, [y0] + params, allow_unused=True)
+    gg = [torch.zeros_like(x) if g is None else g for g, x in zip(gg, [y0] + params)]
+    np.testing.assert_allclose(gg[0].cpu().numpy(), case['second_y0'], rtol=1e-7, atol=1e-9)
+    for (n, _), g in zip(sde.named_parameters(), gg[1:]):
+        np.testing.assert_allclose(g.cpu().numpy(), case['second.' + n], rtol=1e-7, atol=1e-9, err_msg=n)
+
+
+@pytest.mark.parametrize('kind,d,m', [('gbm', 4, 4), ('general', 3, 2)])
+def test_double_backward_reversible_pair(kind, d, m):
+    """The reversible pair cannot be double-backwarded in the reference at all (its re-entered Function finds no saved
+    solver state: reversible_heun.py:93-96 raises).  Here the backward sweep falls back to differentiable torch
+    operations when create_graph=True; since reversible Heun's adjoint is the exact gradient of the discrete solve,
+    its second-order gradients must equal those obtained by double-backpropagating through plain `sdeint`."""
+    tsde = _tsde()
+    dev = torch.device('cuda')
+    sde = problems.make(kind, d, m, 'stratonovich', dtype=torch.float64, seed=9).to(dev)
+    params = list(sde.parameters())
+    B = 5
+    y0 = (0.2 + 0.3 * torch.rand(B, d, dtype=torch.float64, device=dev)).requires_grad_(True)
+    ts = torch.tensor([0.0, 0.125, 0.25], dtype=torch.float64, device=dev)
+    bm_m = d if kind == 'gbm' else m
+    out = []
+    for adjoint in (True, False):
+        bm = tsde.BrownianInterval(0.0, 0.25, size=(B, bm_m), dtype=torch.float64, device=dev, entropy=21)
+        if adjoint:
+            ys = tsde.sdeint_adjoint(sde, y0, ts, bm=bm, method='reversible_heun',
+                                     adjoint_method='adjoint_reversible_heun', dt=2.0 ** -4)
+        else:
+            ys = tsde.sdeint(sde, y0, ts, bm=bm, method='reversible_heun', dt=2.0 ** -4)
+        loss = (ys ** 2).sum()
+        first = torch.autograd.grad(loss, [y0] + params, create_graph=True)
+        second = sum((g ** 2).sum() for g in first)
+        out.append(([g.detach() for g in first], torch.autograd.grad(second, [y0] + params)))
+    for a, b in zip(out[0][0], out[1][0]):
+        torch.testing.assert_close(a, b, rtol=1e-8, atol=1e-10)
+    for a, b in zip(out[0][1], out[1][1]):
+        torch.testing.assert_close(a, b, rtol=1e-6, atol=1e-8)

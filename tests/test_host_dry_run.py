@@ -310,3 +310,22 @@ def test_empty_batch_flows_through(dry, kind, sde_type, method, levy):
         with torch.no_grad():
             ys = tsde.sdeint(sde, torch.ones(0, d), TS, method=method, dt=DT, bm=bm)
         assert ys.shape == (3, 0, d)
+
+
+@pytest.mark.parametrize('kind,sde_type,method,adjoint_method', [
+    ('general', 'stratonovich', 'midpoint', None), ('gbm', 'stratonovich', 'heun', 'heun'),
+    ('gbm', 'stratonovich', 'reversible_heun', 'adjoint_reversible_heun'),
+    ('general', 'stratonovich', 'reversible_heun', 'adjoint_reversible_heun')])
+def test_double_backward_flows_through(dry, kind, sde_type, method, adjoint_method):
+    """create_graph=True through sdeint_adjoint: the generic adjoint re-enters the Function per interval (reference
+    adjoint.py:97-113), the reversible pair switches to its differentiable sweep; both must produce second-order
+    gradients w.r.t. y0 and the parameters."""
+    sde, y0, bm = _setup(kind, sde_type, 'none')
+    y0 = y0.clone().requires_grad_()
+    ys = tsde.sdeint_adjoint(sde, y0, [0.0, 0.125, 0.25], bm=bm, method=method, adjoint_method=adjoint_method, dt=DT)
+    params = list(sde.parameters())
+    first = torch.autograd.grad((ys ** 2).sum(), [y0] + params, create_graph=True, allow_unused=True)
+    assert all(g is not None for g in first)
+    assert first[0].requires_grad
+    second = torch.autograd.grad(sum((g ** 2).sum() for g in first), [y0] + params, allow_unused=True)
+    assert second[0] is not None and second[0].shape == y0.shape

@@ -280,10 +280,16 @@ class _AdjointMarker:
         }[forward_sde.noise_type]
 
 
-def _generic_backward(sde, bm, dt, ys, ts, grad_ys, params, cfg):
+def _generic_backward(sde, bm, dt, ys, ts, grad_ys, params, cfg, differentiable=False):
     """Backward pass through the augmented adjoint SDE (adjoint.py:65-127) for non-reversible pairs:
     integrate (y, adj_y, adj_params) from -ts[i] to -ts[i-1] with `adjoint_method`, newest interval
-    first, resetting y to the stored ys[i-1] and adding grad_ys[i-1] in between."""
+    first, resetting y to the stored ys[i-1] and adding grad_ys[i-1] in between.  `differentiable`: the caller
+    differentiates this backward pass (create_graph=True, i.e. double backward).  As in the reference
+    (adjoint.py:97-113) every interval then RE-ENTERS `_SdeintAdjointMethod.apply` with the augmented adjoint SDE as
+    the SDE: the second-order gradient is the continuous adjoint of the adjoint solve (same `adjoint_method`), with
+    AdjointSDE building its vjp's with create_graph (adjoint_sde.py:97,118,138,183).  The reference's limits are
+    inherited: an Ito SDE whose adjoint needs the Ito correction cannot be double-backwarded (its AdjointSDE has no
+    `f_and_g`, adjoint_sde.py:267-271)."""
     from .adjoint_sde import AdjointSDE
     aug = [ys[-1], grad_ys[-1]] + [torch.zeros_like(p) for p in params]
     shapes = [t.size() for t in aug]
@@ -295,13 +301,48 @@ def _generic_backward(sde, bm, dt, ys, ts, grad_ys, params, cfg):
                        rtol=cfg['adjoint_rtol'], atol=cfg['adjoint_atol'], dt_min=cfg['dt_min'],
                        options=cfg['adjoint_options'])
     flat = torch.cat([t.reshape(-1) for t in aug]).unsqueeze(0)
+    inner_options = {'_cfg': cfg}
     for i in range(ys.size(0) - 1, 0, -1):
-        out, _ = solver.integrate(flat, torch.stack([-ts[i], -ts[i - 1]]), ())
+        if differentiable:
+            out, = _SdeintAdjointMethod.apply(adjoint_sde, torch.stack([-ts[i], -ts[i - 1]]), dt, reverse_bm, solver, {},
+                                              inner_options, 0, flat, *params)
+        else:
+            out, _ = solver.integrate(flat, torch.stack([-ts[i], -ts[i - 1]]), ())
         parts = [p.reshape(s) for p, s in zip(out[-1].squeeze(0).split(numels), shapes)]
         parts[0] = ys[i - 1]
         parts[1] = parts[1] + grad_ys[i - 1]
         flat = torch.cat([t.reshape(-1) for t in parts]).unsqueeze(0)
     return parts[1], parts[2:]
+
+
+def _reversible_backward_differentiable(sde, bm, dt, ts, y0, extras0, params, grad_ys, grad_extras):
+    """Differentiable backward pass of the reversible pair, for double backward (create_graph=True).
+
+    The reference cannot do this at all (its re-entered Function finds no saved solver state and
+    AdjointReversibleHeun.init_extra_solver_state raises, reversible_heun.py:93-96).  Reversible Heun's adjoint IS the
+    exact gradient of the discrete forward solve, so a differentiable version of it is obtained by re-running the
+    forward solve from the Function's saved INPUTS (y0, the initial solver state, the parameters) with every tableau
+    launch recorded as an autograd node, and taking the vector-Jacobian product with create_graph=True.  (Working
+    from the saved inputs rather than from the saved outputs matters: the outputs' history passes through this very
+    Function, and differentiating through it inside its own backward would recurse.)  Memory O(T) like backprop
+    through the solver; first-order backward passes never come here."""
+    with torch.enable_grad():
+        y0_in = y0 if y0.requires_grad else y0.detach().requires_grad_()
+        extras_in = [e if e.requires_grad else e.detach().requires_grad_() for e in extras0]
+        solver = methods.ReversibleHeun(sde=sde, bm=bm, dt=dt, adaptive=False, rtol=None, atol=None, dt_min=None,
+                                        options={})
+        solver._autograd = True
+        ys_re, extras_re = solver.integrate(y0_in, ts, tuple(extras_in))
+        outs, gouts = [], []
+        for o, go in zip([ys_re, *extras_re], [grad_ys, *grad_extras]):
+            if o.requires_grad:
+                outs.append(o)
+                gouts.append(go)
+        inputs = [y0_in, *extras_in, *params]
+        grads = torch.autograd.grad(outs, inputs, gouts, create_graph=True, allow_unused=True)
+    grads = [torch.zeros_like(x) if g is None else g for g, x in zip(grads, inputs)]
+    n = len(extras_in)
+    return grads[0], tuple(grads[1:1 + n]), grads[1 + n:]
 
 
 class _SdeintAdjointMethod(torch.autograd.Function):
@@ -320,7 +361,9 @@ class _SdeintAdjointMethod(torch.autograd.Function):
                 and adjoint_options_reversible(adjoint_options):
             engine = _BackwardEngine(sde, ReverseBrownian(bm), dt, params)
             ctx.bwd_plan = _backward_plan(engine, ys, ts, extras_out)
-        ctx.save_for_backward(ys, ts, *extras_out, *params)
+        # (y0 and the initial solver state are saved as well: the differentiable backward of the reversible pair
+        # re-runs the solve from the Function's INPUTS, see _reversible_backward_differentiable)
+        ctx.save_for_backward(ys, ts, *extras_out, *params, y0, *extras_and_params[:n_extras])
         return (ys, *extras_out)
 
     @staticmethod
@@ -331,15 +374,26 @@ class _SdeintAdjointMethod(torch.autograd.Function):
     @staticmethod
     def _backward(ctx, grad_ys, *grad_extras):
         ys, ts, *rest = ctx.saved_tensors
+        n_in = 1 + ctx.n_extras
+        y0_in, extras_in = rest[-n_in], rest[len(rest) - n_in + 1:]
+        rest = rest[:-n_in]
         extras = rest[:ctx.n_extras]
         params = rest[ctx.n_extras:]
+        # Double backward (reference adjoint.py:97-113 re-enters the Function so that the backward pass is itself
+        # differentiable): when this backward runs with grad mode on (autograd.grad(..., create_graph=True)), the
+        # sweep is executed with differentiable operations instead of the fused no-grad kernels.
+        differentiable = torch.is_grad_enabled()
         if not adjoint_options_reversible(ctx.adjoint_options):
             # generic adjoint: the solver's extra state is not part of the augmented system (adjoint.py:57-60)
-            with torch.no_grad():
+            with (torch.enable_grad() if differentiable else torch.no_grad()):
                 adj_y, adj_params = _generic_backward(ctx.sde, ctx.bm, ctx.dt, ys, ts, grad_ys, list(params),
-                                                      ctx.adjoint_options['_cfg'])
+                                                      ctx.adjoint_options['_cfg'], differentiable)
             return (None, None, None, None, None, None, None, None, adj_y, *([None] * ctx.n_extras), *adj_params)
         grad_extras = [torch.zeros_like(e) if g is None else g for g, e in zip(grad_extras, extras)]
+        if differentiable:
+            adj_y, adj_extras, adj_params = _reversible_backward_differentiable(
+                ctx.sde, ctx.bm, ctx.dt, ts, y0_in, extras_in, list(params), grad_ys, grad_extras)
+            return (None, None, None, None, None, None, None, None, adj_y, *adj_extras, *adj_params)
         with torch.no_grad():
             if ctx.bwd_plan is not None:
                 adj_y, adj_extras, adj_params = _replay_backward(ctx.bwd_plan, ctx.bm, ys, grad_ys, extras,
