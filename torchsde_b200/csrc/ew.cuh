@@ -45,7 +45,7 @@ inline bool pdl_enabled() {
 }
 
 // TSDE_EW_CTAS=n: use at most n resident CTAs per SM for the persistent grids of the row-wise kernels (experiments:
-// leaving register file / thread slots free lets a concurrent branch of the graph co-reside).
+// measured on cfg2, fewer resident CTAs only lose — 47.6 ms per solve at 4, 49.0 at 3, 51.6 at 2).
 inline int ctas_per_sm_limit() {
   static int v = -1;
   if (v < 0) {
@@ -243,56 +243,6 @@ __device__ __forceinline__ void counter_noise(const NoiseP<T>& nz, Key key, uint
   }
 }
 
-// Two-phase form of the single-cell counter noise, used by the software-pipelined fast kernel: `raw` is the integer
-// half (Philox: IMAD.WIDE + LOP3, fma-heavy and alu pipes), `finish` the floating-point half (Box-Muller: fma-lite
-// and SFU pipes).  All warps of a kernel run the same program in near lock-step, so without pipelining the whole SM
-// alternates between an integer phase and a float phase and each phase saturates its pipe while the others idle
-// (ncu r02: math-pipe-throttle + dispatch stalls with no pipe above 40 % on average); issuing iteration i+1's Philox
-// next to iteration i's Box-Muller lets the scheduler mix the pipes.  fp64 keeps the one-phase form (raw = the
-// counter itself).
-template <typename T, bool WANT_U>
-struct RawNoise {
-  uint32_t row, q;  // fp64: nothing precomputed
-};
-template <bool WANT_U>
-struct RawNoise<float, WANT_U> {
-  uint4 xw, xh;
-};
-
-template <bool WANT_U>
-__device__ __forceinline__ void counter_raw(const NoiseP<float>& nz, Key key, uint32_t row, uint32_t q,
-                                            RawNoise<float, WANT_U>& r) {
-  r.xw = philox4x32_10(make_uint4(q | (STREAM_W << 24), row, (uint32_t)nz.cell_id, (uint32_t)(nz.cell_id >> 32)),
-                       key.lo, key.hi);
-  if (WANT_U)
-    r.xh = philox4x32_10(make_uint4(q | (STREAM_H << 24), row, (uint32_t)nz.cell_id, (uint32_t)(nz.cell_id >> 32)),
-                         key.lo, key.hi);
-}
-template <bool WANT_U>
-__device__ __forceinline__ void counter_raw(const NoiseP<double>&, Key, uint32_t row, uint32_t q,
-                                            RawNoise<double, WANT_U>& r) {
-  r.row = row;
-  r.q = q;
-}
-template <bool WANT_U>
-__device__ __forceinline__ void counter_finish(const NoiseP<float>& nz, Key, const RawNoise<float, WANT_U>& r,
-                                               float (&w)[4], float (&u)[4]) {
-  float n[4];
-  box_muller4(r.xw, n);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) w[j] = n[j] * nz.sqrt_h;
-  if (WANT_U) {
-    box_muller4(r.xh, n);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) u[j] = nz.ht * (0.5f * w[j] + n[j] * nz.sqrt_h12);  // _H_to_U :102-103
-  }
-}
-template <bool WANT_U>
-__device__ __forceinline__ void counter_finish(const NoiseP<double>& nz, Key key, const RawNoise<double, WANT_U>& r,
-                                               double (&w)[4], double (&u)[4]) {
-  counter_noise<double, WANT_U, false>(nz, key, r.row, r.q, w, u);
-}
-
 template <typename T, int SRC, bool WANT_U>
 __device__ __forceinline__ void quad_noise(const NoiseP<T>& nz, Key key, int64_t row, int64_t q,
                                            bool vec, int nvalid, T (&w)[4], T (&u)[4]) {
@@ -385,6 +335,9 @@ ew_kernel(const EwP<Op::NIN, Op::NOUT> p, const NoiseP<T> nz, const Op op) {
 // broadcast, quads-per-row a power of two (or divisible by multiply-shift), fewer than 2^31 quads.
 // Everything is 32-bit index arithmetic and there is no per-quad branching.
 //
+// (Tried and rejected, r02: software-pipelining the integer half of iteration i+1's noise (Philox) next to the float
+// half of iteration i (Box-Muller) — 10-15 % SLOWER on every RNG-bound kernel (seed 8.5 -> 9.7 us, cells 6.6 -> 7.4):
+// the carried Philox state costs more than the pipe mixing gains.)
 // Light ops (at most 3 tensors per quad: the Milstein vjp seed, the Brownian materialisation, the
 // predictor stages) are NOT HBM-bound per thread: the Philox + Box-Muller chain (~150 dependent-ish
 // instructions per quad) dominates and one 128-bit load per thread does not cover the HBM latency-bandwidth
@@ -410,24 +363,18 @@ struct FastCtx {
   __device__ __forceinline__ uint32_t quad_of(uint32_t Q, uint32_t row) const {
     return pow2 ? (Q & qmask) : (Q - row * qpr32);
   }
-  __device__ __forceinline__ void raw(uint32_t Q, RawNoise<T, Op::WANT_U>& out) const {
+  __device__ __forceinline__ void rng(uint32_t Q, T (&w)[4], T (&u)[4]) const {
     const uint32_t r = row_of(Q);
-    counter_raw<Op::WANT_U>(nz, key, r + row_off, quad_of(Q, r), out);
-  }
-  __device__ __forceinline__ void finish(const RawNoise<T, Op::WANT_U>& in, T (&w)[4], T (&u)[4]) const {
-    counter_finish<Op::WANT_U>(nz, key, in, w, u);
+    counter_noise<T, Op::WANT_U, false>(nz, key, r + row_off, quad_of(Q, r), w, u);
   }
 };
 
-// One iteration: U quads Q, Q + kThreads, ... (each warp access stays one contiguous 512-byte run).  `cur` holds
-// the integer half of this iteration's counter noise (produced by the previous iteration, or ahead of the
-// dependency wait for the first one); the integer half of the NEXT iteration's noise is produced here, next to this
-// iteration's Box-Muller (see RawNoise).
-template <typename T, typename Op, int SRC, int U>
-__device__ __forceinline__ void ew_fast_body(const FastCtx<T, Op>& c, uint32_t Q, uint32_t Qnext,
-                                             RawNoise<T, Op::WANT_U> (&cur)[U]) {
+// One iteration: U quads Q, Q + kThreads, ... (each warp access stays one contiguous 512-byte run).
+// FIRST: the counter noise was produced ahead of the dependency wait and is passed in (w0, u0).
+template <typename T, typename Op, int SRC, int U, bool FIRST>
+__device__ __forceinline__ void ew_fast_body(const FastCtx<T, Op>& c, uint32_t Q, const T (&w0)[U][4],
+                                             const T (&u0)[U][4]) {
   constexpr int NIN = Op::NIN, NOUT = Op::NOUT;
-  constexpr bool COUNTER = Op::USES_NOISE && SRC == TSDE_SRC_COUNTER;
   bool ok[U];
   T in[U][NIN > 0 ? NIN : 1][4];
 #pragma unroll
@@ -446,18 +393,21 @@ __device__ __forceinline__ void ew_fast_body(const FastCtx<T, Op>& c, uint32_t Q
     }
   }
   T w[U][4], u[U][4];
-  RawNoise<T, Op::WANT_U> nxt[U];
 #pragma unroll
   for (int k = 0; k < U; ++k) {
-    const size_t base = (size_t)(Q + (uint32_t)k * kThreads) * 4;
+    const uint32_t Qk = Q + (uint32_t)k * kThreads;
+    const size_t base = (size_t)Qk * 4;
 #pragma unroll
     for (int j = 0; j < 4; ++j) { w[k][j] = T(0); u[k][j] = T(0); }
     if (Op::USES_NOISE) {
-      if (COUNTER) {
-        // unconditional (a quad past the slice end costs nothing observable): the Philox chains of the next
-        // iteration and the Box-Muller chains of this one must stay in one basic block to interleave
-        c.raw(Qnext + (uint32_t)k * kThreads, nxt[k]);
-        c.finish(cur[k], w[k], u[k]);
+      if (SRC == TSDE_SRC_COUNTER) {
+        if (FIRST) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { w[k][j] = w0[k][j]; u[k][j] = Op::WANT_U ? u0[k][j] : T(0); }
+        } else {
+          c.rng(Qk, w[k], u[k]);  // unconditional (a quad past the slice end costs nothing observable): the U
+                                  // Philox chains must stay in one basic block to interleave
+        }
       } else if (SRC == TSDE_SRC_MEMORY) {
         if (ok[k]) {
           ld4(c.nz.w + base, w[k]);
@@ -471,7 +421,6 @@ __device__ __forceinline__ void ew_fast_body(const FastCtx<T, Op>& c, uint32_t Q
   }
 #pragma unroll
   for (int k = 0; k < U; ++k) {
-    if (COUNTER) cur[k] = nxt[k];
     if (!ok[k]) continue;
     const size_t base = (size_t)(Q + (uint32_t)k * kThreads) * 4;
     T out[NOUT][4];
@@ -503,16 +452,20 @@ ew_fast_kernel(const EwP<Op::NIN, Op::NOUT> p, const NoiseP<T> nz, const Op op) 
                          (uint32_t)p.qpr, (uint32_t)nz.row_offset, p.qmagic, pow2,
                          p.vec > 1 /* host sets vec = 2 to enable evict-first loads */};
   // Programmatic dependent launch: this grid may start while its predecessor in the stream/graph is
-  // still draining.  Everything that does not touch the predecessor's outputs — the Philox half of the
-  // thread's first U quads — runs before `griddepcontrol.wait`; all loads and stores come after.
-  RawNoise<T, Op::WANT_U> cur[U];
+  // still draining.  Everything that does not touch the predecessor's outputs — the Philox/Box-Muller
+  // work of the thread's first U quads — runs before `griddepcontrol.wait`; all loads and stores come after.
+  T w0[U][4], u0[U][4];
   const uint32_t Q0 = q_begin + threadIdx.x;
   if (COUNTER) {
 #pragma unroll
-    for (int k = 0; k < U; ++k) c.raw(Q0 + (uint32_t)k * kThreads, cur[k]);
+    for (int k = 0; k < U; ++k) {
+      c.rng(Q0 + (uint32_t)k * kThreads, w0[k], u0[k]);
+    }
   }
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  for (uint32_t Q = Q0; Q < q_end; Q += U * kThreads) ew_fast_body<T, Op, SRC, U>(c, Q, Q + U * kThreads, cur);
+  if (Q0 >= q_end) return;
+  ew_fast_body<T, Op, SRC, U, true>(c, Q0, w0, u0);
+  for (uint32_t Q = Q0 + U * kThreads; Q < q_end; Q += U * kThreads) ew_fast_body<T, Op, SRC, U, false>(c, Q, w0, u0);
 }
 
 // ---- host-side launcher -----------------------------------------------------------------------
