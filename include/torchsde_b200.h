@@ -152,6 +152,16 @@ int tsde_brownian_merge(const tsde_launch* L, void* w0, void* h0, const void* w1
                         const void* h1, double len0, double len1, double tot);
 
 /*
+ * One launch for the query pattern of the Levy-area methods on a solver grid: W (rows,m), U = h (W/2 + H) (rows,m)
+ * and the Davie / Foster area A (rows,m,m) of ONE primary cell (nz: COUNTER source, n_cells == 1, cell nz->cell_id of
+ * length nz->h), with H drawn from the counter as well and never materialised.  Replaces BrownianInterval.__call__
+ * (ta, tb, return_U=True, return_A=True) for a whole cell: brownian_interval.py:589-687 with _randn :30-32, the
+ * top-level law :551-558, _davie_foster_approximation :78-99 and _H_to_U :102-103.  Requires m % 4 == 0, 4 <= m <= 64.
+ */
+int tsde_brownian_cell_levy(const tsde_launch* L, const tsde_noise* nz, uint64_t a_id, int32_t foster, void* out_w,
+                            void* out_u, void* out_a);
+
+/*
  * GA = g A for the log-ODE correction (base_sde.py:170,191: `ga = torch.bmm(g, a)` inside
  * dg_ga_jvp_column_sum_v1/_v2; used by methods/log_ode.py:39-56).  g is (rows,d,m), a is (rows,m,m) (the Levy
  * area of the step), out_t is (m, rows, d): column l of g A as a contiguous (rows,d) slab, which is what the

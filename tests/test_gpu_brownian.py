@@ -342,3 +342,26 @@ def test_bmm_ga_kernel_vs_torch(dtype, B, d, m):
     ref = torch.bmm(g.double(), a.double()).permute(2, 0, 1)
     tol = dict(rtol=1e-5, atol=1e-5) if dtype == torch.float32 else dict(rtol=1e-12, atol=1e-12)
     torch.testing.assert_close(out.double(), ref, **tol)
+
+
+@pytest.mark.parametrize('levy', ['davie', 'foster'])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float64])
+def test_fused_cell_levy_query_equals_general_path(levy, dtype):
+    """tsde_brownian_cell_levy (W, U, A of one whole grid cell in one launch) against the three-kernel general path
+    (cells -> levy_area -> h_to_u) on the same Brownian motion: bit-identical."""
+    tsde = _tsde()
+    kw = dict(size=(257, 8), dtype=dtype, device=DEV, entropy=99, dt=0.125, levy_area_approximation=levy)
+    fused = tsde.BrownianInterval(0.0, 1.0, **kw)
+    general = tsde.BrownianInterval(0.0, 1.0, **kw)
+    for k in (0, 3, 7):
+        ta, tb = k * 0.125, (k + 1) * 0.125
+        Wf, Uf, Af = fused(ta, tb, return_U=True, return_A=True)
+        general(ta, tb, return_U=True)                      # materialises (and caches) the cell: no fused launch next
+        Wg, Ug, Ag = general(ta, tb, return_U=True, return_A=True)
+        assert torch.equal(Wf, Wg) and torch.equal(Uf, Ug) and torch.equal(Af, Ag)
+    # a two-cell query cannot use the fused launch and must stay consistent with the cells (Chen's relation, :671)
+    W2, A2 = fused(0.0, 0.25, return_A=True)
+    W0, A0 = general(0.0, 0.125, return_A=True)
+    W1, A1 = general(0.125, 0.25, return_A=True)
+    expect = A0 + A1 + 0.5 * (W0.unsqueeze(2) * W1.unsqueeze(1) - W1.unsqueeze(2) * W0.unsqueeze(1))
+    torch.testing.assert_close(A2, expect, rtol=1e-5, atol=1e-6)

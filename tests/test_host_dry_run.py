@@ -191,6 +191,9 @@ def test_every_solver_entry_point_is_reached(dry):
     bm = tsde.BrownianInterval(0.0, 1.0, size=(4, 2), device='cpu', levy_area_approximation='davie')
     bm(0.0, 0.5, return_U=True, return_A=True)
     bm(0.25, 0.75, return_U=True, return_A=True)      # covers pieces of two nodes: increments and areas are merged
+    grid = tsde.BrownianInterval(0.0, 1.0, size=(4, 4), device='cpu', levy_area_approximation='foster', dt=0.25)
+    w, u, a = grid(0.25, 0.5, return_U=True, return_A=True)   # one whole cell of the dt grid: the fused W/U/A launch
+    assert w.shape == u.shape == (4, 4) and a.shape == (4, 4, 4)
     not_reached = set(_cabi.SIGNATURES) - set(dry.calls)
     assert not not_reached, sorted(not_reached)
 

@@ -565,6 +565,13 @@ class BrownianInterval(brownian_base.BaseBrownian):
             if self._dt is not None and self._root.kind == _LEAF and self._root_value is None \
                     and self._user_W is None and self._user_H is None and not self._halfway_tree:
                 self._bind_uniform(self._dt)
+            if self._have_A and return_A:
+                fused = self._query_cell_levy(ta_r, tb_r)
+                if fused is not None:
+                    W, U, A = fused
+                    W, U = W.reshape(self._size), U.reshape(self._size)
+                    A = A.reshape((*self._size, *self._size[-1:]))
+                    return (W, U, A) if return_U else (W, A)
             fast = self._query_cells_wu(ta_r, tb_r, tb - ta) if (self._have_H and not self._have_A) else None
             if fast is not None:
                 W, U = fast
@@ -623,6 +630,40 @@ class BrownianInterval(brownian_base.BaseBrownian):
                                                     None), "tsde_brownian_cells")
         self._last = root
         return W, U
+
+    def _query_cell_levy(self, ta, tb):
+        """Single-launch answer (W, U, A) when [ta, tb] is exactly ONE primary cell of the root grid — the access
+        pattern of a Levy-area method (log-ODE) stepping on its grid, or of sequential dt-spaced queries: the cell's
+        W and H are drawn inside the kernel that forms the area, H is never materialised.  Same numbers as the general
+        path (cells -> levy_area -> h_to_u), which serves every other query."""
+        root = self._root
+        if root.kind != _GRID or len(self._size) < 2 or self._m % 4 != 0 or not (4 <= self._m <= 64):
+            return None
+        b = root.bounds
+        i = bisect.bisect_left(b, ta)
+        if i + 1 >= len(b) or b[i] != ta or b[i + 1] != tb:
+            return None
+        cell = root.cell(i)
+        if self._cache_get(cell) is not None:
+            return None  # (the cell's (W, H) was already materialised: answer from it, as the general path does)
+        nz = _cabi.Noise()
+        nz.source = _cabi.SRC_COUNTER
+        nz.want_u = 1
+        nz.key = self.key_tensor().data_ptr()
+        nz.cell_id = cell.id
+        nz.row_offset = self._row_offset
+        nz.n_cells = 1
+        nz.h = b[i + 1] - b[i]
+        nz.h_total = nz.h
+        nz.cell_h = None
+        W, U, A = self._new(), self._new(), self._new(self._m)
+        L = self._launch()
+        foster = 1 if self._levy_area_approximation == LEVY_AREA_APPROXIMATIONS.foster else 0
+        _cabi.check(_cabi.lib().tsde_brownian_cell_levy(ctypes.byref(L), ctypes.byref(nz), cell.id, foster,
+                                                        W.data_ptr(), U.data_ptr(), A.data_ptr()),
+                    "tsde_brownian_cell_levy")
+        self._last = root
+        return W, U, A
 
     def _piece_value(self, piece):
         if isinstance(piece, _Node):

@@ -302,11 +302,15 @@ __device__ __forceinline__ T levy_pair_value(T wi, T wj, T hi, T hj, T z, T tent
 
 constexpr int kLevyWarps = 8;
 
-template <typename T>
+// GEN: the row's W and H are not read but drawn from the counter (primary cell `cell_id` of length h: W = sqrt(h) N_W,
+// H = sqrt(h/12) N_H, as counter_noise does), and W and U = h (W/2 + H) are written out as well: one launch answers a
+// whole-cell query bm(ta, tb, return_U=True, return_A=True) (brownian_interval.py:589-687).
+template <typename T, bool GEN>
 __global__ void __launch_bounds__(kLevyWarps * 32)
 levy_tile_kernel(const void* keyp, int64_t row_offset, uint64_t a_id, int64_t rows, int m, int npairs, int warps,
                  const T* __restrict__ w, const T* __restrict__ hh, T tenth_h, T davie_std, int foster,
-                 T* __restrict__ out, int vec) {
+                 T* __restrict__ out, int vec, uint64_t cell_id, T sqrt_h, T sqrt_h12, T ht, T* __restrict__ out_w,
+                 T* __restrict__ out_u) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int mm = m * m;
   const int tile = (mm + 2 * m + 3) & ~3;                  // floats per warp: A tile | W | H (16-byte multiple)
@@ -329,12 +333,36 @@ levy_tile_kernel(const void* keyp, int64_t row_offset, uint64_t a_id, int64_t ro
   const int nq = (npairs + 3) >> 2;
   const int64_t row_stride = (int64_t)gridDim.x * warps;
   for (int64_t row = (int64_t)blockIdx.x * warps + warp; row < rows; row += row_stride) {
-    for (int c = lane; c < m; c += 32) {
-      sW[c] = w[row * m + c];
-      sH[c] = hh[row * m + c];
-    }
-    __syncwarp();
     const uint32_t grow = (uint32_t)(row + row_offset);
+    if (GEN) {
+      const int mq = m >> 2;                              // (host guarantees m % 4 == 0 in this mode)
+      for (int t = lane; t < 2 * mq; t += 32) {
+        const bool is_h = t >= mq;
+        const int q = is_h ? t - mq : t;
+        T n[4], v[4];
+        normal4(key, cell_id, is_h ? STREAM_H : STREAM_W, grow, (uint32_t)q, n);
+        const T sc = is_h ? sqrt_h12 : sqrt_h;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = n[j] * sc;
+        st4((is_h ? sH : sW) + 4 * q, v);
+        if (!is_h) st4(out_w + row * m + 4 * q, v);
+      }
+      __syncwarp();
+      for (int q = lane; q < mq; q += 32) {
+        T a4[4], b4[4], u4[4];
+        ld4(sW + 4 * q, a4);
+        ld4(sH + 4 * q, b4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) u4[j] = ht * (T(0.5) * a4[j] + b4[j]);   // _H_to_U :102-103
+        st4(out_u + row * m + 4 * q, u4);
+      }
+    } else {
+      for (int c = lane; c < m; c += 32) {
+        sW[c] = w[row * m + c];
+        sH[c] = hh[row * m + c];
+      }
+      __syncwarp();
+    }
     for (int q = lane; q < nq; q += 32) {
       T z[4];
       normal4(key, a_id, STREAM_A, grow, (uint32_t)q, z);
@@ -406,6 +434,47 @@ merge_area_kernel(int64_t rows, int64_t m, T* a0, const T* a1, const T* w0, cons
 
 using namespace tsde;
 
+constexpr int kLevyNoTile = -54321;
+
+template <typename T, bool GEN>
+static int launch_levy_tiles(const tsde_launch* L, const void* key, int64_t row_offset, uint64_t a_id, const void* w,
+                             const void* hh, double h, int32_t foster, void* out_a, uint64_t cell_id, void* out_w,
+                             void* out_u, cudaStream_t st) {
+  const int64_t m = L->m;
+  const int npairs = (int)(m * (m - 1) / 2);
+  const size_t tile = (size_t)((m * m + 2 * m + 3) & ~3ll) * sizeof(T);
+  const size_t table = ((size_t)2 * npairs + 15) & ~(size_t)15;
+  int warps = (int)((46 * 1024 - table) / tile);
+  if (warps > kLevyWarps) warps = kLevyWarps;
+  if (warps < 1) return kLevyNoTile;
+  const size_t smem = table + (size_t)warps * tile;
+  int64_t blocks = (L->rows + warps - 1) / warps;
+  const int64_t cap = (int64_t)sm_count() * 8;   // persistent: a few CTAs per SM, rows strided over them
+  if (blocks > cap) blocks = cap;
+  const int vec = ((m * m) % 4 == 0 && aligned16(out_a)) ? 1 : 0;
+  levy_tile_kernel<T, GEN><<<(unsigned)blocks, kLevyWarps * 32, smem, st>>>(
+      key, row_offset, a_id, L->rows, (int)m, npairs, warps, (const T*)w, (const T*)hh, (T)(0.1 * h),
+      (T)sqrt((1.0 / 12.0) * h * h), foster, (T*)out_a, vec, cell_id, (T)sqrt(h), (T)sqrt(h / 12.0), (T)h, (T*)out_w,
+      (T*)out_u);
+  return (int)cudaGetLastError();
+}
+
+// One launch for a whole-cell query with Levy area: W, U and A of primary cell nz->cell_id.
+template <typename T>
+static int cell_levy_impl(const tsde_launch* L, const tsde_noise* nz, uint64_t a_id, int32_t foster, void* out_w,
+                          void* out_u, void* out_a) {
+  if (!nz || nz->source != TSDE_SRC_COUNTER || !nz->key || nz->n_cells != 1 || !out_w || !out_u || !out_a)
+    return TSDE_EINVAL;
+  const int64_t m = L->m;
+  if (m < 4 || m > 64 || (m % 4) != 0 || !aligned16(out_w) || !aligned16(out_u)) return TSDE_EINVAL;
+  if (L->rows == 0) return 0;
+  if (L->rows + nz->row_offset > 0xFFFFFFFFll) return TSDE_EINVAL;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(L->stream);
+  const int rc = launch_levy_tiles<T, true>(L, nz->key, nz->row_offset, a_id, nullptr, nullptr, nz->h, foster, out_a,
+                                            nz->cell_id, out_w, out_u, st);
+  return rc == kLevyNoTile ? TSDE_EINVAL : rc;
+}
+
 template <typename T>
 static int levy_impl(const tsde_launch* L, const void* key, int64_t row_offset, uint64_t a_id,
                      const void* w, const void* hh, double h, int32_t foster, void* out_a) {
@@ -418,22 +487,8 @@ static int levy_impl(const tsde_launch* L, const void* key, int64_t row_offset, 
   const double r12 = 1.0 / 12.0;
   const int64_t m = L->m;
   if (m >= 2 && m <= 64) {
-    const int npairs = (int)(m * (m - 1) / 2);
-    const size_t tile = (size_t)((m * m + 2 * m + 3) & ~3ll) * sizeof(T);
-    const size_t table = ((size_t)2 * npairs + 15) & ~(size_t)15;
-    int warps = (int)((46 * 1024 - table) / tile);
-    if (warps > kLevyWarps) warps = kLevyWarps;
-    if (warps >= 1) {
-      const size_t smem = table + (size_t)warps * tile;
-      int64_t blocks = (L->rows + warps - 1) / warps;
-      const int64_t cap = (int64_t)sm_count() * 8;   // persistent: a few CTAs per SM, rows strided over them
-      if (blocks > cap) blocks = cap;
-      const int vec = ((m * m) % 4 == 0 && aligned16(out_a)) ? 1 : 0;
-      levy_tile_kernel<T><<<(unsigned)blocks, kLevyWarps * 32, smem, st>>>(
-          key, row_offset, a_id, L->rows, (int)m, npairs, warps, (const T*)w, (const T*)hh, (T)(0.1 * h),
-          (T)sqrt(r12 * h * h), foster, (T*)out_a, vec);
-      return (int)cudaGetLastError();
-    }
+    const int rc = launch_levy_tiles<T, false>(L, key, row_offset, a_id, w, hh, h, foster, out_a, 0, nullptr, nullptr, st);
+    if (rc != kLevyNoTile) return rc;
   }
   levy_area_kernel<T><<<grid_for(total), kThreads, 0, st>>>(
       key, row_offset, a_id, L->rows, L->m, (const T*)w, (const T*)hh, (T)(0.1 * h),
@@ -460,6 +515,12 @@ int tsde_brownian_cells(const tsde_launch* L, const tsde_noise* nz, void* out_w,
                         void* out_h) {
   return TSDE_DISPATCH_DTYPE(L, cells_impl<float>(L, nz, out_w, out_u, out_h),
                              cells_impl<double>(L, nz, out_w, out_u, out_h));
+}
+
+int tsde_brownian_cell_levy(const tsde_launch* L, const tsde_noise* nz, uint64_t a_id, int32_t foster, void* out_w,
+                            void* out_u, void* out_a) {
+  return TSDE_DISPATCH_DTYPE(L, cell_levy_impl<float>(L, nz, a_id, foster, out_w, out_u, out_a),
+                             cell_levy_impl<double>(L, nz, a_id, foster, out_w, out_u, out_a));
 }
 
 int tsde_brownian_bridge(const tsde_launch* L, const void* key, int64_t row_offset, int32_t depth,
