@@ -59,5 +59,13 @@ a = torch.empty(B, M, M, device=dev)
 Lb = _cabi.make_launch(torch.float32, _cabi.NOISE_DIAGONAL, B, M, M)
 for _ in range(3):
     lib.tsde_brownian_levy_area(ctypes.byref(Lb), key.data_ptr(), 0, 77, w.data_ptr(), h.data_ptr(), 2.0 ** -6, 1, a.data_ptr())
+# bmm(g, A) of the log-ODE correction at the cfg3 size
+B, D, M = 8192, 32, 16
+gg = torch.randn(B, D, M, device=dev)
+aa = torch.randn(B, M, M, device=dev)
+oo = torch.empty(M, B, D, device=dev)
+Lbm = _cabi.make_launch(torch.float32, _cabi.NOISE_GENERAL, B, D, M)
+for _ in range(3):
+    lib.tsde_bmm_ga(ctypes.byref(Lbm), gg.data_ptr(), aa.data_ptr(), oo.data_ptr())
 torch.cuda.synchronize()
 print('ok')

@@ -551,11 +551,42 @@ def gradgrad_cases():
         print('wrote gradgrad', name, len(rec.log), 'queries')
 
 
+def adjoint_adaptive_cases():
+    """sdeint_adjoint with the reversible pair and adjoint_adaptive=True (adjoint.py:245-249: warns, then integrates
+    the adjoint adaptively): gradients on identical increments, including the backward pass's data-dependent queries."""
+    import warnings
+    for i, (name, kind, d, m) in enumerate([('gbm', 'gbm', 5, 5), ('general', 'general', 4, 3), ('scalar', 'scalar', 4, 1)]):
+        torch.manual_seed(6100 + i)
+        tdt = torch.float64
+        sde = problems.make(kind, d, m, 'stratonovich', dtype=tdt, seed=i + 6)
+        B = 3
+        y0 = (0.1 + 0.5 * torch.rand(B, d, dtype=tdt)).requires_grad_(True)
+        ts = torch.tensor([0.0, 0.25, 0.5], dtype=tdt)
+        bm_m = d if kind == 'gbm' else m
+        bm = torchsde.BrownianInterval(0.0, 0.5, size=(B, bm_m), dtype=tdt, entropy=2100 + i)
+        rec = Recorder(bm)
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            ys = torchsde.sdeint_adjoint(sde, y0, ts, bm=rec, method='reversible_heun',
+                                         adjoint_method='adjoint_reversible_heun', dt=0.125, adjoint_adaptive=True,
+                                         adjoint_rtol=1e-2, adjoint_atol=1e-2, dt_min=2e-3)
+            n_fwd = len(rec.log)
+            weights = torch.linspace(0.5, 1.5, ys.numel(), dtype=tdt).reshape(ys.shape)
+            (ys * weights).sum().backward()
+        save = dict(y0=y0.detach().numpy(), ts=ts.numpy(), dt=np.float64(0.125), ys=ys.detach().numpy(), kind=kind, d=d,
+                    m=m, seed=i + 6, weights=weights.numpy(), grad_y0=y0.grad.numpy(), rtol=1e-2, atol=1e-2,
+                    dt_min=2e-3, n_forward_queries=n_fwd)
+        for n, p in sde.named_parameters():
+            save['grad.' + n] = p.grad.numpy()
+        np.savez_compressed(os.path.join(HERE, f'adjadaptive_{name}.npz'), **_rec_save(rec, save))
+        print('wrote adjadaptive', name, n_fwd, 'forward +', len(rec.log) - n_fwd, 'backward queries')
+
+
 if __name__ == '__main__':
-    for only in ('variant', 'logqp', 'bpadaptive', 'gradgrad'):
+    for only in ('variant', 'logqp', 'bpadaptive', 'gradgrad', 'adjadaptive'):
         if only in sys.argv:
             {'variant': variant_cases, 'logqp': logqp_cases, 'bpadaptive': bpadaptive_cases,
-             'gradgrad': gradgrad_cases}[only]()
+             'gradgrad': gradgrad_cases, 'adjadaptive': adjoint_adaptive_cases}[only]()
             sys.exit(0)
     if 'adaptive' in sys.argv:
         adaptive_cases()
@@ -581,3 +612,4 @@ if __name__ == '__main__':
     logqp_cases()
     bpadaptive_cases()
     gradgrad_cases()
+    adjoint_adaptive_cases()

@@ -246,3 +246,30 @@ def test_double_backward_reversible_pair(kind, d, m):
         torch.testing.assert_close(a, b, rtol=1e-8, atol=1e-10)
     for a, b in zip(out[0][1], out[1][1]):
         torch.testing.assert_close(a, b, rtol=1e-6, atol=1e-8)
+
+
+@pytest.mark.parametrize('path', helpers.golden_files('adjadaptive_'), ids=helpers.case_id)
+def test_adjoint_adaptive_reversible_pair_golden_replay(path):
+    """adjoint_adaptive=True with the reversible pair: the reference warns and integrates the adjoint adaptively
+    (adjoint.py:245-249); the backward engine must take the same accept / reject decisions (its queries are replayed
+    from the reference's own log: an unknown (ta, tb) raises) and return the same gradients."""
+    import warnings
+    tsde = _tsde()
+    case = helpers.load(path)
+    dev = torch.device('cuda')
+    kind, d, m = str(case['kind']), int(case['d']), int(case['m'])
+    sde = problems.make(kind, d, m, 'stratonovich', dtype=torch.float64, seed=int(case['seed'])).to(dev)
+    y0 = torch.from_numpy(case['y0']).to(dev).requires_grad_(True)
+    ts = torch.from_numpy(case['ts']).to(dev)
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter('always')
+        ys = tsde.sdeint_adjoint(sde, y0, ts, bm=helpers.replay_torch(case, dev), method='reversible_heun',
+                                 adjoint_method='adjoint_reversible_heun', dt=float(case['dt']), adjoint_adaptive=True,
+                                 adjoint_rtol=float(case['rtol']), adjoint_atol=float(case['atol']),
+                                 dt_min=float(case['dt_min']))
+        (ys * torch.from_numpy(case['weights']).to(dev)).sum().backward()
+    assert any('does not save the time steps' in str(w.message) for w in caught)
+    np.testing.assert_allclose(ys.detach().cpu().numpy(), case['ys'], rtol=1e-11, atol=1e-12)
+    np.testing.assert_allclose(y0.grad.cpu().numpy(), case['grad_y0'], rtol=1e-8, atol=1e-10)
+    for n, p in sde.named_parameters():
+        np.testing.assert_allclose(p.grad.cpu().numpy(), case['grad.' + n], rtol=1e-8, atol=1e-10, err_msg=n)

@@ -332,3 +332,18 @@ def test_double_backward_flows_through(dry, kind, sde_type, method, adjoint_meth
     assert first[0].requires_grad
     second = torch.autograd.grad(sum((g ** 2).sum() for g in first), [y0] + params, allow_unused=True)
     assert second[0] is not None and second[0].shape == y0.shape
+
+
+def test_adjoint_adaptive_reversible_pair_flows_through(dry):
+    """adjoint_adaptive=True on the reversible pair: warns like the reference and runs the adaptive backward sweep."""
+    import warnings as _w
+    sde, y0, bm = _setup('general', 'stratonovich', 'none')
+    y0 = y0.clone().requires_grad_()
+    with _w.catch_warnings(record=True) as caught:
+        _w.simplefilter('always')
+        ys = tsde.sdeint_adjoint(sde, y0, [0.0, 0.125, 0.25], bm=bm, method='reversible_heun', dt=DT,
+                                 adjoint_adaptive=True, adjoint_rtol=1e-1, adjoint_atol=1e-1)
+        ys.sum().backward()
+    assert any('does not save the time steps' in str(w.message) for w in caught)
+    assert y0.grad is not None and all(p.grad is not None for p in sde.parameters())
+    assert dry.calls.get('tsde_adaptive_error_sumsq', 0) > 0

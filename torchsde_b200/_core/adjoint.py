@@ -20,6 +20,7 @@ _brownian/derived.py:27-30).
 Not implemented yet (SURVEY §8(f) "next"): the generic `AdjointSDE` path for
 euler/milstein/midpoint adjoints, double backward, adaptive adjoint stepping.
 """
+import ctypes
 import warnings
 
 import torch
@@ -188,6 +189,108 @@ class _BackwardEngine(base_solver.BaseSDESolver):
     def run(self, ys, ts, grad_ys, extras, grad_extras):
         self.plan(ys, ts)
         return self.sweep(ys, grad_ys, extras, grad_extras)
+
+    # ---- adaptive backward sweep (adjoint_adaptive=True) ------------------------------------------------------
+    # The reference warns that the reversible pair "does not save the time steps used" and then simply runs the
+    # adjoint solver's `integrate` with adaptive=True on every output interval (adjoint.py:245-249, 97-113;
+    # base_solver.py:117-142): one full step against two half steps of AdjointReversibleHeun.step, the error taken
+    # over the whole augmented state (y, adj_y, adj_f, adj_g, adj_z, adj_params), the solver state (f, g, z) carried
+    # along.  Same here: kernels A / B per trial step, increments queried at the data-dependent times through
+    # ReverseBrownian (memory source), one device->host scalar per proposal.
+    def _bstep(self, ta, tb, st, params):
+        """One AdjointReversibleHeun.step from reversed time ta to tb (0-d CPU tensors).  `st` = (y, z0, f0, g0, adj_y,
+        adj_f, adj_g, adj_z, adj_params); returns the new state without modifying `st`."""
+        lib = _cabi.lib()
+        y, z0, f0, g0, adj_y, adj_f, adj_g, adj_z, adj_params = st
+        h = tb - ta
+        dt, half_dt = float(h), float(0.5 * h)
+        w = _contig(self.bm(float(ta), float(tb)))
+        nz = self._feed.from_tensors(w.reshape(self.bm_rows, self.m))
+        t_fwd0 = (-ta).to(self.device)
+        t_fwd1 = (-tb).to(self.device)
+        z1, adj_f_mid, adj_g_mid = torch.empty_like(y), torch.empty_like(adj_f), torch.empty_like(adj_g)
+        _check(lib.tsde_adjoint_reversible_heun_a(
+            self._L, nz, _p(y), _p(z0), _p(f0), _p(g0), _p(adj_y), _p(adj_f), _p(adj_g), dt, half_dt, _p(z1),
+            _p(adj_f_mid), _p(adj_g_mid)), "tsde_adjoint_reversible_heun_a")
+        with torch.enable_grad():
+            z0r = z0.detach().requires_grad_()
+            re_f0, re_g0 = self.sde.f_and_g(t_fwd0, z0r)
+            pairs = [(o, go.view_as(o)) for o, go in ((re_f0, adj_f_mid), (re_g0, adj_g_mid)) if o.requires_grad]
+            if pairs:
+                vjps = torch.autograd.grad([o for o, _ in pairs], [z0r] + list(params), [g for _, g in pairs],
+                                           allow_unused=True)
+            else:
+                vjps = [None] * (1 + len(params))
+        vjp_z = _contig(vjps[0]) if vjps[0] is not None else torch.zeros_like(z0)
+        new_params = [ap if v is None else ap + v for ap, v in zip(adj_params, vjps[1:])]
+        f1, g1 = self.sde.f_and_g(t_fwd1, z1)
+        f1, g1 = _contig(f1), _contig(g1)
+        y1, adj_y1, adj_z1 = torch.empty_like(y), torch.empty_like(adj_y), torch.empty_like(adj_z)
+        adj_f1, adj_g1 = torch.empty_like(adj_f), torch.empty_like(adj_g)
+        _check(lib.tsde_adjoint_reversible_heun_b(
+            self._L, nz, _p(y), _p(f0), _p(f1), _p(g0), _p(g1), _p(adj_y), _p(adj_z), _p(vjp_z), dt, half_dt,
+            _p(y1), _p(adj_y1), _p(adj_z1), _p(adj_f1), _p(adj_g1)), "tsde_adjoint_reversible_heun_b")
+        return (y1, z1, f1, g1, adj_y1, adj_f1, adj_g1, adj_z1, new_params)
+
+    def _aug_error(self, a, b, rtol, atol):
+        """compute_error (adaptive_stepping.py:42-76) over the augmented state: RMS over ALL elements of the flat
+        vector the reference integrates."""
+        eps = 1e-7
+        lib = _cabi.lib()
+        parts = [(a[0], b[0])] + [(a[k], b[k]) for k in (4, 5, 6, 7)] + list(zip(a[8], b[8]))
+        if self._err_buf is None or self._err_buf.numel() < 1024 + len(parts):
+            self._err_buf = torch.zeros(1024 + len(parts), dtype=torch.float64, device=self.device)
+        buf = self._err_buf
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        total = 0
+        for k, (x, y) in enumerate(parts):
+            x, y = _contig(x), _contig(y)
+            n = x.numel()
+            total += n
+            L = _cabi.make_launch(self.dtype, _cabi.NOISE_DIAGONAL, 1, n, n, stream)
+            _check(lib.tsde_adaptive_error_sumsq(ctypes.byref(L), _p(x), _p(y), float(rtol), float(atol),
+                                                 eps, buf[len(parts):].data_ptr(), buf[k:].data_ptr()),
+                   "tsde_adaptive_error_sumsq")
+        err = (float(buf[:len(parts)].sum().item()) / total) ** 0.5
+        assert err == err, ('Found nans in the error estimate. Try increasing the tolerance or regularizing '
+                            'the dynamics.')
+        return max(err, eps)
+
+    def run_adaptive(self, ys, ts, grad_ys, extras, grad_extras, rtol, atol, dt_min):
+        y_last = _contig(ys[-1])
+        self._prepare(y_last)
+        self._refresh_stream()
+        self._feed = base_solver.NoiseFeed(self, self.bm, None)
+        self._err_buf = None
+        T = ts.numel()
+        neg = (-ts).detach().to('cpu')
+        dt0 = self.dt.detach().to('cpu') if torch.is_tensor(self.dt) else self.dt
+        f0, g0, z0 = (_contig(x.detach()) for x in extras)
+        adj_f, adj_g, adj_z = (_contig(x).clone() for x in grad_extras)
+        st = (y_last, z0, f0, g0, _contig(grad_ys[-1]).clone(), adj_f, adj_g, adj_z,
+              [torch.zeros_like(p) for p in self.params])
+        params = self.params
+        for i in range(T - 1, 0, -1):
+            curr_t, end_t = neg[i], neg[i - 1]
+            step_size, prev_error_ratio = dt0, None                 # (every interval is a fresh `integrate` call)
+            while curr_t < end_t:
+                next_t = min(curr_t + step_size, end_t)
+                full = self._bstep(curr_t, next_t, st, params)
+                mid_t = 0.5 * (curr_t + next_t)
+                half = self._bstep(curr_t, mid_t, st, params)
+                two = self._bstep(mid_t, next_t, half, params)
+                error_estimate = self._aug_error(full, two, rtol, atol)
+                step_size, prev_error_ratio = self._update_step_size(
+                    error_estimate=error_estimate, prev_step_size=step_size, prev_error_ratio=prev_error_ratio)
+                if step_size < dt_min:
+                    warnings.warn("Hitting minimum allowed step size in adaptive time-stepping.")
+                    step_size = dt_min
+                    prev_error_ratio = None
+                if error_estimate <= 1 or step_size <= dt_min:
+                    curr_t, st = next_t, two
+            # adjoint.py:114-116 (the interval ends exactly on -ts[i-1]: interpolation is the identity)
+            st = (_contig(ys[i - 1]), st[1], st[2], st[3], st[4] + grad_ys[i - 1]) + st[5:]
+        return st[4], (st[5], st[6], st[7]), st[8]
 
 
 _BWD_PLANS = __import__('weakref').WeakKeyDictionary()
@@ -358,7 +461,7 @@ class _SdeintAdjointMethod(torch.autograd.Function):
         ys, extras_out = sdeint_mod._integrate(solver, y0.detach(), ts, extras, options)
         ctx.bwd_plan = None
         if adjoint_options.get('cuda_graph', False) and isinstance(bm, BrownianInterval) \
-                and adjoint_options_reversible(adjoint_options):
+                and adjoint_options_reversible(adjoint_options) and adjoint_options.get('_adaptive') is None:
             engine = _BackwardEngine(sde, ReverseBrownian(bm), dt, params)
             ctx.bwd_plan = _backward_plan(engine, ys, ts, extras_out)
         # (y0 and the initial solver state are saved as well: the differentiable backward of the reversible pair
@@ -395,7 +498,11 @@ class _SdeintAdjointMethod(torch.autograd.Function):
                 ctx.sde, ctx.bm, ctx.dt, ts, y0_in, extras_in, list(params), grad_ys, grad_extras)
             return (None, None, None, None, None, None, None, None, adj_y, *adj_extras, *adj_params)
         with torch.no_grad():
-            if ctx.bwd_plan is not None:
+            if ctx.adjoint_options.get('_adaptive') is not None:
+                engine = _BackwardEngine(ctx.sde, ReverseBrownian(ctx.bm), ctx.dt, params)
+                adj_y, adj_extras, adj_params = engine.run_adaptive(ys, ts, grad_ys, extras, grad_extras,
+                                                                    **ctx.adjoint_options['_adaptive'])
+            elif ctx.bwd_plan is not None:
                 adj_y, adj_extras, adj_params = _replay_backward(ctx.bwd_plan, ctx.bm, ys, grad_ys, extras,
                                                                  grad_extras)
             else:
@@ -454,8 +561,9 @@ def sdeint_adjoint(sde, y0, ts, bm=None, method=None, adjoint_method=None, dt=1e
     if adjoint_method == METHODS.adjoint_reversible_heun and not reversible:
         raise ValueError(f"adjoint_method={repr(adjoint_method)} requires method={repr(METHODS.reversible_heun)}.")
     if reversible and adjoint_adaptive:
-        raise NotImplementedError("torchsde_b200: adjoint_adaptive is not supported for the reversible pair (it "
-                                  "does not record its step sizes; reference warning adjoint.py:246-249).")
+        # (the reference has already warned above that this "may not be perfectly accurate", adjoint.py:245-249, and
+        # then runs the adjoint solver adaptively; so does the backward engine, see _BackwardEngine.run_adaptive)
+        adjoint_options['_adaptive'] = dict(rtol=adjoint_rtol, atol=adjoint_atol, dt_min=dt_min)
     if not reversible:
         # generic AdjointSDE path: remember the adjoint solver's configuration for backward()
         adjoint_options['_cfg'] = dict(adjoint_method=adjoint_method, adjoint_adaptive=adjoint_adaptive,
