@@ -724,15 +724,25 @@ def main():
     if args.impl == 'reference':
         run_reference(args, w, rank, world)
         return
-    if world > 1:
+    if os.environ.get('TSDE_BENCH_NO_PG') and world > 1:
+        # bisecting aid (profiles/r02_multi_gpu_bisect.sh): N ranks under torchrun but NO process group — every rank
+        # behaves like an independent single-GPU run on its own device and prints its own line
+        world, rank = 1, 0
+    group = world > 1 or bool(os.environ.get('TSDE_FORCE_PG'))  # (TSDE_FORCE_PG: bisecting aid, a 1-rank NCCL group)
+    if group:
         import torch.distributed as dist
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        os.environ.setdefault('MASTER_PORT', '29512')
+        os.environ.setdefault('RANK', '0')
+        os.environ.setdefault('WORLD_SIZE', '1')
         torch.cuda.set_device(local_rank)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        if world == 1:
+            dist.barrier()
     try:
         run_ours(args, w, rank, world, local_rank)
     finally:
-        if world > 1:
+        if group:
             import torch.distributed as dist
             dist.destroy_process_group()
 

@@ -72,14 +72,17 @@ def test_tma_path_bit_identical(case, materialise, dtype, monkeypatch):
 
 
 def test_default_routing(monkeypatch):
-    """Without TSDE_GEN_TMA: m = 64 goes to the TMA-staged kernel once the batch fills the pipeline, m = 16 never."""
+    """Without TSDE_GEN_TMA (r02 routing): once the batch fills the pipeline m = 64 goes to the TMA-staged kernel, and so
+    does m = 16 for tableaus with a single g operand (Euler); two-operand tableaus (Heun) at m = 16 and small batches stay
+    on the per-thread-load kernel."""
     import ctypes
     from torchsde_b200 import _cabi
     monkeypatch.delenv('TSDE_GEN_TMA', raising=False)
     dev = torch.device('cuda')
     lib = _cabi.lib()
     key = torch.tensor([7], dtype=torch.int64, device=dev)
-    for (B, D, M), expect_tma in (((65536, 32, 64), True), ((256, 32, 64), False), ((65536, 32, 16), False)):
+    for (B, D, M), expect_tma in (((65536, 32, 64), True), ((256, 32, 64), False), ((65536, 32, 16), True),
+                                  ((256, 32, 16), False)):
         L = _cabi.make_launch(torch.float32, _cabi.NOISE_GENERAL, B, D, M)
         nz = _cabi.Noise()
         nz.source, nz.key, nz.cell_id, nz.n_cells, nz.h, nz.h_total = _cabi.SRC_COUNTER, key.data_ptr(), 5, 1, 0.01, 0.01
@@ -98,6 +101,18 @@ def test_default_routing(monkeypatch):
                 assert (lib.tsde_kernel_launches(1) > before) == expect_tma, (B, D, M)
             outs.append(o)
         assert torch.equal(outs[0], outs[1])
+    # two g operands at m = 16: per-thread-load kernel by default
+    B, D, M = 65536, 32, 16
+    L = _cabi.make_launch(torch.float32, _cabi.NOISE_GENERAL, B, D, M)
+    nz = _cabi.Noise()
+    nz.source, nz.key, nz.cell_id, nz.n_cells, nz.h, nz.h_total = _cabi.SRC_COUNTER, key.data_ptr(), 5, 1, 0.01, 0.01
+    e = [torch.rand(B, D, device=dev) for _ in range(4)]
+    g2 = [torch.rand(B, D, M, device=dev) for _ in range(2)]
+    monkeypatch.delenv('TSDE_GEN_TMA', raising=False)
+    before = lib.tsde_kernel_launches(1)
+    _cabi.check(lib.tsde_step_heun(ctypes.byref(L), ctypes.byref(nz), e[0].data_ptr(), e[1].data_ptr(), e[2].data_ptr(),
+                                   g2[0].data_ptr(), g2[1].data_ptr(), 0.01, e[3].data_ptr()), 'tsde_step_heun')
+    assert lib.tsde_kernel_launches(1) == before
 
 
 def test_tma_path_in_cuda_graph(monkeypatch):

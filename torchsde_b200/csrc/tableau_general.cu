@@ -306,13 +306,11 @@ gen_cta_kernel(const GenP<Op::NE, Op::NG, Op::NO> p, const NoiseP<T> nz, const O
 // same chunk -> lane mapping and summation order as `gen_cta_kernel` (so both paths are
 // bit-identical), and hand the stage back through an `empty` barrier (one arrive per warp).  There
 // is no CTA-wide barrier in the steady state.
-// Consumer variant.  0 (default, the one measured in profiles/r01_gen_tma_ab.log): lane-per-chunk with the
-// m/4-lane shuffle tree.  1: two-phase consumer without shuffles (lane-per-chunk partial dot products to a
-// shared scratch array, then lane-per-output pairwise tree + coalesced epilogue; ~3x fewer instructions
-// per chunk in SASS) — verified bit-identical on the GPU (tests/test_gpu_general_tma.py), not yet timed.
-#ifndef TSDE_TMA_TWO_PHASE
-#define TSDE_TMA_TWO_PHASE 0
-#endif
+// Consumer: two phases without shuffles (lane-per-chunk partial dot products to a shared scratch array, then
+// lane-per-output pairwise tree + coalesced epilogue).  It replaced the r01 lane-per-chunk consumer with an m/4-lane
+// shuffle tree after the A/B of r02 (profiles/r02_two_phase_ab.log, us per launch shuffle-tree -> two-phase, same box,
+// bit-identical outputs): Euler B=65536 d=64 m=16 54.5 -> 53.0 (91.6 % of the HBM peak; per-thread-load kernel 55.6),
+// Heun 94.3 -> 92.6, Euler d=32 m=64 91.7 -> 87.9 (97.4 %; per-thread-load kernel 110.9).
 
 constexpr int kTmaThreads = 256;
 constexpr int kTmaStages = 4;
@@ -486,7 +484,6 @@ gen_tma_kernel(const GenP<Op::NE, Op::NG, Op::NO> p, const NoiseP<T> nz, const O
     return;
   }
 
-#if TSDE_TMA_TWO_PHASE
   // ---------------- consumer warps: contract out of shared memory, combine, store ----------------------
   // Two phases per tile, both with consecutive lanes on consecutive shared-memory words (conflict-free):
   //   1. lane-per-chunk: chunk c (4 consecutive elements of the tile, (row, d) slot c >> MQ_SHIFT, Brownian
@@ -588,101 +585,17 @@ gen_tma_kernel(const GenP<Op::NE, Op::NG, Op::NO> p, const NoiseP<T> nz, const O
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);  // this warp no longer reads stage s
   }
-#else
-  // ---------------- consumer warps: contract out of shared memory, combine, store ----------------------
-  // Chunk c (4 consecutive elements of the tile, c = pass * 256 + tid) belongs to (row, d) slot c >> MQ_SHIFT
-  // and to row slot >> d_shift of the tile: no divisions, no per-chunk bookkeeping.  Shared memory is
-  // addressed with 32-bit shared-window addresses.
-  asm volatile("griddepcontrol.wait;" ::: "memory");  // the predecessor's reads of our outputs are complete
-  const int mc = tid & (mq - 1);
-  const uint32_t stage0_addr = smem_u32(stages);
-  const uint32_t g_lane_off = (uint32_t)tid * 4u * (uint32_t)sizeof(T);
-  for (int it = 0; it < n_my; ++it) {
-    const int s = it % kTmaStages;
-    const int64_t t = t_begin + it;
-    const int nrows = rows_of(t);
-    const int total = (nrows << d_shift) << mq_shift;   // chunks in this tile
-    const int64_t slot0 = (t * rs) << d_shift;          // first (row, d) slot of the tile
-    const uint32_t sp = stage0_addr + (uint32_t)s * tp.stage_stride;
-    const uint32_t e_addr = sp + NG * tp.g_stride;
-    const uint32_t w_addr = sp + w_off + (uint32_t)(4 * mc) * (uint32_t)sizeof(T);
-    const uint32_t u_addr = w_addr + tp.w_stride;
-    mbar_wait(&full[s], (uint32_t)((it / kTmaStages) & 1));
-    for (int base = 0; base < total; base += kTmaThreads * kTmaUnroll) {  // warp-uniform trip count
-      T gv[kTmaUnroll][NG][4];
-      T ev[kTmaUnroll][NE > 0 ? NE : 1];
-      bool valid[kTmaUnroll];
-#pragma unroll
-      for (int un = 0; un < kTmaUnroll; ++un) {
-        const int c = base + un * kTmaThreads + tid;
-        valid[un] = c < total;
-        const uint32_t goff = (uint32_t)(base + un * kTmaThreads) * 4u * (uint32_t)sizeof(T) + g_lane_off;
-#pragma unroll
-        for (int i = 0; i < NG; ++i) {
-          if (valid[un]) {
-            lds4(sp + (uint32_t)i * tp.g_stride + goff, gv[un][i]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) gv[un][i][j] = T(0);
-          }
-        }
-        if (valid[un] && mc == 0) {
-          const uint32_t slot = (uint32_t)c >> mq_shift;
-#pragma unroll
-          for (int i = 0; i < NE; ++i) ev[un][i] = lds1<T>(e_addr + (uint32_t)i * tp.e_stride + slot * (uint32_t)sizeof(T));
-        }
-      }
-#pragma unroll
-      for (int un = 0; un < kTmaUnroll; ++un) {
-        const int c = base + un * kTmaThreads + tid;
-        const uint32_t slot = (uint32_t)c >> mq_shift;
-        const uint32_t rsel = valid[un] ? (slot >> d_shift) : 0u;
-        T part[NP];
-#pragma unroll
-        for (int k = 0; k < NP; ++k) part[k] = T(0);
-        T w4[4], u4[4];
-        lds4(w_addr + rsel * (uint32_t)m * (uint32_t)sizeof(T), w4);
-        if (Op::WANT_U) lds4(u_addr + rsel * (uint32_t)m * (uint32_t)sizeof(T), u4);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          T gj[NG];
-#pragma unroll
-          for (int i = 0; i < NG; ++i) gj[i] = gv[un][i][j];
-#pragma unroll
-          for (int k = 0; k < NP; ++k)
-            part[k] = fma(op.gval(k, gj), op.weight(k, w4[j], Op::WANT_U ? u4[j] : T(0)), part[k]);
-        }
-#pragma unroll
-        for (int off = 1; off < mq; off <<= 1) {
-#pragma unroll
-          for (int k = 0; k < NP; ++k) part[k] = part[k] + __shfl_xor_sync(0xffffffffu, part[k], off);
-        }
-        if (valid[un] && mc == 0) {
-          T e[NE > 0 ? NE : 1], o[NO];
-#pragma unroll
-          for (int i = 0; i < NE; ++i) e[i] = ev[un][i];
-          op.combine(e, part, o);
-#pragma unroll
-          for (int i = 0; i < NO; ++i) reinterpret_cast<T*>(p.o[i])[slot0 + slot] = o[i];
-        }
-      }
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[s]);  // this warp no longer reads stage s
-  }
-#endif
 }
 
-// Which launches take the TMA-staged kernel (TSDE_GEN_TMA):
-//   unset  m = 64 only, when the batch fills the pipeline — the one regime where it measurably beats the
-//          per-thread-load kernel (B=65536, d=32, m=64: 92 us vs 111 us, 93 % vs 77 % of the HBM peak; for m = 16
-//          the two tie at 87 % for one g operand and the per-thread-load kernel wins 100 % vs 97 % for two;
-//          profiles/r01_gen_tma_ab.log);
+// Which launches take the TMA-staged kernel (TSDE_GEN_TMA), from the r02 A/B (profiles/r02_two_phase_ab.log):
+//   unset  when the batch fills the pipeline:  m = 64 always (97 % vs 77 % of the HBM peak for the per-thread-load
+//          kernel);  m = 16 for tableaus with ONE g operand (91.6 % vs 87.2 %) — with two g operands the
+//          per-thread-load kernel already streams at 100 % and stays;  m = 8, 32: per-thread-load kernel (not measured);
 //   0      never;   1  every eligible shape when the batch fills the pipeline;   2  every eligible shape.
 // Both kernels are bit-identical (tests/test_gpu_general_tma.py), so the choice never changes results.
-inline int gen_tma_mode(int64_t mq) {
+inline int gen_tma_mode(int64_t mq, int n_g_operands) {
   const char* e = getenv("TSDE_GEN_TMA");
-  if (!e) return mq == 16 ? 1 : 0;
+  if (!e) return (mq == 16 || (mq == 4 && n_g_operands == 1)) ? 1 : 0;
   if (e[0] == '0') return 0;
   if (e[0] == '2' || e[0] == 'f') return 2;
   return 1;
@@ -745,7 +658,7 @@ static int launch_gen_tma(const tsde_launch* L, const tsde_noise* nz, GenP<Op::N
   tp.n_tiles = (L->rows + rs - 1) / rs;
   tp.scratch_np_stride = (uint32_t)up128((size_t)rs * L->d * mq * sizeof(T));
   tp.scratch_stride = (uint32_t)(Op::NP * tp.scratch_np_stride);
-  const size_t smem = 128 + (size_t)kTmaStages * tp.stage_stride + (TSDE_TMA_TWO_PHASE ? 2 * (size_t)tp.scratch_stride : 0);
+  const size_t smem = 128 + (size_t)kTmaStages * tp.stage_stride + 2 * (size_t)tp.scratch_stride;
   if (smem > 200 * 1024) return kTmaNotEligible;
   p.rb = (int32_t)rs;
   auto go = [&](auto kernel) -> int {
@@ -804,7 +717,7 @@ static int launch_gen(const tsde_launch* L, const tsde_noise* nz,
   if (L->rows + nz->row_offset > 0xFFFFFFFFll) return TSDE_EINVAL;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(L->stream);
   if (vec) {
-    if (int mode = p.gbcast ? 0 : gen_tma_mode(mq)) {  // (a broadcast g has no tile stream to stage)
+    if (int mode = p.gbcast ? 0 : gen_tma_mode(mq, Op::NG)) {  // (a broadcast g has no tile stream to stage)
       int rc = launch_gen_tma<T, Op>(L, nz, p, np, op, mode, st);
       if (rc != kTmaNotEligible) return rc;
     }
