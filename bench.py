@@ -682,7 +682,7 @@ def run_secondary(rank, world, dev):
     torch.cuda.empty_cache()
     # ---- cfg5: BrownianInterval sweeps, 64 sequential dt-spaced queries ----
     M, nq, h = 16, 64, 2.0 ** -6
-    for levy, logb in (('none', 20), ('space-time', 20), ('foster', 17)):
+    for levy, logb in (('none', 20), ('space-time', 20), ('foster', 17), ('foster', 19)):
         Bq = 1 << logb
 
         def sweep(i, levy=levy, Bq=Bq):
@@ -695,7 +695,7 @@ def run_secondary(rank, world, dev):
         el, _ = _timed(sweep, 2, 3, dev, world)
         written = {'none': M * 4, 'space-time': 2 * M * 4, 'foster': (2 * M + M * M) * 4}[levy]
         v = world * Bq * nq / el
-        res[f'cfg5_brownian_{levy}'] = {"value": v, "unit": "row-queries/s", "ms_per_sweep": el * 1e3,
+        res[f'cfg5_brownian_{levy}' + ('' if (levy, logb) != ('foster', 19) else '_b2e19')] = {"value": v, "unit": "row-queries/s", "ms_per_sweep": el * 1e3,
                                         "config": {"batch_per_gpu": Bq, "channels": M, "queries": nq, "levy": levy},
                                         "written_GBps_per_gpu": v / world * written / 1e9,
                                         "write_roofline_frac": v / world * written / 1e9 / peak}
@@ -706,7 +706,7 @@ def run_secondary(rank, world, dev):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))

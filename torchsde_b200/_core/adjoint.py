@@ -418,34 +418,66 @@ def _generic_backward(sde, bm, dt, ys, ts, grad_ys, params, cfg, differentiable=
     return parts[1], parts[2:]
 
 
-def _reversible_backward_differentiable(sde, bm, dt, ts, y0, extras0, params, grad_ys, grad_extras):
+def _recomputed_solve(sde, bm, dt, ts, y0, extras0):
+    """Reversible-Heun forward solve with every tableau launch recorded as an autograd node."""
+    solver = methods.ReversibleHeun(sde=sde, bm=bm, dt=dt, adaptive=False, rtol=None, atol=None, dt_min=None, options={})
+    solver._autograd = True
+    ys, extras = solver.integrate(y0, ts, tuple(extras0))
+    return [ys, *extras]
+
+
+class _ReversibleVJP(torch.autograd.Function):
     """Differentiable backward pass of the reversible pair, for double backward (create_graph=True).
 
     The reference cannot do this at all (its re-entered Function finds no saved solver state and
     AdjointReversibleHeun.init_extra_solver_state raises, reversible_heun.py:93-96).  Reversible Heun's adjoint IS the
-    exact gradient of the discrete forward solve, so a differentiable version of it is obtained by re-running the
-    forward solve from the Function's saved INPUTS (y0, the initial solver state, the parameters) with every tableau
-    launch recorded as an autograd node, and taking the vector-Jacobian product with create_graph=True.  (Working
-    from the saved inputs rather than from the saved outputs matters: the outputs' history passes through this very
-    Function, and differentiating through it inside its own backward would recurse.)  Memory O(T) like backprop
-    through the solver; first-order backward passes never come here."""
-    with torch.enable_grad():
-        y0_in = y0 if y0.requires_grad else y0.detach().requires_grad_()
-        extras_in = [e if e.requires_grad else e.detach().requires_grad_() for e in extras0]
-        solver = methods.ReversibleHeun(sde=sde, bm=bm, dt=dt, adaptive=False, rtol=None, atol=None, dt_min=None,
-                                        options={})
-        solver._autograd = True
-        ys_re, extras_re = solver.integrate(y0_in, ts, tuple(extras_in))
-        outs, gouts = [], []
-        for o, go in zip([ys_re, *extras_re], [grad_ys, *grad_extras]):
-            if o.requires_grad:
-                outs.append(o)
-                gouts.append(go)
-        inputs = [y0_in, *extras_in, *params]
-        grads = torch.autograd.grad(outs, inputs, gouts, create_graph=True, allow_unused=True)
-    grads = [torch.zeros_like(x) if g is None else g for g, x in zip(grads, inputs)]
-    n = len(extras_in)
-    return grads[0], tuple(grads[1:1 + n]), grads[1 + n:]
+    exact gradient of the discrete forward solve, so the same vector-Jacobian product is obtained by re-running the
+    forward solve from the outer Function's saved INPUTS (y0, initial solver state, parameters) with autograd nodes.
+    It is wrapped in a Function of its own so that it returns PARTIAL derivatives w.r.t. each input (the initial solver
+    state (f0, g0, z0) is itself a function of y0 and the parameters upstream; differentiating through that history
+    here would count those paths twice) while staying differentiable: `backward` rebuilds the solve on detached leaves
+    and differentiates the first-order gradients (second order; no third).  Memory O(T) like backprop through the
+    solver; first-order backward passes never come here."""
+
+    @staticmethod
+    def forward(ctx, sde, bm, dt, ts, n_extras, *tensors):
+        ctx.sde, ctx.bm, ctx.dt, ctx.n_extras = sde, bm, dt, n_extras
+        ctx.save_for_backward(ts, *tensors)
+        gouts = tensors[:1 + n_extras]
+        with torch.enable_grad():
+            leaves = [t.detach().requires_grad_() for t in tensors[1 + n_extras:2 + 2 * n_extras]]
+            params = list(tensors[2 + 2 * n_extras:])
+            outs = _recomputed_solve(sde, bm, dt, ts, leaves[0], leaves[1:])
+            pairs = [(o, g) for o, g in zip(outs, gouts) if o.requires_grad]
+            grads = torch.autograd.grad([o for o, _ in pairs], leaves + params, [g for _, g in pairs], allow_unused=True)
+        return tuple(torch.zeros_like(x) if g is None else g.detach() for g, x in zip(grads, leaves + params))
+
+    @staticmethod
+    def backward(ctx, *gg):
+        ts, *tensors = ctx.saved_tensors
+        n = ctx.n_extras
+        with torch.enable_grad():
+            gouts = [t.detach().requires_grad_() for t in tensors[:1 + n]]
+            leaves = [t.detach().requires_grad_() for t in tensors[1 + n:2 + 2 * n]]
+            params = list(tensors[2 + 2 * n:])
+            outs = _recomputed_solve(ctx.sde, ctx.bm, ctx.dt, ts, leaves[0], leaves[1:])
+            pairs = [(o, g) for o, g in zip(outs, gouts) if o.requires_grad]
+            first = torch.autograd.grad([o for o, _ in pairs], leaves + params, [g for _, g in pairs], create_graph=True,
+                                        allow_unused=True)
+            sel = [(f, g) for f, g in zip(first, gg) if f is not None and f.requires_grad and g is not None]
+            inputs = gouts + leaves + params
+            if sel:
+                second = torch.autograd.grad([f for f, _ in sel], inputs, [g for _, g in sel], allow_unused=True)
+            else:
+                second = [None] * len(inputs)
+        return (None, None, None, None, None, *second)
+
+
+def _reversible_backward_differentiable(sde, bm, dt, ts, y0, extras0, params, grad_ys, grad_extras):
+    """Gradients w.r.t. (y0, initial solver state, parameters) as differentiable tensors: see _ReversibleVJP."""
+    n = len(extras0)
+    grads = _ReversibleVJP.apply(sde, bm, dt, ts, n, grad_ys, *grad_extras, y0, *extras0, *params)
+    return grads[0], tuple(grads[1:1 + n]), list(grads[1 + n:])
 
 
 class _SdeintAdjointMethod(torch.autograd.Function):

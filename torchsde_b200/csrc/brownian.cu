@@ -291,12 +291,17 @@ struct HToUOp {
 // one warp per row — lanes draw the row's pair normals (one Philox quad = 4 pairs per lane), form the upper
 // triangle, mirror it (A is antisymmetric, exactly: this translation unit is compiled without FMA contraction)
 // into a warp-private shared tile, and the warp stores the tile with fully coalesced 128-bit writes.
+// Foster's std needs one square root per pair: fp32 takes the SFU's (MUFU.SQRT, ~1 ulp; the IEEE-rounded `sqrtf`
+// is a ~10-instruction Newton sequence and the kernel is issue-bound), fp64 the correctly rounded one.
+__device__ __forceinline__ float levy_sqrt(float x) { return mufu_sqrt(x); }
+__device__ __forceinline__ double levy_sqrt(double x) { return sqrt(x); }
+
 template <typename T>
 __device__ __forceinline__ T levy_pair_value(T wi, T wj, T hi, T hj, T z, T tenth_h, T davie_std, int foster) {
   const T a = hi * wj - wi * hj;
   const T n = z * T(0.70710678118654752440);   // N_ij
   const T noise = n - (-n);                      // N_ij - N_ji
-  const T std_ = foster ? sqrt(tenth_h * ((tenth_h + hi * hi) + hj * hj)) : davie_std;
+  const T std_ = foster ? levy_sqrt(tenth_h * ((tenth_h + hi * hi) + hj * hj)) : davie_std;
   return a + std_ * noise;
 }
 
@@ -332,6 +337,16 @@ levy_tile_kernel(const void* keyp, int64_t row_offset, uint64_t a_id, int64_t ro
   const Key key = load_key(keyp);
   const int nq = (npairs + 3) >> 2;
   const int64_t row_stride = (int64_t)gridDim.x * warps;
+  // A lane's pairs do not depend on the row when one pass covers them (nq <= 32, i.e. m <= 16): look the indices up
+  // once — tile offsets of A_ij / A_ji and of the four W/H operands — instead of once per row.
+  const bool one_pass = nq <= 32;
+  int pi[4], pj[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int p = 4 * lane + k;
+    pi[k] = (one_pass && p < npairs) ? pairs_i[p] : -1;
+    pj[k] = (one_pass && p < npairs) ? pairs_j[p] : 0;
+  }
   for (int64_t row = (int64_t)blockIdx.x * warps + warp; row < rows; row += row_stride) {
     const uint32_t grow = (uint32_t)(row + row_offset);
     if (GEN) {
@@ -363,17 +378,33 @@ levy_tile_kernel(const void* keyp, int64_t row_offset, uint64_t a_id, int64_t ro
       }
       __syncwarp();
     }
-    for (int q = lane; q < nq; q += 32) {
-      T z[4];
-      normal4(key, a_id, STREAM_A, grow, (uint32_t)q, z);
+    if (one_pass) {
+      if (lane < nq) {
+        T z[4];
+        normal4(key, a_id, STREAM_A, grow, (uint32_t)lane, z);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int p = 4 * q + k;
-        if (p < npairs) {
-          const int i = pairs_i[p], j = pairs_j[p];
-          const T v = levy_pair_value(sW[i], sW[j], sH[i], sH[j], z[k], tenth_h, davie_std, foster);
-          sA[i * m + j] = v;
-          sA[j * m + i] = -v;
+        for (int k = 0; k < 4; ++k) {
+          if (pi[k] >= 0) {
+            const int i = pi[k], j = pj[k];
+            const T v = levy_pair_value(sW[i], sW[j], sH[i], sH[j], z[k], tenth_h, davie_std, foster);
+            sA[i * m + j] = v;
+            sA[j * m + i] = -v;
+          }
+        }
+      }
+    } else {
+      for (int q = lane; q < nq; q += 32) {
+        T z[4];
+        normal4(key, a_id, STREAM_A, grow, (uint32_t)q, z);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int p = 4 * q + k;
+          if (p < npairs) {
+            const int i = pairs_i[p], j = pairs_j[p];
+            const T v = levy_pair_value(sW[i], sW[j], sH[i], sH[j], z[k], tenth_h, davie_std, foster);
+            sA[i * m + j] = v;
+            sA[j * m + i] = -v;
+          }
         }
       }
     }
