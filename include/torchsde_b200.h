@@ -162,6 +162,16 @@ int tsde_brownian_cell_levy(const tsde_launch* L, const tsde_noise* nz, uint64_t
                             void* out_u, void* out_a);
 
 /*
+ * `logqp=True` (diagonal noise): the KL-integrand augmentation of SDELogqp.f_and_g_diagonal
+ * (base_sde.py:266-283, misc.py:66-68):  u = (f - h) / stable(g),  f_aug = [f, 0.5 sum_d u^2],  g_aug = [g, 0].
+ * f, g, h are (rows,d); f_aug, g_aug are (rows,d+1).  L: noise_type DIAGONAL, d = m = state channels WITHOUT the
+ * log-ratio channel.  (General noise solves a least-squares problem per row, `pinverse`: it stays in the host's
+ * linear algebra.)
+ */
+int tsde_logqp_augment(const tsde_launch* L, const void* f, const void* g, const void* h, double eps,
+                       void* f_aug, void* g_aug);
+
+/*
  * GA = g A for the log-ODE correction (base_sde.py:170,191: `ga = torch.bmm(g, a)` inside
  * dg_ga_jvp_column_sum_v1/_v2; used by methods/log_ode.py:39-56).  g is (rows,d,m), a is (rows,m,m) (the Levy
  * area of the step), out_t is (m, rows, d): column l of g A as a contiguous (rows,d) slab, which is what the

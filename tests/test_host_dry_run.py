@@ -191,6 +191,15 @@ def test_every_solver_entry_point_is_reached(dry):
     bm = tsde.BrownianInterval(0.0, 1.0, size=(4, 2), device='cpu', levy_area_approximation='davie')
     bm(0.0, 0.5, return_U=True, return_A=True)
     bm(0.25, 0.75, return_U=True, return_A=True)      # covers pieces of two nodes: increments and areas are merged
+    class Latent(torch.nn.Module):   # diagonal-noise logqp under no_grad: the fused KL-integrand launch
+        noise_type, sde_type = 'diagonal', 'ito'
+        f = staticmethod(lambda t, y: -y)
+        h = staticmethod(lambda t, y: -0.5 * y)
+        g = staticmethod(lambda t, y: 0.3 + 0.0 * y)
+    with torch.no_grad():
+        ys, logqp = tsde.sdeint(Latent(), torch.ones(4, 3), TS, method='euler', dt=DT, logqp=True,
+                                bm=tsde.BrownianInterval(0.0, TS[-1], size=(4, 4), dtype=torch.float32, device='cpu'))
+    assert ys.shape == (3, 4, 3) and logqp.shape == (2, 4)
     grid = tsde.BrownianInterval(0.0, 1.0, size=(4, 4), device='cpu', levy_area_approximation='foster', dt=0.25)
     w, u, a = grid(0.25, 0.5, return_U=True, return_A=True)   # one whole cell of the dt grid: the fused W/U/A launch
     assert w.shape == u.shape == (4, 4) and a.shape == (4, 4, 4)

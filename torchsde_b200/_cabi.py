@@ -55,6 +55,7 @@ SIGNATURES = {
     'tsde_brownian_levy_area': [_L, _P, ctypes.c_int64, ctypes.c_uint64, _P, _P, _D, _I, _P],
     'tsde_brownian_merge_area': [_L, _P, _P, _P, _P],
     'tsde_bmm_ga': [_L, _P, _P, _P],
+    'tsde_logqp_augment': [_L, _P, _P, _P, _D, _P, _P],
     'tsde_brownian_cell_levy': [_L, _N, ctypes.c_uint64, _I, _P, _P, _P],
     'tsde_step_euler': [_L, _N, _P, _P, _P, _D, _P],
     'tsde_milstein_vjp_seed': [_L, _N, _P, _D, _I, _P],

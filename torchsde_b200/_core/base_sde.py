@@ -145,9 +145,36 @@ class SDELogqp(BaseSDE):
     def f_and_g(self, t, y):
         state = y[:, :-1]
         base = self._base_sde
-        f, g = base.f(t, state), base.g(t, state)
-        rate = _kl_rate(f, g, base.h(t, state), self._diagonal)
+        f, g, h = base.f(t, state), base.g(t, state), base.h(t, state)
+        differentiated = torch.is_grad_enabled() and (f.requires_grad or g.requires_grad or h.requires_grad)
+        if self._diagonal and not differentiated and self._on_device(f):
+            return self._fused_augment(f, g, h)
+        rate = _kl_rate(f, g, h, self._diagonal)
         return torch.cat([f, rate], dim=1), self._pad_diffusion(g)
+
+    @staticmethod
+    def _on_device(t):
+        from .. import _cabi
+        try:
+            _cabi.require_cuda(t)
+            return True
+        except RuntimeError:
+            return False
+
+    @staticmethod
+    def _fused_augment(f, g, h, epsilon=1e-7):
+        """One kernel instead of ~10 ATen launches when nothing has to be differentiated (inference solves and the
+        no-grad forward pass of `sdeint_adjoint`; the vjp's of the backward pass go through the torch ops above)."""
+        import ctypes
+        from .. import _cabi
+        f, g, h = (x if x.is_contiguous() else x.contiguous() for x in (f, g, h))
+        rows, d = f.shape
+        f_aug = torch.empty((rows, d + 1), dtype=f.dtype, device=f.device)
+        g_aug = torch.empty_like(f_aug)
+        L = _cabi.make_launch(f.dtype, _cabi.NOISE_DIAGONAL, rows, d, d, device=f.device)
+        _cabi.check(_cabi.lib().tsde_logqp_augment(ctypes.byref(L), f.data_ptr(), g.data_ptr(), h.data_ptr(), epsilon,
+                                                   f_aug.data_ptr(), g_aug.data_ptr()), "tsde_logqp_augment")
+        return f_aug, g_aug
 
     def f(self, t, y):
         return self.f_and_g(t, y)[0]
