@@ -286,11 +286,11 @@ def run_reference(args, w, rank, world):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": common_config(args, w, world), "gpu_launches": 0}
     if ref is not None:
-        # size the per-step sample so that warmup + steps solves end within a few minutes (~150 s)
+        # size the per-step sample so that warmup + steps solves end within a few minutes (~100 s)
         threads, tried = best_reference_threads(ref, w)
         _, el = cpu_reference_run(ref, w, 2)
         per_step = max(el / 2, 1e-3)
-        budget = float(os.environ.get('TSDE_BENCH_REF_BUDGET_S', 150.0))
+        budget = float(os.environ.get('TSDE_BENCH_REF_BUDGET_S', 100.0))
         n_steps = int(max(2, min(w['T'], budget / (args.warmup + args.steps) / per_step)))
         vals = []
         for i in range(args.warmup + args.steps):
@@ -481,7 +481,7 @@ def run_ours(args, w, rank, world, local_rank):
     line = {
         "metric": METRIC, "value": value, "unit": "traj-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": common_config(args, w, world),
         "impl_details": {"cuda_graph": opts['cuda_graph'], "row_split": args.row_split,
                          "result": "plan-owned static series (options static_output=True): valid until the next solve",
@@ -714,10 +714,14 @@ def main():
     ap.add_argument('--no-secondary', action='store_true', help='skip the cfg3/cfg4/cfg5 block')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline sample')
     ap.add_argument('--row-split', type=int, default=1)
+    ap.add_argument('--strong', action='store_true',
+                    help='strong scaling: the workload batch is the GLOBAL batch, split over the ranks')
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
     if os.environ.get('TSDE_BENCH_B'):  # experiments only: override the batch size
         w['B'] = int(os.environ['TSDE_BENCH_B'])
+    if args.strong:
+        w['B'] = w['B'] // max(int(os.environ.get('WORLD_SIZE', '1')), 1)
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
