@@ -1,24 +1,27 @@
-"""`sdeint_adjoint` for the algebraically reversible pair reversible_heun / adjoint_reversible_heun.
+"""`sdeint_adjoint`: custom autograd node around the forward solve, with three backward engines.
 
 Reference: torchsde/_core/adjoint.py (`_SdeintAdjointMethod` :29-127, `sdeint_adjoint` :130-278,
-`_select_default_adjoint_method` :281-296) and methods/reversible_heun.py:76-144
-(`AdjointReversibleHeun.step`).
+`_select_default_adjoint_method` :281-296), methods/reversible_heun.py:76-144 (`AdjointReversibleHeun.step`) and
+_core/adjoint_sde.py (the augmented backward SDE).
 
-The reference packs (y, adj_y, adj_f, adj_g, adj_z, adj_params...) into one flat vector with a dummy
-batch dimension and re-enters `autograd.Function.apply` once per output interval, copying the whole
-augmented state through `flatten` / `flat_to_shape` on every step (adjoint.py:75-79,114-119;
-reversible_heun.py:142; adjoint_sde.py:104).  Here the augmented state stays in separate buffers,
-and one backward step is exactly
-    kernel A (reconstruct z1, first half of the adjoint bookkeeping)
-    user f_and_g at z0 + one torch.autograd.grad (the vjp)          <- user code, stays in torch
-    user f_and_g at z1
-    kernel B (reconstruct y1, second half of the bookkeeping)
-with the Brownian increment of the step regenerated from the Philox counter in both kernels
-(the same cells the forward pass consumed, addressed in reverse: `ReverseBrownian` semantics,
-_brownian/derived.py:27-30).
-
-Not implemented yet (SURVEY §8(f) "next"): the generic `AdjointSDE` path for
-euler/milstein/midpoint adjoints, double backward, adaptive adjoint stepping.
+* Reversible pair (method='reversible_heun', adjoint_method='adjoint_reversible_heun'): the reference packs
+  (y, adj_y, adj_f, adj_g, adj_z, adj_params...) into one flat vector with a dummy batch dimension and re-enters
+  `autograd.Function.apply` once per output interval, copying the whole augmented state through `flatten` /
+  `flat_to_shape` on every step (adjoint.py:75-79,114-119; reversible_heun.py:142; adjoint_sde.py:104).  Here the
+  augmented state stays in separate buffers, and one backward step is exactly
+      kernel A (reconstruct z1, first half of the adjoint bookkeeping)
+      user f_and_g at z0 + one torch.autograd.grad (the vjp)          <- user code, stays in torch
+      user f_and_g at z1
+      kernel B (reconstruct y1, second half of the bookkeeping)
+  with the Brownian increment of the step regenerated from the Philox counter in both kernels (the same cells the
+  forward pass consumed, addressed in reverse: `ReverseBrownian` semantics, _brownian/derived.py:27-30).  The sweep
+  can be captured as a CUDA graph (`adjoint_options={'cuda_graph': True}`); with `adjoint_adaptive=True` it runs the
+  reference's adaptive controller on the augmented state (`_BackwardEngine.run_adaptive`).
+* Every other pair: the generic `AdjointSDE` (adjoint_sde.py) integrated backwards by the ordinary solvers on the flat
+  augmented state (`_generic_backward`).
+* Double backward (create_graph=True): the generic path re-enters `_SdeintAdjointMethod.apply` per interval exactly
+  like the reference (adjoint.py:97-113); the reversible pair — which the reference cannot double-backward — goes
+  through `_ReversibleVJP`.
 """
 import ctypes
 import warnings
@@ -139,6 +142,13 @@ class _BackwardEngine(base_solver.BaseSDESolver):
         adj_params = [torch.zeros_like(p) for p in params]
         sde = self.sde
         k = 0
+        # The reference evaluates f_and_g twice per backward step: with autograd at (t0, z0) for the vjp (:119-129) and
+        # without at (t1, z1) for the reconstruction (:133) — and notes "it should be possible to make one fewer
+        # forward call by re-using the forward computation in the previous step" (:117-118).  It is: step k's z1 IS
+        # step k+1's z0 (same time, same tensor), so the evaluation at (t1, z1) is recorded by autograd and kept as
+        # `pending` for the next step's vjp.  Same numbers (the kernels are deterministic), one user forward
+        # evaluation per step instead of two.
+        pending = None
         for n, sched in enumerate(self.scheds):
             i = T - 1 - n
             for _ in range(sched.n_steps):
@@ -153,8 +163,11 @@ class _BackwardEngine(base_solver.BaseSDESolver):
                     L, self._feed.get(c), _p(y), _p(z0), _p(f0), _p(g0), _p(adj_y), _p(adj_f), _p(adj_g),
                     c.dt, half_dt, _p(z1), _p(adj_f_mid), _p(adj_g_mid)), "tsde_adjoint_reversible_heun_a")
                 with torch.enable_grad():
-                    z0r = z0.detach().requires_grad_()
-                    re_f0, re_g0 = sde.f_and_g(t_fwd0, z0r)
+                    if pending is None:
+                        z0r = z0.detach().requires_grad_()
+                        re_f0, re_g0 = sde.f_and_g(t_fwd0, z0r)
+                    else:
+                        z0r, re_f0, re_g0 = pending
                     outs, gouts = [], []
                     for o, go in ((re_f0, adj_f_mid), (re_g0, adj_g_mid)):
                         if o.requires_grad:
@@ -164,12 +177,15 @@ class _BackwardEngine(base_solver.BaseSDESolver):
                         vjps = torch.autograd.grad(outs, [z0r] + list(params), gouts, allow_unused=True)
                     else:
                         vjps = [None] * (1 + len(params))
+                    del re_f0, re_g0, outs
+                    z1r = z1.detach().requires_grad_()
+                    f1_graph, g1_graph = sde.f_and_g(t_fwd1, z1r)
+                    pending = (z1r, f1_graph, g1_graph)
                 vjp_z = vjps[0] if vjps[0] is not None else torch.zeros_like(z0)
                 for ap, v in zip(adj_params, vjps[1:]):
                     if v is not None:
                         ap.add_(v)
-                f1, g1 = sde.f_and_g(t_fwd1, z1)
-                f1, g1 = _contig(f1), _contig(g1)
+                f1, g1 = _contig(f1_graph.detach()), _contig(g1_graph.detach())
                 y1 = torch.empty_like(y)
                 adj_y1 = torch.empty_like(adj_y)
                 adj_z1 = torch.empty_like(adj_z)
