@@ -153,6 +153,23 @@ def device_guard(device):
     return torch.cuda.device(device)
 
 
+class nvtx_range:
+    """NVTX range around a host-side phase (solve, graph capture, replay, backward sweep) when TSDE_NVTX=1 — what
+    shows up as named spans on an Nsight Systems timeline (tracing).  Free when the variable is unset."""
+    _on = os.environ.get('TSDE_NVTX', '0') not in ('0', '')
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if self._on:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if self._on:
+            torch.cuda.nvtx.range_pop()
+
+
 def ptr(t):
     """Device pointer of a contiguous tensor (or NULL)."""
     if t is None:

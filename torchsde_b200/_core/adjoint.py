@@ -519,7 +519,7 @@ class _SdeintAdjointMethod(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_ys, *grad_extras):
-        with _cabi.device_guard(grad_ys.device):
+        with _cabi.device_guard(grad_ys.device), _cabi.nvtx_range('tsde: adjoint backward'):
             return _SdeintAdjointMethod._backward(ctx, grad_ys, *grad_extras)
 
     @staticmethod

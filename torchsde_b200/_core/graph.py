@@ -37,6 +37,7 @@ import torch
 
 from . import base_solver
 from . import schedule as schedule_lib
+from .._cabi import nvtx_range as _nvtx
 
 _PLANS = weakref.WeakKeyDictionary()
 MAX_PLANS_PER_SDE = 4  # every plan owns its output series (T x B x D): keep the cache small
@@ -137,7 +138,8 @@ def integrate_captured(solver, y0, ts, extra0, static_ok=False):
     plan = plans.get(key)
     if plan is None and key not in plans:
         try:
-            plan = _capture(solver, sched, binding, y0, ts, extra0)
+            with _nvtx('tsde: capture solve'):
+                plan = _capture(solver, sched, binding, y0, ts, extra0)
         except RuntimeError as e:
             # f / g did something a stream capture cannot record (a host sync or a host<->device copy — e.g.
             # `pinverse` in the general-noise KL rate of logqp=True, or `.item()` in user code).  Such SDEs run
@@ -156,7 +158,8 @@ def integrate_captured(solver, y0, ts, extra0, static_ok=False):
     plan.key.copy_(binding.interval.key_tensor())
     for dst, src in zip(plan.extra_in, extra0):
         dst.copy_(src)
-    plan.graph.replay()
+    with _nvtx('tsde: replay solve'):
+        plan.graph.replay()
     LAST_PLAN = plan
     return _hand_out(plan, solver, static_ok)
 

@@ -57,7 +57,8 @@ def sdeint(sde, y0, ts, bm=None, method=None, dt=1e-3, adaptive=False, rtol=1e-5
     solver = solver_fn(sde=sde, bm=bm, dt=dt, adaptive=adaptive, rtol=rtol, atol=atol, dt_min=dt_min,
                        options=options)
     _cabi.require_cuda(y0)
-    with _cabi.device_guard(y0.device):  # launches go to y0's device whatever the caller's current device is
+    with _cabi.device_guard(y0.device), _cabi.nvtx_range(f'tsde: sdeint {method}'):
+        # (launches go to y0's device whatever the caller's current device is)
         return _solve(sde, solver, y0, ts, adaptive, options, logqp, extra, extra_solver_state)
 
 
