@@ -1,0 +1,18 @@
+#!/bin/bash
+# r02 call 9: GPU suite on the final kernels; reference suite (xdist, default device = GPU); bench; ncu of levy/bmm; racecheck of everything but the TMA ring
+set -x
+mkdir -p gpurun_out
+( time python -m pytest tests -m gpu -q -p no:cacheprovider ) > gpurun_out/r02_gputests.log 2>&1
+tail -8 gpurun_out/r02_gputests.log
+( time REFSUITE_LOG=gpurun_out/r02_reference_suite_full.log timeout 1200 python tests/reference_suite.py ) > gpurun_out/r02_reference_suite.log 2>&1
+tail -3 gpurun_out/r02_reference_suite.log | cut -c1-1800
+python bench.py > gpurun_out/r02_bench_n1.json 2> gpurun_out/r02_bench_n1.err
+python -c "
+import json
+d=json.loads(open('gpurun_out/r02_bench_n1.json').read().strip().splitlines()[-1])
+print('full', d['ms_per_step'], d['roofline_whole_step']['frac'], d['e2e']['ms_per_step'], {k:round(v['avg_launch_us'],2) for k,v in d['kernels'].items()}, d['roofline']['traffic'])
+for k,v in d['secondary'].items(): print(k, v if isinstance(v,str) else {a:(round(b,4) if isinstance(b,float) else b) for a,b in v.items() if a in ('value','ms_per_solve','ms_per_step','ms_per_sweep','roofline_frac','write_roofline_frac')})
+"
+python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/r02_bench_reference.json 2> gpurun_out/r02_bench_reference.err; cut -c1-1200 gpurun_out/r02_bench_reference.json
+ncu --set full --import-source on --clock-control none --kernel-name-base demangled -k regex:'levy_tile|bmm_ga' -c 6 -o gpurun_out/r02c9_k python profiles/kernels_for_ncu.py > gpurun_out/r02c9_ncu.log 2>&1; tail -2 gpurun_out/r02c9_ncu.log
+du -sh gpurun_out

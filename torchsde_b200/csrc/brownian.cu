@@ -307,17 +307,9 @@ __device__ __forceinline__ T levy_pair_value(T wi, T wj, T hi, T hj, T z, T tent
 
 constexpr int kLevyWarps = 8;
 
-// pair index of (lo < hi) in row-major upper-triangular order
-__device__ __forceinline__ int levy_pair_index(int lo, int hi, int m) { return lo * m - ((lo * (lo + 1)) >> 1) + (hi - lo - 1); }
-
-// One warp per row.  Per row: (1) W and H of the row into warp-private shared memory (read, or — GEN — drawn from the
-// counter, in which case W and U = h (W/2 + H) are written out too: one launch answers a whole-cell query
-// bm(ta, tb, return_U=True, return_A=True), brownian_interval.py:589-687); (2) the row's pair normals, one Philox quad
-// = 4 pairs per lane, into shared memory with conflict-free 128-bit stores; (3) every lane forms the elements it OWNS
-// in the output row — groups of 4 consecutive A[i][j0..j0+3], so its stores are coalesced 128-bit writes straight
-// from registers: there is no (m x m) staging tile and no transposed shared-memory traffic (an earlier version that
-// mirrored the upper triangle into a shared tile spent its time in 16-way bank conflicts).  A_ji = -A_ij holds
-// exactly: both are formed from the same (lo, hi)-ordered expression (no FMA contraction in this translation unit).
+// GEN: the row's W and H are not read but drawn from the counter (primary cell `cell_id` of length h: W = sqrt(h) N_W,
+// H = sqrt(h/12) N_H, as counter_noise does), and W and U = h (W/2 + H) are written out as well: one launch answers a
+// whole-cell query bm(ta, tb, return_U=True, return_A=True) (brownian_interval.py:589-687).
 template <typename T, bool GEN>
 __global__ void __launch_bounds__(kLevyWarps * 32)
 levy_tile_kernel(const void* keyp, int64_t row_offset, uint64_t a_id, int64_t rows, int m, int npairs, int warps,
@@ -326,33 +318,38 @@ levy_tile_kernel(const void* keyp, int64_t row_offset, uint64_t a_id, int64_t ro
                  T* __restrict__ out_u) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int mm = m * m;
-  const int nq = (npairs + 3) >> 2;
-  const int per_warp = (4 * nq + 2 * m + 3) & ~3;          // floats per warp: Z (4 nq) | W (m) | H (m)
+  const int ld = m + 1;                                   // padded row stride of the shared tile: the mirrored stores
+                                                          // sA[j][i] of consecutive lanes then fall into different banks
+                                                          // (with stride m = 16 they were 16-way conflicts: measured
+                                                          // 71 us per 131072 x 16 x 16 query, LSU-bound)
+  const int tile = (m * ld + 2 * m + 3) & ~3;              // floats per warp: A tile | W | H (16-byte multiple)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (warp >= warps) return;
-  T* sZ = reinterpret_cast<T*>(smem_raw) + (size_t)warp * per_warp;
-  T* sW = sZ + 4 * nq;
+  unsigned char* pairs_i = smem_raw;                       // [npairs] row index of pair p
+  unsigned char* pairs_j = pairs_i + npairs;               // [npairs] column index
+  T* tiles = reinterpret_cast<T*>(smem_raw + (((size_t)2 * npairs + 15) & ~(size_t)15));
+  T* sA = tiles + (size_t)warp * tile;
+  T* sW = sA + m * ld;
   T* sH = sW + m;
+  // pair table (shared by the CTA) and the tile's zero diagonal (written once: rows never touch it)
+  for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    int p = i * m - (i * (i + 1)) / 2;                     // first pair of row i
+    for (int j = i + 1; j < m; ++j, ++p) { pairs_i[p] = (unsigned char)i; pairs_j[p] = (unsigned char)j; }
+  }
+  if (warp < warps) for (int i = lane; i < m; i += 32) sA[i * ld + i] = T(0);
+  __syncthreads();
+  if (warp >= warps) return;
   const Key key = load_key(keyp);
+  const int nq = (npairs + 3) >> 2;
   const int64_t row_stride = (int64_t)gridDim.x * warps;
-  const int ngroups = mm >> 2;                               // groups of 4 consecutive elements (vec path: m % 4 == 0)
-  // the groups a lane owns do not depend on the row: for up to two groups per lane (m <= 16) keep their indices
-  const bool cached = vec && ngroups <= 64;
-  int gi[2], gj0[2], gp[2][4];
+  // A lane's pairs do not depend on the row when one pass covers them (nq <= 32, i.e. m <= 16): look the indices up
+  // once — tile offsets of A_ij / A_ji and of the four W/H operands — instead of once per row.
+  const bool one_pass = nq <= 32;
+  int pi[4], pj[4];
 #pragma unroll
-  for (int t = 0; t < 2; ++t) {
-    const int e4 = lane + 32 * t;
-    gi[t] = -1;
-    gj0[t] = 0;
-    if (cached && e4 < ngroups) {
-      gi[t] = (4 * e4) / m;
-      gj0[t] = 4 * e4 - gi[t] * m;
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int i = gi[t], j = gj0[t] + k;
-      gp[t][k] = (i < 0 || i == j) ? -1 : levy_pair_index(i < j ? i : j, i < j ? j : i, m);
-    }
+  for (int k = 0; k < 4; ++k) {
+    const int p = 4 * lane + k;
+    pi[k] = (one_pass && p < npairs) ? pairs_i[p] : -1;
+    pj[k] = (one_pass && p < npairs) ? pairs_j[p] : 0;
   }
   for (int64_t row = (int64_t)blockIdx.x * warps + warp; row < rows; row += row_stride) {
     const uint32_t grow = (uint32_t)(row + row_offset);
@@ -369,20 +366,8 @@ levy_tile_kernel(const void* keyp, int64_t row_offset, uint64_t a_id, int64_t ro
         st4((is_h ? sH : sW) + 4 * q, v);
         if (!is_h) st4(out_w + row * m + 4 * q, v);
       }
-    } else {
-      for (int c = lane; c < m; c += 32) {
-        sW[c] = w[row * m + c];
-        sH[c] = hh[row * m + c];
-      }
-    }
-    for (int q = lane; q < nq; q += 32) {
-      T z[4];
-      normal4(key, a_id, STREAM_A, grow, (uint32_t)q, z);
-      st4(sZ + 4 * q, z);
-    }
-    __syncwarp();
-    if (GEN) {
-      for (int q = lane; q < (m >> 2); q += 32) {
+      __syncwarp();
+      for (int q = lane; q < mq; q += 32) {
         T a4[4], b4[4], u4[4];
         ld4(sW + 4 * q, a4);
         ld4(sH + 4 * q, b4);
@@ -390,46 +375,56 @@ levy_tile_kernel(const void* keyp, int64_t row_offset, uint64_t a_id, int64_t ro
         for (int j = 0; j < 4; ++j) u4[j] = ht * (T(0.5) * a4[j] + b4[j]);   // _H_to_U :102-103
         st4(out_u + row * m + 4 * q, u4);
       }
+    } else {
+      for (int c = lane; c < m; c += 32) {
+        sW[c] = w[row * m + c];
+        sH[c] = hh[row * m + c];
+      }
+      __syncwarp();
     }
-    T* dst = out + row * (int64_t)mm;
-    if (vec) {
-      auto group = [&](int e4, int i, int j0, const int* pp) {
-        const T wi = sW[i], hi = sH[i];
-        T wj[4], hj[4], v[4];
-        ld4(sW + j0, wj);
-        ld4(sH + j0, hj);
+    if (one_pass) {
+      if (lane < nq) {
+        T z[4];
+        normal4(key, a_id, STREAM_A, grow, (uint32_t)lane, z);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const int j = j0 + k;
-          if (i == j) { v[k] = T(0); continue; }
-          const int p = pp ? pp[k] : levy_pair_index(i < j ? i : j, i < j ? j : i, m);
-          const T z = sZ[p];
-          // (lo, hi)-ordered expression, negated for the lower triangle
-          v[k] = i < j ? levy_pair_value(wi, wj[k], hi, hj[k], z, tenth_h, davie_std, foster)
-                       : -levy_pair_value(wj[k], wi, hj[k], hi, z, tenth_h, davie_std, foster);
-        }
-        st4(dst + 4 * e4, v);
-      };
-      if (cached) {
-        if (gi[0] >= 0) group(lane, gi[0], gj0[0], gp[0]);
-        if (gi[1] >= 0) group(lane + 32, gi[1], gj0[1], gp[1]);
-      } else {
-        for (int e4 = lane; e4 < ngroups; e4 += 32) {
-          const int i = (4 * e4) / m;
-          group(e4, i, 4 * e4 - i * m, nullptr);
+          if (pi[k] >= 0) {
+            const int i = pi[k], j = pj[k];
+            const T v = levy_pair_value(sW[i], sW[j], sH[i], sH[j], z[k], tenth_h, davie_std, foster);
+            sA[i * ld + j] = v;
+            sA[j * ld + i] = -v;
+          }
         }
       }
     } else {
-      for (int e = lane; e < mm; e += 32) {
-        const int i = e / m, j = e - i * m;
-        T v = T(0);
-        if (i != j) {
-          const int lo = i < j ? i : j, hi_ = i < j ? j : i;
-          const T val = levy_pair_value(sW[lo], sW[hi_], sH[lo], sH[hi_], sZ[levy_pair_index(lo, hi_, m)], tenth_h,
-                                        davie_std, foster);
-          v = i < j ? val : -val;
+      for (int q = lane; q < nq; q += 32) {
+        T z[4];
+        normal4(key, a_id, STREAM_A, grow, (uint32_t)q, z);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int p = 4 * q + k;
+          if (p < npairs) {
+            const int i = pairs_i[p], j = pairs_j[p];
+            const T v = levy_pair_value(sW[i], sW[j], sH[i], sH[j], z[k], tenth_h, davie_std, foster);
+            sA[i * ld + j] = v;
+            sA[j * ld + i] = -v;
+          }
         }
-        dst[e] = v;
+      }
+    }
+    __syncwarp();
+    T* dst = out + row * (int64_t)mm;
+    if (vec) {   // m % 4 == 0: a lane gathers 4 consecutive columns of one tile row and writes them as one 128-bit store
+      for (int e = 4 * lane; e < mm; e += 128) {
+        const int i = e / m, j0 = e - i * m;
+        const T* src = sA + i * ld + j0;
+        const T v4[4] = {src[0], src[1], src[2], src[3]};
+        st4(dst + e, v4);
+      }
+    } else {
+      for (int e = lane; e < mm; e += 32) {
+        const int i = e / m;
+        dst[e] = sA[i * ld + (e - i * m)];
       }
     }
     __syncwarp();
@@ -486,15 +481,16 @@ static int launch_levy_tiles(const tsde_launch* L, const void* key, int64_t row_
                              void* out_u, cudaStream_t st) {
   const int64_t m = L->m;
   const int npairs = (int)(m * (m - 1) / 2);
-  const size_t tile = (size_t)((4 * ((npairs + 3) / 4) + 2 * m + 3) & ~3ll) * sizeof(T);   // Z | W | H per warp
-  int warps = (int)((46 * 1024) / tile);
+  const size_t tile = (size_t)((m * (m + 1) + 2 * m + 3) & ~3ll) * sizeof(T);   // padded A tile | W | H per warp
+  const size_t table = ((size_t)2 * npairs + 15) & ~(size_t)15;
+  int warps = (int)((46 * 1024 - table) / tile);
   if (warps > kLevyWarps) warps = kLevyWarps;
   if (warps < 1) return kLevyNoTile;
-  const size_t smem = (size_t)warps * tile;
+  const size_t smem = table + (size_t)warps * tile;
   int64_t blocks = (L->rows + warps - 1) / warps;
   const int64_t cap = (int64_t)sm_count() * 8;   // persistent: a few CTAs per SM, rows strided over them
   if (blocks > cap) blocks = cap;
-  const int vec = ((m * m) % 4 == 0 && aligned16(out_a)) ? 1 : 0;
+  const int vec = (m % 4 == 0 && aligned16(out_a)) ? 1 : 0;   // groups of 4 consecutive columns of one row
   levy_tile_kernel<T, GEN><<<(unsigned)blocks, kLevyWarps * 32, smem, st>>>(
       key, row_offset, a_id, L->rows, (int)m, npairs, warps, (const T*)w, (const T*)hh, (T)(0.1 * h),
       (T)sqrt((1.0 / 12.0) * h * h), foster, (T*)out_a, vec, cell_id, (T)sqrt(h), (T)sqrt(h / 12.0), (T)h, (T*)out_w,
