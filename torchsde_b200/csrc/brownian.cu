@@ -344,12 +344,24 @@ levy_tile_kernel(const void* keyp, int64_t row_offset, uint64_t a_id, int64_t ro
   // A lane's pairs do not depend on the row when one pass covers them (nq <= 32, i.e. m <= 16): look the indices up
   // once — tile offsets of A_ij / A_ji and of the four W/H operands — instead of once per row.
   const bool one_pass = nq <= 32;
-  int pi[4], pj[4];
+  int pi[4], pj[4], oa[4], ob[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int p = 4 * lane + k;
     pi[k] = (one_pass && p < npairs) ? pairs_i[p] : -1;
     pj[k] = (one_pass && p < npairs) ? pairs_j[p] : 0;
+    oa[k] = pi[k] * ld + pj[k];   // tile offset of A_ij
+    ob[k] = pj[k] * ld + pi[k];   // ... and of A_ji
+  }
+  // likewise the (up to two, m <= 16) groups of 4 consecutive output elements a lane copies out per row
+  const bool copy_cached = vec && mm <= 256;
+  int src_off[2], dst_off[2];
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int e = 4 * lane + 128 * t;
+    const int i = e / m;
+    dst_off[t] = (copy_cached && e < mm) ? e : -1;
+    src_off[t] = i * ld + (e - i * m);
   }
   for (int64_t row = (int64_t)blockIdx.x * warps + warp; row < rows; row += row_stride) {
     const uint32_t grow = (uint32_t)(row + row_offset);
@@ -391,8 +403,8 @@ levy_tile_kernel(const void* keyp, int64_t row_offset, uint64_t a_id, int64_t ro
           if (pi[k] >= 0) {
             const int i = pi[k], j = pj[k];
             const T v = levy_pair_value(sW[i], sW[j], sH[i], sH[j], z[k], tenth_h, davie_std, foster);
-            sA[i * ld + j] = v;
-            sA[j * ld + i] = -v;
+            sA[oa[k]] = v;
+            sA[ob[k]] = -v;
           }
         }
       }
@@ -414,7 +426,16 @@ levy_tile_kernel(const void* keyp, int64_t row_offset, uint64_t a_id, int64_t ro
     }
     __syncwarp();
     T* dst = out + row * (int64_t)mm;
-    if (vec) {   // m % 4 == 0: a lane gathers 4 consecutive columns of one tile row and writes them as one 128-bit store
+    if (copy_cached) {
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        if (dst_off[t] >= 0) {
+          const T* src = sA + src_off[t];
+          const T v4[4] = {src[0], src[1], src[2], src[3]};
+          st4(dst + dst_off[t], v4);
+        }
+      }
+    } else if (vec) {   // m % 4 == 0: a lane gathers 4 consecutive columns of one tile row, one 128-bit store
       for (int e = 4 * lane; e < mm; e += 128) {
         const int i = e / m, j0 = e - i * m;
         const T* src = sA + i * ld + j0;
