@@ -91,7 +91,8 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms',
+                                          os.environ.get('TSDE_BENCH_SAMPLER_MS', '200')],  # (the recipe's period)
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
