@@ -296,40 +296,69 @@ struct HToUOp {
 __device__ __forceinline__ float levy_sqrt(float x) { return mufu_sqrt(x); }
 __device__ __forceinline__ double levy_sqrt(double x) { return sqrt(x); }
 
+template <typename T, bool FOSTER>
+__device__ __forceinline__ T levy_pair_value_t(T wi, T wj, T hi, T hj, T z, T tenth_h, T davie_std) {
+  const T a = hi * wj - wi * hj;
+  // N_ij = z / sqrt(2), N_ji = -N_ij: N_ij - N_ji = 2 N_ij.  One multiplication by 2 fl(1/sqrt 2) gives exactly
+  // twice fl(z fl(1/sqrt 2)) (scaling by two commutes with rounding), i.e. the bits of n - (-n).
+  const T noise = z * (T(2) * T(0.70710678118654752440));
+  const T std_ = FOSTER ? levy_sqrt(tenth_h * ((tenth_h + hi * hi) + hj * hj)) : davie_std;
+  return a + std_ * noise;
+}
 template <typename T>
 __device__ __forceinline__ T levy_pair_value(T wi, T wj, T hi, T hj, T z, T tenth_h, T davie_std, int foster) {
-  const T a = hi * wj - wi * hj;
-  const T n = z * T(0.70710678118654752440);   // N_ij
-  const T noise = n - (-n);                      // N_ij - N_ji
-  const T std_ = foster ? levy_sqrt(tenth_h * ((tenth_h + hi * hi) + hj * hj)) : davie_std;
-  return a + std_ * noise;
+  return foster ? levy_pair_value_t<T, true>(wi, wj, hi, hj, z, tenth_h, davie_std)
+                : levy_pair_value_t<T, false>(wi, wj, hi, hj, z, tenth_h, davie_std);
 }
 
 constexpr int kLevyWarps = 8;
 
+// floats per warp in shared memory: padded A tile | W | H | one scratch word (16-byte multiple)
+__host__ __device__ constexpr int levy_tile_elems(int m) { return (m * (m + 1) + 2 * m + 1 + 3) & ~3; }
+
+// The four pairs of one Philox quad: operands through per-lane shared-memory pointers looked up once per kernel
+// (slots past the last pair point at the scratch word, so the pass has no per-pair branch).
+template <typename T, bool FOSTER>
+__device__ __forceinline__ void levy_quad_pairs(const T* const (&pw_i)[4], const T* const (&pw_j)[4], int m,
+                                                T* const (&pa)[4], T* const (&pb)[4], const T (&z)[4], T tenth_h,
+                                                T davie_std) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const T v = levy_pair_value_t<T, FOSTER>(pw_i[k][0], pw_j[k][0], pw_i[k][m], pw_j[k][m], z[k], tenth_h,
+                                             davie_std);
+    *pa[k] = v;
+    *pb[k] = -v;
+  }
+}
+
 // GEN: the row's W and H are not read but drawn from the counter (primary cell `cell_id` of length h: W = sqrt(h) N_W,
 // H = sqrt(h/12) N_H, as counter_noise does), and W and U = h (W/2 + H) are written out as well: one launch answers a
 // whole-cell query bm(ta, tb, return_U=True, return_A=True) (brownian_interval.py:589-687).
-template <typename T, bool GEN>
-__global__ void __launch_bounds__(kLevyWarps * 32)
-levy_tile_kernel(const void* keyp, int64_t row_offset, uint64_t a_id, int64_t rows, int m, int npairs, int warps,
+// MT: the channel count as a compile-time constant (0 = run-time `m_rt`); with it the tile stride, the pair count
+// and the copy-out pattern fold into immediates.
+template <typename T, bool GEN, int MT>
+__global__ void __launch_bounds__(kLevyWarps * 32, (MT && sizeof(T) == 4 && !GEN) ? 5 : 3)
+levy_tile_kernel(const void* keyp, int64_t row_offset, uint64_t a_id, int64_t rows, int m_rt, int warps,
                  const T* __restrict__ w, const T* __restrict__ hh, T tenth_h, T davie_std, int foster,
                  T* __restrict__ out, int vec, uint64_t cell_id, T sqrt_h, T sqrt_h12, T ht, T* __restrict__ out_w,
                  T* __restrict__ out_u) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int m = MT ? MT : m_rt;
   const int mm = m * m;
+  const int npairs = (m * (m - 1)) >> 1;
   const int ld = m + 1;                                   // padded row stride of the shared tile: the mirrored stores
                                                           // sA[j][i] of consecutive lanes then fall into different banks
                                                           // (with stride m = 16 they were 16-way conflicts: measured
                                                           // 71 us per 131072 x 16 x 16 query, LSU-bound)
-  const int tile = (m * ld + 2 * m + 3) & ~3;              // floats per warp: A tile | W | H (16-byte multiple)
+  const int tile = levy_tile_elems(m);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned char* pairs_i = smem_raw;                       // [npairs] row index of pair p
   unsigned char* pairs_j = pairs_i + npairs;               // [npairs] column index
   T* tiles = reinterpret_cast<T*>(smem_raw + (((size_t)2 * npairs + 15) & ~(size_t)15));
   T* sA = tiles + (size_t)warp * tile;
-  T* sW = sA + m * ld;
+  T* sW = sA + m * ld;                                     // W | H contiguous: sH = sW + m
   T* sH = sW + m;
+  T* scratch = sH + m;
   // pair table (shared by the CTA) and the tile's zero diagonal (written once: rows never touch it)
   for (int i = threadIdx.x; i < m; i += blockDim.x) {
     int p = i * m - (i * (i + 1)) / 2;                     // first pair of row i
@@ -341,17 +370,21 @@ levy_tile_kernel(const void* keyp, int64_t row_offset, uint64_t a_id, int64_t ro
   const Key key = load_key(keyp);
   const int nq = (npairs + 3) >> 2;
   const int64_t row_stride = (int64_t)gridDim.x * warps;
-  // A lane's pairs do not depend on the row when one pass covers them (nq <= 32, i.e. m <= 16): look the indices up
-  // once — tile offsets of A_ij / A_ji and of the four W/H operands — instead of once per row.
+  // A lane's pairs do not depend on the row when one pass covers them (nq <= 32, i.e. m <= 16): look them up once.
   const bool one_pass = nq <= 32;
-  int pi[4], pj[4], oa[4], ob[4];
+  const T* pw_i[4];
+  const T* pw_j[4];
+  T* pa[4];
+  T* pb[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int p = 4 * lane + k;
-    pi[k] = (one_pass && p < npairs) ? pairs_i[p] : -1;
-    pj[k] = (one_pass && p < npairs) ? pairs_j[p] : 0;
-    oa[k] = pi[k] * ld + pj[k];   // tile offset of A_ij
-    ob[k] = pj[k] * ld + pi[k];   // ... and of A_ji
+    const bool ok = one_pass && p < npairs;
+    const int i = ok ? pairs_i[p] : 0, j = ok ? pairs_j[p] : 0;
+    pw_i[k] = sW + i;
+    pw_j[k] = sW + j;
+    pa[k] = ok ? sA + i * ld + j : scratch;   // A_ij
+    pb[k] = ok ? sA + j * ld + i : scratch;   // A_ji
   }
   // likewise the (up to two, m <= 16) groups of 4 consecutive output elements a lane copies out per row
   const bool copy_cached = vec && mm <= 256;
@@ -363,7 +396,22 @@ levy_tile_kernel(const void* keyp, int64_t row_offset, uint64_t a_id, int64_t ro
     dst_off[t] = (copy_cached && e < mm) ? e : -1;
     src_off[t] = i * ld + (e - i * m);
   }
-  for (int64_t row = (int64_t)blockIdx.x * warps + warp; row < rows; row += row_stride) {
+  // W | H of a row: element c of the 2m-vector (c < m: W_c, else H_{c-m}) is loaded by lane c % 32; the next row's
+  // elements are fetched while the current row is worked on.
+  T pre[4] = {T(0), T(0), T(0), T(0)};
+  const T* wh_src[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int c = lane + 32 * t;
+    wh_src[t] = (c < m) ? w + c : hh + (c - m);
+  }
+  int64_t row = (int64_t)blockIdx.x * warps + warp;
+  if (!GEN && row < rows) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      if (lane + 32 * t < 2 * m) pre[t] = wh_src[t][row * m];
+  }
+  for (; row < rows; row += row_stride) {
     const uint32_t grow = (uint32_t)(row + row_offset);
     if (GEN) {
       const int mq = m >> 2;                              // (host guarantees m % 4 == 0 in this mode)
@@ -388,25 +436,23 @@ levy_tile_kernel(const void* keyp, int64_t row_offset, uint64_t a_id, int64_t ro
         st4(out_u + row * m + 4 * q, u4);
       }
     } else {
-      for (int c = lane; c < m; c += 32) {
-        sW[c] = w[row * m + c];
-        sH[c] = hh[row * m + c];
-      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        if (lane + 32 * t < 2 * m) sW[lane + 32 * t] = pre[t];
       __syncwarp();
+      const int64_t nxt = row + row_stride;
+      if (nxt < rows) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+          if (lane + 32 * t < 2 * m) pre[t] = wh_src[t][nxt * m];
+      }
     }
     if (one_pass) {
       if (lane < nq) {
         T z[4];
         normal4(key, a_id, STREAM_A, grow, (uint32_t)lane, z);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (pi[k] >= 0) {
-            const int i = pi[k], j = pj[k];
-            const T v = levy_pair_value(sW[i], sW[j], sH[i], sH[j], z[k], tenth_h, davie_std, foster);
-            sA[oa[k]] = v;
-            sA[ob[k]] = -v;
-          }
-        }
+        if (foster) levy_quad_pairs<T, true>(pw_i, pw_j, m, pa, pb, z, tenth_h, davie_std);
+        else levy_quad_pairs<T, false>(pw_i, pw_j, m, pa, pb, z, tenth_h, davie_std);
       }
     } else {
       for (int q = lane; q < nq; q += 32) {
@@ -448,7 +494,8 @@ levy_tile_kernel(const void* keyp, int64_t row_offset, uint64_t a_id, int64_t ro
         dst[e] = sA[i * ld + (e - i * m)];
       }
     }
-    __syncwarp();
+    // no barrier here: the next row's tile stores come after the barrier that follows its W | H stores, and those
+    // only overwrite what was last read before the barrier above
   }
 }
 
@@ -502,20 +549,29 @@ static int launch_levy_tiles(const tsde_launch* L, const void* key, int64_t row_
                              void* out_u, cudaStream_t st) {
   const int64_t m = L->m;
   const int npairs = (int)(m * (m - 1) / 2);
-  const size_t tile = (size_t)((m * (m + 1) + 2 * m + 3) & ~3ll) * sizeof(T);   // padded A tile | W | H per warp
+  const size_t tile = (size_t)levy_tile_elems((int)m) * sizeof(T);
   const size_t table = ((size_t)2 * npairs + 15) & ~(size_t)15;
   int warps = (int)((46 * 1024 - table) / tile);
   if (warps > kLevyWarps) warps = kLevyWarps;
   if (warps < 1) return kLevyNoTile;
   const size_t smem = table + (size_t)warps * tile;
-  int64_t blocks = (L->rows + warps - 1) / warps;
-  const int64_t cap = (int64_t)sm_count() * 8;   // persistent: a few CTAs per SM, rows strided over them
-  if (blocks > cap) blocks = cap;
   const int vec = (m % 4 == 0 && aligned16(out_a)) ? 1 : 0;   // groups of 4 consecutive columns of one row
-  levy_tile_kernel<T, GEN><<<(unsigned)blocks, kLevyWarps * 32, smem, st>>>(
-      key, row_offset, a_id, L->rows, (int)m, npairs, warps, (const T*)w, (const T*)hh, (T)(0.1 * h),
-      (T)sqrt((1.0 / 12.0) * h * h), foster, (T*)out_a, vec, cell_id, (T)sqrt(h), (T)sqrt(h / 12.0), (T)h, (T*)out_w,
-      (T*)out_u);
+  // persistent: exactly the CTAs that are resident at once (one wave), rows strided over them
+#define TSDE_LEVY_LAUNCH(MT)                                                                                         \
+  int per_sm = 0;                                                                                                    \
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, levy_tile_kernel<T, GEN, MT>, kLevyWarps * 32, smem) != \
+          cudaSuccess || per_sm < 1)                                                                                 \
+    per_sm = 1;                                                                                                      \
+  int64_t blocks = (L->rows + warps - 1) / warps;                                                                    \
+  if (blocks > (int64_t)sm_count() * per_sm) blocks = (int64_t)sm_count() * per_sm;                                  \
+  levy_tile_kernel<T, GEN, MT><<<(unsigned)blocks, kLevyWarps * 32, smem, st>>>(                                     \
+      key, row_offset, a_id, L->rows, (int)m, warps, (const T*)w, (const T*)hh, (T)(0.1 * h),                        \
+      (T)sqrt((1.0 / 12.0) * h * h), foster, (T*)out_a, vec, cell_id, (T)sqrt(h), (T)sqrt(h / 12.0), (T)h,           \
+      (T*)out_w, (T*)out_u)
+  if (m == 16) { TSDE_LEVY_LAUNCH(16); }
+  else if (m == 8) { TSDE_LEVY_LAUNCH(8); }
+  else { TSDE_LEVY_LAUNCH(0); }
+#undef TSDE_LEVY_LAUNCH
   return (int)cudaGetLastError();
 }
 

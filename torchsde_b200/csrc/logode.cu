@@ -19,7 +19,7 @@ namespace tsde {
 constexpr int kBmmThreads = 256;
 
 template <typename T, int M>
-__global__ void __launch_bounds__(kBmmThreads)
+__global__ void __launch_bounds__(kBmmThreads, (M <= 16 && sizeof(T) == 4) ? 3 : 1)
 bmm_ga_kernel(int64_t rows, int d, const T* __restrict__ g, const T* __restrict__ a, T* __restrict__ out,
               int rows_per_cta) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -59,13 +59,28 @@ bmm_ga_kernel(int64_t rows, int d, const T* __restrict__ g, const T* __restrict_
       for (int k = 0; k < M; ++k) gk[k] = gp[k];
     }
     const T* A = sA + r * (M * M);
+    // all M results of the thread accumulate at once, k ascending for each (the order of the one-result-at-a-time
+    // loop): A[k][.] then comes out of shared memory as 128-bit broadcasts, M*M/4 loads instead of M*M
+    T acc[M];
 #pragma unroll
-    for (int l = 0; l < M; ++l) {
-      T acc = T(0);
+    for (int l = 0; l < M; ++l) acc[l] = T(0);
 #pragma unroll
-      for (int k = 0; k < M; ++k) acc = fma(gk[k], A[k * M + l], acc);
-      out[(int64_t)l * plane + row * d + dd] = acc;
+    for (int k = 0; k < M; ++k) {
+      if (M % 4 == 0) {
+#pragma unroll
+        for (int l = 0; l < M; l += 4) {
+          T a4[4];
+          ld4(A + k * M + l, a4);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[l + j] = fma(gk[k], a4[j], acc[l + j]);
+        }
+      } else {
+#pragma unroll
+        for (int l = 0; l < M; ++l) acc[l] = fma(gk[k], A[k * M + l], acc[l]);
+      }
     }
+#pragma unroll
+    for (int l = 0; l < M; ++l) out[(int64_t)l * plane + row * d + dd] = acc[l];
   }
 }
 
