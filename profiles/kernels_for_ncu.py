@@ -59,6 +59,13 @@ a = torch.empty(B, M, M, device=dev)
 Lb = _cabi.make_launch(torch.float32, _cabi.NOISE_DIAGONAL, B, M, M)
 for _ in range(3):
     lib.tsde_brownian_levy_area(ctypes.byref(Lb), key.data_ptr(), 0, 77, w.data_ptr(), h.data_ptr(), 2.0 ** -6, 1, a.data_ptr())
+# ... and the fused whole-cell query (W, U and A drawn in one launch), same shape
+wo, uo = torch.empty(B, M, device=dev), torch.empty(B, M, device=dev)
+nzc = noise()
+nzc.h = nzc.h_total = 2.0 ** -6
+for _ in range(3):
+    rc = lib.tsde_brownian_cell_levy(ctypes.byref(Lb), ctypes.byref(nzc), 77, 1, wo.data_ptr(), uo.data_ptr(), a.data_ptr())
+    assert rc == 0, rc
 # bmm(g, A) of the log-ODE correction at the cfg3 size
 B, D, M = 8192, 32, 16
 gg = torch.randn(B, D, M, device=dev)

@@ -313,19 +313,26 @@ __device__ __forceinline__ T levy_pair_value(T wi, T wj, T hi, T hj, T z, T tent
 
 constexpr int kLevyWarps = 8;
 
-// floats per warp in shared memory: padded A tile | W | H | one scratch word (16-byte multiple)
-__host__ __device__ constexpr int levy_tile_elems(int m) { return (m * (m + 1) + 2 * m + 1 + 3) & ~3; }
+// Rows a warp handles per pass in the generating mode: the W and H normals of one row are only m/2 Philox quads, so
+// one warp-wide pass draws them for 32 / (m/2) rows at once (m = 16: 4 rows) instead of leaving most lanes idle.
+__host__ __device__ constexpr int levy_group_rows(int m, bool gen) {
+  return (gen && m >= 4 && 64 / m >= 1) ? 64 / m : 1;
+}
+// floats per warp in shared memory: padded A tile | (W | H) x rows per pass | one scratch word (16-byte multiple)
+__host__ __device__ constexpr int levy_tile_elems(int m, bool gen) {
+  return (m * (m + 1) + 2 * m * levy_group_rows(m, gen) + 1 + 3) & ~3;
+}
 
 // The four pairs of one Philox quad: operands through per-lane shared-memory pointers looked up once per kernel
 // (slots past the last pair point at the scratch word, so the pass has no per-pair branch).
 template <typename T, bool FOSTER>
-__device__ __forceinline__ void levy_quad_pairs(const T* const (&pw_i)[4], const T* const (&pw_j)[4], int m,
+__device__ __forceinline__ void levy_quad_pairs(const T* const (&pw_i)[4], const T* const (&pw_j)[4], int off, int m,
                                                 T* const (&pa)[4], T* const (&pb)[4], const T (&z)[4], T tenth_h,
                                                 T davie_std) {
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const T v = levy_pair_value_t<T, FOSTER>(pw_i[k][0], pw_j[k][0], pw_i[k][m], pw_j[k][m], z[k], tenth_h,
-                                             davie_std);
+    const T v = levy_pair_value_t<T, FOSTER>(pw_i[k][off], pw_j[k][off], pw_i[k][off + m], pw_j[k][off + m], z[k],
+                                             tenth_h, davie_std);
     *pa[k] = v;
     *pb[k] = -v;
   }
@@ -337,7 +344,7 @@ __device__ __forceinline__ void levy_quad_pairs(const T* const (&pw_i)[4], const
 // MT: the channel count as a compile-time constant (0 = run-time `m_rt`); with it the tile stride, the pair count
 // and the copy-out pattern fold into immediates.
 template <typename T, bool GEN, int MT>
-__global__ void __launch_bounds__(kLevyWarps * 32, (MT && sizeof(T) == 4 && !GEN) ? 5 : 3)
+__global__ void __launch_bounds__(kLevyWarps * 32, (MT && sizeof(T) == 4) ? (GEN ? 4 : 5) : 3)
 levy_tile_kernel(const void* keyp, int64_t row_offset, uint64_t a_id, int64_t rows, int m_rt, int warps,
                  const T* __restrict__ w, const T* __restrict__ hh, T tenth_h, T davie_std, int foster,
                  T* __restrict__ out, int vec, uint64_t cell_id, T sqrt_h, T sqrt_h12, T ht, T* __restrict__ out_w,
@@ -350,15 +357,15 @@ levy_tile_kernel(const void* keyp, int64_t row_offset, uint64_t a_id, int64_t ro
                                                           // sA[j][i] of consecutive lanes then fall into different banks
                                                           // (with stride m = 16 they were 16-way conflicts: measured
                                                           // 71 us per 131072 x 16 x 16 query, LSU-bound)
-  const int tile = levy_tile_elems(m);
+  const int tile = levy_tile_elems(m, GEN);
+  const int R = levy_group_rows(m, GEN);                   // rows per pass (1 unless generating)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned char* pairs_i = smem_raw;                       // [npairs] row index of pair p
   unsigned char* pairs_j = pairs_i + npairs;               // [npairs] column index
   T* tiles = reinterpret_cast<T*>(smem_raw + (((size_t)2 * npairs + 15) & ~(size_t)15));
   T* sA = tiles + (size_t)warp * tile;
-  T* sW = sA + m * ld;                                     // W | H contiguous: sH = sW + m
-  T* sH = sW + m;
-  T* scratch = sH + m;
+  T* sW = sA + m * ld;                                     // row r of the pass: W at sW + 2 m r, H at sW + 2 m r + m
+  T* scratch = sW + 2 * m * R;
   // pair table (shared by the CTA) and the tile's zero diagonal (written once: rows never touch it)
   for (int i = threadIdx.x; i < m; i += blockDim.x) {
     int p = i * m - (i * (i + 1)) / 2;                     // first pair of row i
@@ -405,97 +412,113 @@ levy_tile_kernel(const void* keyp, int64_t row_offset, uint64_t a_id, int64_t ro
     const int c = lane + 32 * t;
     wh_src[t] = (c < m) ? w + c : hh + (c - m);
   }
-  int64_t row = (int64_t)blockIdx.x * warps + warp;
-  if (!GEN && row < rows) {
+  int64_t base = ((int64_t)blockIdx.x * warps + warp) * R;
+  if (!GEN && base < rows) {
 #pragma unroll
     for (int t = 0; t < 4; ++t)
-      if (lane + 32 * t < 2 * m) pre[t] = wh_src[t][row * m];
+      if (lane + 32 * t < 2 * m) pre[t] = wh_src[t][base * m];
   }
-  for (; row < rows; row += row_stride) {
-    const uint32_t grow = (uint32_t)(row + row_offset);
+  for (; base < rows; base += row_stride * R) {
     if (GEN) {
-      const int mq = m >> 2;                              // (host guarantees m % 4 == 0 in this mode)
-      for (int t = lane; t < 2 * mq; t += 32) {
-        const bool is_h = t >= mq;
-        const int q = is_h ? t - mq : t;
+      const int mq = m >> 2, gq = 2 * mq;                  // (host guarantees m % 4 == 0 in this mode)
+      for (int t = lane; t < R * gq; t += 32) {            // one trip: R gq <= 32
+        const int rg = t / gq, tq = t - rg * gq;
+        const bool is_h = tq >= mq;
+        const int q = is_h ? tq - mq : tq;
+        const int64_t row = base + rg;                     // rows past the end are drawn but not stored
         T n[4], v[4];
-        normal4(key, cell_id, is_h ? STREAM_H : STREAM_W, grow, (uint32_t)q, n);
+        normal4(key, cell_id, is_h ? STREAM_H : STREAM_W, (uint32_t)(row + row_offset), (uint32_t)q, n);
         const T sc = is_h ? sqrt_h12 : sqrt_h;
 #pragma unroll
         for (int j = 0; j < 4; ++j) v[j] = n[j] * sc;
-        st4((is_h ? sH : sW) + 4 * q, v);
-        if (!is_h) st4(out_w + row * m + 4 * q, v);
+        st4(sW + 2 * m * rg + (is_h ? m : 0) + 4 * q, v);
+        if (!is_h && row < rows) st4(out_w + row * m + 4 * q, v);
       }
       __syncwarp();
-      for (int q = lane; q < mq; q += 32) {
-        T a4[4], b4[4], u4[4];
-        ld4(sW + 4 * q, a4);
-        ld4(sH + 4 * q, b4);
+      for (int t = lane; t < R * mq; t += 32) {
+        const int rg = t / mq, q = t - rg * mq;
+        const int64_t row = base + rg;
+        if (row < rows) {
+          T a4[4], b4[4], u4[4];
+          ld4(sW + 2 * m * rg + 4 * q, a4);
+          ld4(sW + 2 * m * rg + m + 4 * q, b4);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) u4[j] = ht * (T(0.5) * a4[j] + b4[j]);   // _H_to_U :102-103
-        st4(out_u + row * m + 4 * q, u4);
+          for (int j = 0; j < 4; ++j) u4[j] = ht * (T(0.5) * a4[j] + b4[j]);   // _H_to_U :102-103
+          st4(out_u + row * m + 4 * q, u4);
+        }
       }
     } else {
 #pragma unroll
       for (int t = 0; t < 4; ++t)
         if (lane + 32 * t < 2 * m) sW[lane + 32 * t] = pre[t];
       __syncwarp();
-      const int64_t nxt = row + row_stride;
+      const int64_t nxt = base + row_stride;
       if (nxt < rows) {
 #pragma unroll
         for (int t = 0; t < 4; ++t)
           if (lane + 32 * t < 2 * m) pre[t] = wh_src[t][nxt * m];
       }
     }
-    if (one_pass) {
-      if (lane < nq) {
-        T z[4];
-        normal4(key, a_id, STREAM_A, grow, (uint32_t)lane, z);
-        if (foster) levy_quad_pairs<T, true>(pw_i, pw_j, m, pa, pb, z, tenth_h, davie_std);
-        else levy_quad_pairs<T, false>(pw_i, pw_j, m, pa, pb, z, tenth_h, davie_std);
-      }
-    } else {
-      for (int q = lane; q < nq; q += 32) {
-        T z[4];
-        normal4(key, a_id, STREAM_A, grow, (uint32_t)q, z);
+#pragma unroll 1
+    for (int rg = 0; rg < R; ++rg) {
+      const int64_t row = base + rg;
+      if (GEN && row >= rows) break;
+      const int off = GEN ? 2 * m * rg : 0;
+      const uint32_t grow = (uint32_t)(row + row_offset);
+      if (one_pass) {
+        if (lane < nq) {
+          T z[4];
+          normal4(key, a_id, STREAM_A, grow, (uint32_t)lane, z);
+          if (foster) levy_quad_pairs<T, true>(pw_i, pw_j, off, m, pa, pb, z, tenth_h, davie_std);
+          else levy_quad_pairs<T, false>(pw_i, pw_j, off, m, pa, pb, z, tenth_h, davie_std);
+        }
+      } else {
+        const T* rW = sW + off;
+        const T* rH = rW + m;
+        for (int q = lane; q < nq; q += 32) {
+          T z[4];
+          normal4(key, a_id, STREAM_A, grow, (uint32_t)q, z);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int p = 4 * q + k;
-          if (p < npairs) {
-            const int i = pairs_i[p], j = pairs_j[p];
-            const T v = levy_pair_value(sW[i], sW[j], sH[i], sH[j], z[k], tenth_h, davie_std, foster);
-            sA[i * ld + j] = v;
-            sA[j * ld + i] = -v;
+          for (int k = 0; k < 4; ++k) {
+            const int p = 4 * q + k;
+            if (p < npairs) {
+              const int i = pairs_i[p], j = pairs_j[p];
+              const T v = levy_pair_value(rW[i], rW[j], rH[i], rH[j], z[k], tenth_h, davie_std, foster);
+              sA[i * ld + j] = v;
+              sA[j * ld + i] = -v;
+            }
           }
         }
       }
-    }
-    __syncwarp();
-    T* dst = out + row * (int64_t)mm;
-    if (copy_cached) {
+      __syncwarp();
+      T* dst = out + row * (int64_t)mm;
+      if (copy_cached) {
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        if (dst_off[t] >= 0) {
-          const T* src = sA + src_off[t];
+        for (int t = 0; t < 2; ++t) {
+          if (dst_off[t] >= 0) {
+            const T* src = sA + src_off[t];
+            const T v4[4] = {src[0], src[1], src[2], src[3]};
+            st4(dst + dst_off[t], v4);
+          }
+        }
+      } else if (vec) {   // m % 4 == 0: a lane gathers 4 consecutive columns of one tile row, one 128-bit store
+        for (int e = 4 * lane; e < mm; e += 128) {
+          const int i = e / m, j0 = e - i * m;
+          const T* src = sA + i * ld + j0;
           const T v4[4] = {src[0], src[1], src[2], src[3]};
-          st4(dst + dst_off[t], v4);
+          st4(dst + e, v4);
+        }
+      } else {
+        for (int e = lane; e < mm; e += 32) {
+          const int i = e / m;
+          dst[e] = sA[i * ld + (e - i * m)];
         }
       }
-    } else if (vec) {   // m % 4 == 0: a lane gathers 4 consecutive columns of one tile row, one 128-bit store
-      for (int e = 4 * lane; e < mm; e += 128) {
-        const int i = e / m, j0 = e - i * m;
-        const T* src = sA + i * ld + j0;
-        const T v4[4] = {src[0], src[1], src[2], src[3]};
-        st4(dst + e, v4);
-      }
-    } else {
-      for (int e = lane; e < mm; e += 32) {
-        const int i = e / m;
-        dst[e] = sA[i * ld + (e - i * m)];
-      }
+      // Reading mode: no barrier here — the next row's tile stores come after the barrier that follows its W | H
+      // stores, and those only overwrite what was last read before the barrier above.  Generating mode: the next
+      // row of the pass writes the tile straight away.
+      if (GEN) __syncwarp();
     }
-    // no barrier here: the next row's tile stores come after the barrier that follows its W | H stores, and those
-    // only overwrite what was last read before the barrier above
   }
 }
 
@@ -549,7 +572,7 @@ static int launch_levy_tiles(const tsde_launch* L, const void* key, int64_t row_
                              void* out_u, cudaStream_t st) {
   const int64_t m = L->m;
   const int npairs = (int)(m * (m - 1) / 2);
-  const size_t tile = (size_t)levy_tile_elems((int)m) * sizeof(T);
+  const size_t tile = (size_t)levy_tile_elems((int)m, GEN) * sizeof(T);
   const size_t table = ((size_t)2 * npairs + 15) & ~(size_t)15;
   int warps = (int)((46 * 1024 - table) / tile);
   if (warps > kLevyWarps) warps = kLevyWarps;
@@ -562,7 +585,8 @@ static int launch_levy_tiles(const tsde_launch* L, const void* key, int64_t row_
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, levy_tile_kernel<T, GEN, MT>, kLevyWarps * 32, smem) != \
           cudaSuccess || per_sm < 1)                                                                                 \
     per_sm = 1;                                                                                                      \
-  int64_t blocks = (L->rows + warps - 1) / warps;                                                                    \
+  const int64_t per_cta = (int64_t)warps * levy_group_rows((int)m, GEN);                                             \
+  int64_t blocks = (L->rows + per_cta - 1) / per_cta;                                                                \
   if (blocks > (int64_t)sm_count() * per_sm) blocks = (int64_t)sm_count() * per_sm;                                  \
   levy_tile_kernel<T, GEN, MT><<<(unsigned)blocks, kLevyWarps * 32, smem, st>>>(                                     \
       key, row_offset, a_id, L->rows, (int)m, warps, (const T*)w, (const T*)hh, (T)(0.1 * h),                        \
