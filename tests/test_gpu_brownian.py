@@ -200,11 +200,11 @@ def test_cells_and_bridge_vs_oracle(dtype, levy, size):
 
 @pytest.mark.parametrize('dtype', ['f32', 'f64'])
 @pytest.mark.parametrize('levy', ['davie', 'foster'])
-def test_levy_area_vs_oracle(dtype, levy):
+@pytest.mark.parametrize('rows,m', [(21, 4), (300, 16), (70, 8), (9, 5), (6, 40), (11, 2)])
+def test_levy_area_vs_oracle(dtype, levy, rows, m):
     tsde = _tsde()
     tdt, npdt = (torch.float64, np.float64) if dtype == 'f64' else (torch.float32, np.float32)
     tol = dict(rtol=1e-12, atol=1e-13) if dtype == 'f64' else dict(rtol=3e-5, atol=1e-5)
-    rows, m = 21, 4
     bm = tsde.BrownianInterval(0.0, 2.0, size=(rows, m), dtype=tdt, device=DEV, entropy=5,
                                levy_area_approximation=levy)
     W_, U_, A_ = bm(0.0, 2.0, return_U=True, return_A=True)
@@ -346,11 +346,13 @@ def test_bmm_ga_kernel_vs_torch(dtype, B, d, m):
 
 @pytest.mark.parametrize('levy', ['davie', 'foster'])
 @pytest.mark.parametrize('dtype', [torch.float32, torch.float64])
-def test_fused_cell_levy_query_equals_general_path(levy, dtype):
+@pytest.mark.parametrize('size', [(257, 8), (1030, 16), (77, 4), (45, 32), (19, 12), (5, 64)])
+def test_fused_cell_levy_query_equals_general_path(levy, dtype, size):
     """tsde_brownian_cell_levy (W, U, A of one whole grid cell in one launch) against the three-kernel general path
-    (cells -> levy_area -> h_to_u) on the same Brownian motion: bit-identical."""
+    (cells -> levy_area -> h_to_u) on the same Brownian motion: bit-identical.  The fused kernel draws the W | H
+    normals of 64/m rows per warp pass: the row counts are not multiples of that group."""
     tsde = _tsde()
-    kw = dict(size=(257, 8), dtype=dtype, device=DEV, entropy=99, dt=0.125, levy_area_approximation=levy)
+    kw = dict(size=size, dtype=dtype, device=DEV, entropy=99, dt=0.125, levy_area_approximation=levy)
     fused = tsde.BrownianInterval(0.0, 1.0, **kw)
     general = tsde.BrownianInterval(0.0, 1.0, **kw)
     for k in (0, 3, 7):
