@@ -473,7 +473,12 @@ def run_ours(args, w, rank, world, local_rank):
         graph_mod.drop_plans(sde)       # the cfg2 plan pins 16.8 GB: release it before the other workloads
         del sde
         torch.cuda.empty_cache()
-        secondary = run_secondary(rank, world, dev)
+        try:
+            secondary = run_secondary(rank, world, dev)
+        except Exception as exc:  # the headline line must survive a failure in the extra workloads (reported, loudly)
+            import traceback
+            traceback.print_exc()
+            secondary = {"error": f"{type(exc).__name__}: {exc}"}
     if rank != 0:
         return
     peak, peak_src = peaks()
@@ -683,23 +688,46 @@ def run_secondary(rank, world, dev):
     torch.cuda.empty_cache()
     # ---- cfg5: BrownianInterval sweeps, 64 sequential dt-spaced queries ----
     M, nq, h = 16, 64, 2.0 ** -6
-    for levy, logb in (('none', 20), ('space-time', 20), ('foster', 17), ('foster', 19)):
+    # (sequential order, then a random permutation of the same 64 intervals — the counter-based
+    # source answers a whole-cell query in one launch whatever was asked before it)
+    perm = np.random.default_rng(5).permutation(nq).tolist()
+    for levy, logb, order in (('none', 20, None), ('space-time', 20, None), ('space-time', 20, perm),
+                              ('foster', 17, None), ('foster', 19, None), ('foster', 20, perm)):
         Bq = 1 << logb
 
-        def sweep(i, levy=levy, Bq=Bq):
+        def sweep(i, levy=levy, Bq=Bq, order=order):
             bm = tsde.BrownianInterval(0.0, 1.0, size=(Bq, M), dtype=torch.float32, device=dev, entropy=700 + i, dt=h,
                                        levy_area_approximation=levy)
             bm.shard_rows(rank * Bq)
-            for k in range(nq):
+            for k in (order or range(nq)):
                 r = bm(k * h, (k + 1) * h, return_U=levy != 'none', return_A=levy == 'foster')
             return r
         el, _ = _timed(sweep, 2, 3, dev, world)
         written = {'none': M * 4, 'space-time': 2 * M * 4, 'foster': (2 * M + M * M) * 4}[levy]
         v = world * Bq * nq / el
-        res[f'cfg5_brownian_{levy}' + ('' if (levy, logb) != ('foster', 19) else '_b2e19')] = {"value": v, "unit": "row-queries/s", "ms_per_sweep": el * 1e3,
-                                        "config": {"batch_per_gpu": Bq, "channels": M, "queries": nq, "levy": levy},
+        name = f'cfg5_brownian_{levy}' + ('' if logb in (17, 20) and order is None else f'_b2e{logb}') + \
+            ('_permuted' if order else '')
+        res[name] = {"value": v, "unit": "row-queries/s", "ms_per_sweep": el * 1e3,
+                                        "config": {"batch_per_gpu": Bq, "channels": M, "queries": nq, "levy": levy,
+                                                   "order": "random permutation" if order else "sequential"},
                                         "written_GBps_per_gpu": v / world * written / 1e9,
                                         "write_roofline_frac": v / world * written / 1e9 / peak}
+    # batch sweep of the same 64-query pattern (B in 2^10 .. 2^20): where the host's ~tens of microseconds
+    # per Python-level query stop mattering
+    sweep_res = {}
+    for levy in ('none', 'space-time', 'foster'):
+        for logb in (10, 12, 14, 16, 18):
+            def sweep(i, levy=levy, Bq=1 << logb):
+                bm = tsde.BrownianInterval(0.0, 1.0, size=(Bq, M), dtype=torch.float32, device=dev, entropy=800 + i,
+                                           dt=h, levy_area_approximation=levy)
+                bm.shard_rows(rank * Bq)
+                for k in range(nq):
+                    r = bm(k * h, (k + 1) * h, return_U=levy != 'none', return_A=levy == 'foster')
+                return r
+            el, _ = _timed(sweep, 2, 3, dev, world)
+            sweep_res[f'{levy}_b2e{logb}'] = {"row_queries_per_s": world * (1 << logb) * nq / el,
+                                              "us_per_query": el / nq * 1e6}
+    res['cfg5_batch_sweep'] = sweep_res
     torch.cuda.empty_cache()
     return res
 
