@@ -319,6 +319,11 @@ class BrownianInterval(brownian_base.BaseBrownian):
     def _new(self, *extra):
         return torch.empty((self._rows, self._m, *extra), dtype=self._dtype, device=self._device)
 
+    def _new_out(self, *extra):
+        """An output buffer already in the caller-visible shape (same contiguous (rows, m[, m]) memory): the
+        single-launch query paths hand it out as is, without a reshape."""
+        return torch.empty((*self._size, *extra), dtype=self._dtype, device=self._device)
+
     def _cell_h_dev(self, node):
         if node.cell_h_dev is None:
             b = node.bounds
@@ -571,13 +576,10 @@ class BrownianInterval(brownian_base.BaseBrownian):
                 fused = self._query_cell_levy(ta_r, tb_r)
                 if fused is not None:
                     W, U, A = fused
-                    W, U = W.reshape(self._size), U.reshape(self._size)
-                    A = A.reshape((*self._size, *self._size[-1:]))
                     return (W, U, A) if return_U else (W, A)
-            fast = self._query_cells_wu(ta_r, tb_r, tb - ta) if (self._have_H and not self._have_A) else None
+            fast = self._query_cells_wu(ta_r, tb_r, tb - ta) if not self._have_A else None
             if fast is not None:
                 W, U = fast
-                W, U = W.reshape(self._size), U.reshape(self._size)
                 if return_U:
                     return (W, U, None) if return_A else (W, U)
                 return (W, None) if return_A else W
@@ -605,7 +607,8 @@ class BrownianInterval(brownian_base.BaseBrownian):
     def _query_cells_wu(self, ta, tb, h_total):
         """Single-launch answer (W, U) when [ta, tb] is exactly a run of whole primary cells of the root
         grid (the access pattern of a fixed-step solver / of sequential dt-spaced queries): U is formed in
-        the same kernel as W, H is never materialised."""
+        the same kernel as W, H is never materialised (U is None without a space-time Levy area; the launch is the
+        one `_draw_cells` makes for the same cells, so the numbers are those of the general path)."""
         root = self._root
         if root.kind != _GRID:
             return None
@@ -618,7 +621,7 @@ class BrownianInterval(brownian_base.BaseBrownian):
             return None
         nz = _cabi.Noise()
         nz.source = _cabi.SRC_COUNTER
-        nz.want_u = 1
+        nz.want_u = 1 if self._have_H else 0
         nz.key = self.key_tensor().data_ptr()
         nz.cell_id = (root.cell_base + i) & _MASK64
         nz.row_offset = self._row_offset
@@ -626,10 +629,11 @@ class BrownianInterval(brownian_base.BaseBrownian):
         nz.h = b[i + 1] - b[i]
         nz.h_total = h_total
         nz.cell_h = self._cell_h_dev(root).data_ptr() + 8 * i if j - i > 1 else None
-        W, U = self._new(), self._new()
+        W = self._new_out()
+        U = self._new_out() if self._have_H else None
         L = self._launch()
-        _cabi.check(_cabi.lib().tsde_brownian_cells(ctypes.byref(L), ctypes.byref(nz), W.data_ptr(), U.data_ptr(),
-                                                    None), "tsde_brownian_cells")
+        _cabi.check(_cabi.lib().tsde_brownian_cells(ctypes.byref(L), ctypes.byref(nz), W.data_ptr(),
+                                                    None if U is None else U.data_ptr(), None), "tsde_brownian_cells")
         self._last = root
         return W, U
 
@@ -658,7 +662,7 @@ class BrownianInterval(brownian_base.BaseBrownian):
         nz.h = b[i + 1] - b[i]
         nz.h_total = nz.h
         nz.cell_h = None
-        W, U, A = self._new(), self._new(), self._new(self._m)
+        W, U, A = self._new_out(), self._new_out(), self._new_out(self._m)
         L = self._launch()
         foster = 1 if self._levy_area_approximation == LEVY_AREA_APPROXIMATIONS.foster else 0
         _cabi.check(_cabi.lib().tsde_brownian_cell_levy(ctypes.byref(L), ctypes.byref(nz), cell.id, foster,
