@@ -101,7 +101,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.monotonic(), line.strip()))
+
+    def mark(self):
+        """The timed region starts here: the process was started (and NVML initialised) before the warm-up, so that
+        its start-up does not run against the first timed steps; only samples taken from now on are reported."""
+        self.t_mark = time.monotonic()
 
     def stop(self):
         if self.proc is None:
@@ -113,7 +118,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for ln in self.lines:
+        t_mark = getattr(self, 't_mark', 0.0)
+        timed = [ln for t, ln in self.lines if t >= t_mark] or [ln for _, ln in self.lines[-1:]]
+        for ln in timed:
             p = [x.strip() for x in ln.split(',')]
             if len(p) < 6:
                 continue
@@ -411,13 +418,14 @@ def run_ours(args, w, rank, world, local_rank):
         torch.cuda.synchronize(dev)
 
     # ---- device-resident throughput (`value`) ----
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for i in range(args.warmup):
         solve(y0_dev, 1000 + i)
     barrier()
     launches0 = _cabi.LAUNCHES
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler.mark()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for i in range(args.steps):

@@ -499,6 +499,7 @@ template <typename T, typename Op>
 inline int launch_ew(const tsde_launch* L, const tsde_noise* nz, bool bcast,
                      const void* const* ins, void* const* outs, const Op& op) {
   EwP<Op::NIN, Op::NOUT> p{};
+  if (L->rows == 0) return 0;
   bool vec = (L->d % 4) == 0;
   for (int i = 0; i < Op::NIN; ++i) {
     if (!ins[i]) return TSDE_EINVAL;
@@ -591,8 +592,11 @@ inline int launch_ew(const tsde_launch* L, const tsde_noise* nz, bool bcast,
 // A launch descriptor every entry point can rely on: non-null, non-negative row count, positive widths.
 inline bool launch_invalid(const tsde_launch* L) { return !L || L->rows < 0 || L->d <= 0 || L->m <= 0; }
 
+// (an empty batch is a valid launch that does nothing: its tensors have no storage, so their pointers are null)
 #define TSDE_DISPATCH_DTYPE(L, EXPR_F32, EXPR_F64)                                                   \
   (::tsde::launch_invalid(L) ? TSDE_EINVAL                                                           \
+   : ((L)->dtype != TSDE_F32 && (L)->dtype != TSDE_F64) ? TSDE_EINVAL                                \
+   : (L)->rows == 0          ? 0                                                                     \
    : (L)->dtype == TSDE_F32  ? (EXPR_F32)                                                            \
    : (L)->dtype == TSDE_F64  ? (EXPR_F64)                                                            \
                              : TSDE_EINVAL)

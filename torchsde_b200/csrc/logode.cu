@@ -19,18 +19,37 @@ namespace tsde {
 constexpr int kBmmThreads = 256;
 
 template <typename T, int M>
-__global__ void __launch_bounds__(kBmmThreads, (M <= 16 && sizeof(T) == 4) ? 3 : 1)
+__global__ void __launch_bounds__(kBmmThreads, (M <= 16 && sizeof(T) == 4) ? 4 : 1)
 bmm_ga_kernel(int64_t rows, int d, const T* __restrict__ g, const T* __restrict__ a, T* __restrict__ out,
               int rows_per_cta) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* sA = reinterpret_cast<T*>(smem_raw);                       // [rows_per_cta][M*M]
   const int64_t row0 = (int64_t)blockIdx.x * rows_per_cta;
   const int nrows = (int)((rows - row0) < rows_per_cta ? (rows - row0) : rows_per_cta);
+  // the thread's first g row goes into registers BEFORE the A tiles are staged: both global-memory latencies of the
+  // CTA (g, then A -> shared -> barrier) overlap instead of following each other
+  T gk[M];
+  auto load_g = [&](int idx) {
+    const T* gp = g + (row0 * d + idx) * M;                       // (row0 + r) * d + dd = row0 * d + idx
+    if (M % 4 == 0) {
+#pragma unroll
+      for (int k = 0; k < M; k += 4) {
+        T v[4];
+        ld4(gp + k, v);
+        gk[k] = v[0]; gk[k + 1] = v[1]; gk[k + 2] = v[2]; gk[k + 3] = v[3];
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < M; ++k) gk[k] = gp[k];
+    }
+  };
+  if ((int)threadIdx.x < nrows * d) load_g(threadIdx.x);
   // stage the group's A matrices (contiguous in global memory)
   {
     const int64_t base = row0 * (M * M);
     const int total = nrows * M * M;
     if (M % 4 == 0) {
+#pragma unroll 2
       for (int e = 4 * threadIdx.x; e < total; e += 4 * kBmmThreads) {
         T v[4];
         ld4(a + base + e, v);
@@ -45,19 +64,7 @@ bmm_ga_kernel(int64_t rows, int d, const T* __restrict__ g, const T* __restrict_
   for (int idx = threadIdx.x; idx < nrows * d; idx += kBmmThreads) {
     const int r = idx / d, dd = idx - r * d;
     const int64_t row = row0 + r;
-    T gk[M];
-    const T* gp = g + (row * d + dd) * M;
-    if (M % 4 == 0) {
-#pragma unroll
-      for (int k = 0; k < M; k += 4) {
-        T v[4];
-        ld4(gp + k, v);
-        gk[k] = v[0]; gk[k + 1] = v[1]; gk[k + 2] = v[2]; gk[k + 3] = v[3];
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < M; ++k) gk[k] = gp[k];
-    }
+    if (idx != (int)threadIdx.x) load_g(idx);
     const T* A = sA + r * (M * M);
     // all M results of the thread accumulate at once, k ascending for each (the order of the one-result-at-a-time
     // loop): A[k][.] then comes out of shared memory as 128-bit broadcasts, M*M/4 loads instead of M*M

@@ -696,6 +696,7 @@ static int launch_gen(const tsde_launch* L, const tsde_noise* nz,
   if (!nz) return TSDE_EINVAL;
   if (nz->source != TSDE_SRC_MEMORY && nz->source != TSDE_SRC_COUNTER)
     return TSDE_EINVAL;  // (a user-supplied product, TSDE_SRC_UNIT, goes through the element-wise entry points)
+  if (L->rows == 0) return 0;  // empty batch: nothing to do (its tensors have no storage)
   GenP<Op::NE, Op::NG, Op::NO> p{};
   bool vec = (L->m % 4) == 0;
   int i = 0;
