@@ -312,6 +312,14 @@ __device__ __forceinline__ T levy_pair_value(T wi, T wj, T hi, T hj, T z, T tent
 }
 
 constexpr int kLevyWarps = 8;
+// resident CTAs per SM the fp32 compile-time-m instantiations are compiled for (register budget 65536 / (256 n));
+// overridable for A/B builds (-DTSDE_LEVY_CTAS=4)
+#ifndef TSDE_LEVY_CTAS
+#define TSDE_LEVY_CTAS 5
+#endif
+#ifndef TSDE_LEVY_CTAS_GEN
+#define TSDE_LEVY_CTAS_GEN 4
+#endif
 
 // Rows a warp handles per pass in the generating mode: the W and H normals of one row are only m/2 Philox quads, so
 // one warp-wide pass draws them for 32 / (m/2) rows at once (m = 16: 4 rows) instead of leaving most lanes idle.
@@ -325,10 +333,58 @@ __host__ __device__ constexpr int levy_tile_elems(int m, bool gen) {
 
 // The four pairs of one Philox quad: operands through per-lane shared-memory pointers looked up once per kernel
 // (slots past the last pair point at the scratch word, so the pass has no per-pair branch).
+#ifndef TSDE_LEVY_PACKED
+#define TSDE_LEVY_PACKED 1
+#endif
+// fp32: two pairs per packed (f32x2) instruction, half the issue slots of the scalar pass (the kernel is issue-bound).
+// The cross term H_i W_j - W_i H_j keeps its three roundings (the subtraction is fma(x, -1, y): the product by -1 is
+// exact).  The sum of squares under the root and the final std * noise + cross term are fused multiply-adds, written
+// out as such: ptxas contracts a packed multiply feeding a packed add even when both carry .rn (observed in the SASS),
+// so the source says what runs.  The result differs from the scalar pass (fp64, m > 16) by at most an ulp of the noise
+// term; the area's noise is a fresh draw per query and pinned to the oracle by tolerance, A = -A^T stays exact.
+template <bool FOSTER>
+__device__ __forceinline__ void levy_quad_pairs_f32x2(const float* const (&pw_i)[4], const float* const (&pw_j)[4],
+                                                      int off, int m, float* const (&pa)[4], float* const (&pb)[4],
+                                                      const float (&z)[4], float tenth_h, float davie_std) {
+  const float c2 = 2.0f * 0.70710678118654752440f;
+#pragma unroll
+  for (int k = 0; k < 4; k += 2) {
+    const f32x2 wi = pack2(pw_i[k][off], pw_i[k + 1][off]);
+    const f32x2 wj = pack2(pw_j[k][off], pw_j[k + 1][off]);
+    const f32x2 hi = pack2(pw_i[k][off + m], pw_i[k + 1][off + m]);
+    const f32x2 hj = pack2(pw_j[k][off + m], pw_j[k + 1][off + m]);
+    const f32x2 a = fma2(mul2(wi, hj), pack2(-1.0f, -1.0f), mul2(hi, wj));   // hi wj - wi hj
+    const f32x2 noise = mul2(pack2(z[k], z[k + 1]), pack2(c2, c2));
+    f32x2 sd;
+    if (FOSTER) {
+      const f32x2 t = pack2(tenth_h, tenth_h);
+      const f32x2 s = mul2(t, fma2(hj, hj, fma2(hi, hi, t)));
+      float s0, s1;
+      unpack2(s, s0, s1);
+      sd = pack2(levy_sqrt(s0), levy_sqrt(s1));
+    } else {
+      sd = pack2(davie_std, davie_std);
+    }
+    const f32x2 v = fma2(sd, noise, a);
+    float v0, v1;
+    unpack2(v, v0, v1);
+    *pa[k] = v0;
+    *pb[k] = -v0;
+    *pa[k + 1] = v1;
+    *pb[k + 1] = -v1;
+  }
+}
+
 template <typename T, bool FOSTER>
 __device__ __forceinline__ void levy_quad_pairs(const T* const (&pw_i)[4], const T* const (&pw_j)[4], int off, int m,
                                                 T* const (&pa)[4], T* const (&pb)[4], const T (&z)[4], T tenth_h,
                                                 T davie_std) {
+#if TSDE_LEVY_PACKED
+  if constexpr (sizeof(T) == 4) {
+    levy_quad_pairs_f32x2<FOSTER>(pw_i, pw_j, off, m, pa, pb, z, tenth_h, davie_std);
+    return;
+  }
+#endif
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const T v = levy_pair_value_t<T, FOSTER>(pw_i[k][off], pw_j[k][off], pw_i[k][off + m], pw_j[k][off + m], z[k],
@@ -344,7 +400,7 @@ __device__ __forceinline__ void levy_quad_pairs(const T* const (&pw_i)[4], const
 // MT: the channel count as a compile-time constant (0 = run-time `m_rt`); with it the tile stride, the pair count
 // and the copy-out pattern fold into immediates.
 template <typename T, bool GEN, int MT>
-__global__ void __launch_bounds__(kLevyWarps * 32, (MT && sizeof(T) == 4) ? (GEN ? 4 : 5) : 3)
+__global__ void __launch_bounds__(kLevyWarps * 32, (MT && sizeof(T) == 4) ? (GEN ? TSDE_LEVY_CTAS_GEN : TSDE_LEVY_CTAS) : 3)
 levy_tile_kernel(const void* keyp, int64_t row_offset, uint64_t a_id, int64_t rows, int m_rt, int warps,
                  const T* __restrict__ w, const T* __restrict__ hh, T tenth_h, T davie_std, int foster,
                  T* __restrict__ out, int vec, uint64_t cell_id, T sqrt_h, T sqrt_h12, T ht, T* __restrict__ out_w,
