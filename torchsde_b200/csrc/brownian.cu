@@ -312,13 +312,15 @@ __device__ __forceinline__ T levy_pair_value(T wi, T wj, T hi, T hj, T z, T tent
 }
 
 constexpr int kLevyWarps = 8;
-// resident CTAs per SM the fp32 compile-time-m instantiations are compiled for (register budget 65536 / (256 n));
-// overridable for A/B builds (-DTSDE_LEVY_CTAS=4)
+// resident CTAs per SM the fp32 compile-time-m instantiations are compiled for (register budget 65536 / (256 n)).
+// Measured at 131072 x 16 x 16 (profiles/r02_levy_ab.log, area / fused cell query, us): n = 6: 45.1 / 49.3,
+// 5: 43.3 / 49.3, 4: 42.4 / 47.2, 3: 41.1 / 47.2 — the issue-bound kernel prefers the instruction schedule 71
+// registers allow to more resident warps.  Overridable for A/B builds (-DTSDE_LEVY_CTAS=4).
 #ifndef TSDE_LEVY_CTAS
-#define TSDE_LEVY_CTAS 5
+#define TSDE_LEVY_CTAS 3
 #endif
 #ifndef TSDE_LEVY_CTAS_GEN
-#define TSDE_LEVY_CTAS_GEN 4
+#define TSDE_LEVY_CTAS_GEN 3
 #endif
 
 // Rows a warp handles per pass in the generating mode: the W and H normals of one row are only m/2 Philox quads, so
@@ -379,18 +381,16 @@ template <typename T, bool FOSTER>
 __device__ __forceinline__ void levy_quad_pairs(const T* const (&pw_i)[4], const T* const (&pw_j)[4], int off, int m,
                                                 T* const (&pa)[4], T* const (&pb)[4], const T (&z)[4], T tenth_h,
                                                 T davie_std) {
-#if TSDE_LEVY_PACKED
-  if constexpr (sizeof(T) == 4) {
+  if constexpr (TSDE_LEVY_PACKED && sizeof(T) == 4) {
     levy_quad_pairs_f32x2<FOSTER>(pw_i, pw_j, off, m, pa, pb, z, tenth_h, davie_std);
-    return;
-  }
-#endif
+  } else {
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const T v = levy_pair_value_t<T, FOSTER>(pw_i[k][off], pw_j[k][off], pw_i[k][off + m], pw_j[k][off + m], z[k],
-                                             tenth_h, davie_std);
-    *pa[k] = v;
-    *pb[k] = -v;
+    for (int k = 0; k < 4; ++k) {
+      const T v = levy_pair_value_t<T, FOSTER>(pw_i[k][off], pw_j[k][off], pw_i[k][off + m], pw_j[k][off + m], z[k],
+                                               tenth_h, davie_std);
+      *pa[k] = v;
+      *pb[k] = -v;
+    }
   }
 }
 
