@@ -441,17 +441,26 @@ def run_ours(args, w, rank, world, local_rank):
     parity = parity_check(w, sde, last['bm'], ys, row_offset) if rank == 0 else None
 
     # ---- end to end through the public API with HOST buffers (`e2e`) ----
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     gathered = torch.empty((world * B, D), dtype=torch.float32, device=dev) if world > 1 else None
-    e0.record()
-    for i in range(args.steps):
+
+    def e2e_step(i):
         y0 = y0_host.to(dev, non_blocking=True)           # H2D of the step's inputs
         ys = solve(y0, 3000 + i)
         if world > 1:
             # the one collective of the path: gather the row shards' terminal states over NVLink
             dist.all_gather_into_tensor(gathered, ys[-1].contiguous())
         out_host.copy_(ys[-1], non_blocking=True)          # D2H of the step's result (terminal states)
+        return ys
+
+    # warm-up of THIS path as well (the first all_gather sets up NCCL's channels for the collective: ~100 ms that
+    # an N = 2 run without it showed as +6 ms per step)
+    for i in range(args.warmup):
+        ys = e2e_step(-1 - i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        ys = e2e_step(i)
     e1.record()
     barrier()
     e2e_elapsed = e0.elapsed_time(e1) * 1e-3
@@ -506,7 +515,7 @@ def run_ours(args, w, rank, world, local_rank):
         "per_rank_ms_per_step": [round(x, 3) for x in per_rank_ms],
         "e2e": {"value": e2e_value, "unit": "traj-steps/s", "h2d_bytes_per_step": int(y0_host.numel() * 4),
                 "d2h_bytes_per_step": int(out_host.numel() * 4), "ms_per_step": e2e_elapsed / args.steps * 1e3,
-                "result_copied": "ys[-1] (terminal states)",
+                "result_copied": "ys[-1] (terminal states)", "warmup": args.warmup,
                 "collective": None if world == 1 else "one NCCL all_gather of the terminal states per solve"},
         "gpu_launches": int(launches_per_solve * args.steps),
         "gpu_launches_note": "C-ABI kernel launches of this library captured in the replayed CUDA graph "

@@ -312,15 +312,16 @@ __device__ __forceinline__ T levy_pair_value(T wi, T wj, T hi, T hj, T z, T tent
 }
 
 constexpr int kLevyWarps = 8;
-// resident CTAs per SM the fp32 compile-time-m instantiations are compiled for (register budget 65536 / (256 n)).
-// Measured at 131072 x 16 x 16 (profiles/r02_levy_ab.log, area / fused cell query, us): n = 6: 45.1 / 49.3,
-// 5: 43.3 / 49.3, 4: 42.4 / 47.2, 3: 41.1 / 47.2 — the issue-bound kernel prefers the instruction schedule 71
-// registers allow to more resident warps.  Overridable for A/B builds (-DTSDE_LEVY_CTAS=4).
+// Register budget of the fp32 compile-time-m instantiations, as the minimum number of resident CTAs per SM they are
+// compiled for (65536 / (256 n) registers per thread).  Measured at 131072 x 16 x 16 (profiles/r02_levy_ab.log,
+// r02_levy_ab2.log; area kernel / fused cell query, us): n = 6: 45.1 / 49.3, 5: 43.3 / 49.3, 4: 42.4 / 47.2,
+// 3: 41.1 / 47.2, 2: 40.0 / 43.1 (79 / 96 registers, what the compiler takes when it may) — the issue-bound kernel
+// prefers the longer instruction schedule to more resident warps.  Overridable for A/B builds (-DTSDE_LEVY_CTAS=4).
 #ifndef TSDE_LEVY_CTAS
-#define TSDE_LEVY_CTAS 3
+#define TSDE_LEVY_CTAS 2
 #endif
 #ifndef TSDE_LEVY_CTAS_GEN
-#define TSDE_LEVY_CTAS_GEN 3
+#define TSDE_LEVY_CTAS_GEN 2
 #endif
 
 // Rows a warp handles per pass in the generating mode: the W and H normals of one row are only m/2 Philox quads, so
