@@ -310,7 +310,9 @@ class BrownianInterval(brownian_base.BaseBrownian):
         if self._key_dev is None:
             self._require_cuda()
             k = self._key if self._key < (1 << 63) else self._key - (1 << 64)
-            self._key_dev = torch.tensor([k], dtype=torch.int64, device=self._device)
+            # (a fill kernel, not a host-to-device copy: creating an interval does not synchronise the host with the
+            # work already queued on the device)
+            self._key_dev = torch.full((1,), k, dtype=torch.int64, device=self._device)
         return self._key_dev
 
     def _launch(self):
