@@ -71,7 +71,8 @@ enum {
 typedef struct tsde_launch {
   int32_t dtype;      /* TSDE_F32 | TSDE_F64                       */
   int32_t noise_type; /* TSDE_NOISE_*                              */
-  int64_t rows;       /* trajectories held by this rank            */
+  int64_t rows;       /* trajectories held by this rank; 0 is a valid launch that does nothing (operand pointers
+                         of an empty batch may be NULL)            */
   int64_t d;          /* state channels                            */
   int64_t m;          /* Brownian channels                         */
   void*   stream;     /* cudaStream_t                              */

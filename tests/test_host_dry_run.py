@@ -356,3 +356,31 @@ def test_adjoint_adaptive_reversible_pair_flows_through(dry):
     assert any('does not save the time steps' in str(w.message) for w in caught)
     assert y0.grad is not None and all(p.grad is not None for p in sde.parameters())
     assert dry.calls.get('tsde_adaptive_error_sumsq', 0) > 0
+
+
+@pytest.mark.parametrize('levy,entry', [('none', 'tsde_brownian_cells'), ('space-time', 'tsde_brownian_cells'),
+                                        ('foster', 'tsde_brownian_cell_levy')])
+@pytest.mark.parametrize('size', [(6, 8), (3, 2, 8)])
+def test_whole_cell_queries_are_one_launch_each(dry, levy, entry, size):
+    """dt-spaced queries on an interval created with `dt=` (cfg5's access pattern): every whole-cell query, in any
+    order, is answered by exactly one launch — also W-only queries — and the outputs come in the caller-visible
+    shape without a reshape (they are allocated in it)."""
+    h = 0.125
+    bm = tsde.BrownianInterval(0.0, 1.0, size=size, dtype=torch.float32, device='cpu', entropy=3, dt=h,
+                               levy_area_approximation=levy)
+    want_u, want_a = levy != 'none', levy == 'foster'
+    for n, k in enumerate((0, 5, 2, 7)):
+        before = dict(dry.calls)
+        out = bm(k * h, (k + 1) * h, return_U=want_u, return_A=want_a)
+        new = {name: c - before.get(name, 0) for name, c in dry.calls.items() if c != before.get(name, 0)}
+        assert new == {entry: 1}, (levy, k, new)
+        out = out if isinstance(out, tuple) else (out,)
+        assert tuple(out[0].shape) == size and out[0].is_contiguous()
+        if want_u:
+            assert tuple(out[1].shape) == size
+        if want_a:
+            assert tuple(out[2].shape) == (*size, size[-1])
+    # a query that is not a run of whole cells takes the general path (bridge), with more than one launch
+    before = sum(dry.calls.values())
+    bm(0.0625, 0.3, return_U=want_u, return_A=want_a)
+    assert sum(dry.calls.values()) - before > 1

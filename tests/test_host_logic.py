@@ -380,7 +380,17 @@ def test_cabi_rejects_malformed_calls_without_touching_the_device():
             for launch in (None, ctypes.byref(ok), ctypes.byref(negative), ctypes.byref(no_width)):
                 rc = getattr(lib, name)(*args_for(name, launch))
                 assert rc == EINVAL, (name, rc)
-        # an empty launch returns 0 before touching the device
+        # an empty launch (rows == 0) is a valid no-op for every entry point, whatever its operands: the tensors of an
+        # empty batch have no storage, their data pointers are null
+        for dtype, noise_type, m in ((torch.float32, _cabi.NOISE_DIAGONAL, 8), (torch.float64, _cabi.NOISE_GENERAL, 4)):
+            empty = _cabi.make_launch(dtype, noise_type, 0, 8, m, 0)
+            for name in _cabi.SIGNATURES:
+                rc = getattr(lib, name)(*args_for(name, ctypes.byref(empty)))
+                # (entry points that exist for one noise layout only still reject the other one)
+                assert rc in (0, EINVAL), (name, rc)
+                if rc == EINVAL:
+                    other = _cabi.make_launch(dtype, 1 - noise_type, 0, 8, 8 if noise_type else 4, 0)
+                    assert getattr(lib, name)(*args_for(name, ctypes.byref(other))) == 0, name
         empty = _cabi.make_launch(torch.float32, _cabi.NOISE_DIAGONAL, 0, 8, 8, 0)
         buf = (ctypes.c_float * 64)()
         p = ctypes.addressof(buf)
@@ -439,3 +449,37 @@ def test_c_client_of_the_abi(tmp_path):
                     os.path.join(ROOT, 'tests', 'c', 'abi_client.c'), '-o', exe, '-ldl'], check=True)
     r = subprocess.run([exe, _cabi.LIB_PATH], capture_output=True, text=True)
     assert r.returncode == 0 and 'c client ok, abi 1' in r.stdout, (r.returncode, r.stdout, r.stderr)
+
+
+def test_bench_clock_sampler_reports_the_timed_window_only():
+    """bench.py starts `nvidia-smi -lms` before the warm-up (so that its start-up does not run against the first timed
+    steps) and reports only samples taken after `mark()`; throttle reasons outside the window do not count, an empty
+    window falls back to the last sample."""
+    import importlib.util
+    import time
+    spec = importlib.util.spec_from_file_location('bench_under_test', os.path.join(ROOT, 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+
+    class _Done:
+        def terminate(self):
+            pass
+
+        def wait(self, timeout=None):
+            return 0
+
+    s = bench.ClockSampler(0)
+    s.proc = _Done()
+    t = time.monotonic()
+    warm = '1500, 1965, Not Active, Not Active, Active, Not Active'   # sw_thermal_slowdown during the warm-up only
+    timed = '1965, 1965, Not Active, Not Active, Not Active, Active'  # sw_power_cap inside the window: kept and noted
+    s.lines = [(t - 2.0, warm), (t - 1.0, warm)]
+    s.t_mark = t
+    s.lines += [(t + 0.1, timed), (t + 0.3, timed)]
+    got = s.stop()
+    assert got == {'sm_mhz': 1965.0, 'sm_max_mhz': 1965.0, 'samples': 2, 'reasons': ['sw_power_cap']}
+    empty = bench.ClockSampler(0)
+    empty.proc = _Done()
+    empty.lines = [(t - 2.0, warm)]
+    empty.t_mark = t
+    assert empty.stop()['samples'] == 1 and empty.stop()['sm_mhz'] == 1500.0
