@@ -1,14 +1,9 @@
-"""Typing aliases the reference's tests/utils.py imports from torchsde.types (annotations only)."""
-from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple, Union  # noqa: F401
+"""The four names the reference's tests/utils.py takes from `torchsde.types` (annotations only)."""
+import typing
 
 import torch
-from torch import nn
 
-Tensor = torch.Tensor
-Tensors = Sequence[Tensor]
-TensorOrTensors = Union[Tensor, Tensors]
-Scalar = Union[float, Tensor]
-Vector = Union[Sequence[float], Tensor]
-Module = nn.Module
-Modules = Sequence[Module]
-ModuleOrModules = Union[Module, Modules]
+Callable = typing.Callable
+Optional = typing.Optional
+TensorOrTensors = typing.Union[torch.Tensor, typing.Sequence[torch.Tensor]]
+ModuleOrModules = typing.Union[torch.nn.Module, typing.Sequence[torch.nn.Module]]
