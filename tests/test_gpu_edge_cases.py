@@ -101,3 +101,56 @@ def test_more_than_2_31_quads():
     np.testing.assert_allclose(out[rows - 1].cpu().numpy(), W[0], rtol=2e-5, atol=5e-6)
     del y0, g, out
     torch.cuda.empty_cache()
+
+
+def _sync_warnings(fn):
+    """Run fn with PyTorch's synchronisation debug mode on; return the warnings about synchronising CUDA calls."""
+    import warnings
+    torch.cuda.synchronize()
+    prev = torch.cuda.get_sync_debug_mode()
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter('always')
+        torch.cuda.set_sync_debug_mode('warn')
+        try:
+            out = fn()
+        finally:
+            torch.cuda.set_sync_debug_mode(prev)
+    torch.cuda.synchronize()
+    return out, [str(w.message) for w in caught if 'synchroniz' in str(w.message).lower()]
+
+
+def test_cached_solve_does_not_synchronise_the_host():
+    """A training or sampling loop builds a new BrownianInterval per solve and calls sdeint again: with the schedule
+    and the graph plan cached, nothing on that path may wait for the device (the host prepares solve k+1 while solve k
+    replays).  Until late in r02 the interval's Philox key was uploaded with a synchronous host-to-device copy."""
+    tsde = _tsde()
+    sde = problems.GBMDiagonal(8, 'ito', seed=1, dtype=torch.float32).to(DEV)
+    ts = (torch.arange(5, dtype=torch.float32) * 2.0 ** -4).to(DEV)
+    y0 = torch.full((64, 8), 0.1, device=DEV)
+
+    def solve(entropy, graph):
+        bm = tsde.BrownianInterval(0.0, 0.25, size=(64, 8), dtype=torch.float32, device=DEV, entropy=entropy)
+        with torch.no_grad():
+            return tsde.sdeint(sde, y0, ts, bm=bm, method='milstein', dt=2.0 ** -4, options={'cuda_graph': graph})
+
+    for graph in (True, False):
+        first = solve(1, graph)
+        solve(2, graph)
+        again, syncs = _sync_warnings(lambda: solve(1, graph))
+        assert syncs == [], syncs
+        assert torch.equal(first, again)
+
+
+@pytest.mark.parametrize('levy', ['none', 'space-time', 'foster'])
+def test_whole_cell_queries_do_not_synchronise_the_host(levy):
+    tsde = _tsde()
+    h = 2.0 ** -6
+
+    def sweep():
+        bm = tsde.BrownianInterval(0.0, 1.0, size=(256, 16), dtype=torch.float32, device=DEV, entropy=9, dt=h,
+                                   levy_area_approximation=levy)
+        return [bm(k * h, (k + 1) * h, return_U=levy != 'none', return_A=levy == 'foster') for k in (0, 7, 3)]
+
+    sweep()
+    _, syncs = _sync_warnings(sweep)
+    assert syncs == [], syncs
