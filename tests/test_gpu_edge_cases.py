@@ -117,11 +117,12 @@ def _sync_warnings(fn):
             torch.cuda.set_sync_debug_mode(prev)
     torch.cuda.synchronize()
     # (the mode announces itself once per process with a 'prototype feature' warning: not a finding)
-    return out, [str(w.message) for w in caught
+    return out, [f"{w.filename}:{w.lineno}: {w.message}" for w in caught
                  if 'synchroniz' in str(w.message).lower() and 'prototype feature' not in str(w.message)]
 
 
-def test_cached_solve_does_not_synchronise_the_host():
+@pytest.mark.parametrize('graph', [True, False])
+def test_cached_solve_does_not_synchronise_the_host(graph):
     """A training or sampling loop builds a new BrownianInterval per solve and calls sdeint again: with the schedule
     and the graph plan cached, nothing on that path may wait for the device (the host prepares solve k+1 while solve k
     replays).  Until late in r02 the interval's Philox key was uploaded with a synchronous host-to-device copy."""
@@ -135,12 +136,11 @@ def test_cached_solve_does_not_synchronise_the_host():
         with torch.no_grad():
             return tsde.sdeint(sde, y0, ts, bm=bm, method='milstein', dt=2.0 ** -4, options={'cuda_graph': graph})
 
-    for graph in (True, False):
-        first = solve(1, graph)
-        solve(2, graph)
-        again, syncs = _sync_warnings(lambda: solve(1, graph))
-        assert syncs == [], syncs
-        assert torch.equal(first, again)
+    first = solve(1, graph)
+    solve(2, graph)
+    again, syncs = _sync_warnings(lambda: solve(1, graph))
+    assert syncs == [], syncs
+    assert torch.equal(first, again)
 
 
 @pytest.mark.parametrize('levy', ['none', 'space-time', 'foster'])
