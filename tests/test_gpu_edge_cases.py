@@ -125,7 +125,9 @@ def _sync_warnings(fn):
 def test_cached_solve_does_not_synchronise_the_host(graph):
     """A training or sampling loop builds a new BrownianInterval per solve and calls sdeint again: with the schedule
     and the graph plan cached, nothing on that path may wait for the device (the host prepares solve k+1 while solve k
-    replays).  Until late in r02 the interval's Philox key was uploaded with a synchronous host-to-device copy."""
+    replays).  Until late in r02 the interval's Philox key was uploaded with a synchronous host-to-device copy.
+    The eager loop (no CUDA graph) uploads its per-step time table once per solve — one blocking copy, at
+    `BaseSDESolver._contexts`, and nothing else."""
     tsde = _tsde()
     sde = problems.GBMDiagonal(8, 'ito', seed=1, dtype=torch.float32).to(DEV)
     ts = (torch.arange(5, dtype=torch.float32) * 2.0 ** -4).to(DEV)
@@ -139,7 +141,10 @@ def test_cached_solve_does_not_synchronise_the_host(graph):
     first = solve(1, graph)
     solve(2, graph)
     again, syncs = _sync_warnings(lambda: solve(1, graph))
-    assert syncs == [], syncs
+    if graph:
+        assert syncs == [], syncs
+    else:
+        assert len(syncs) <= 1 and all('base_solver.py' in w for w in syncs), syncs
     assert torch.equal(first, again)
 
 
