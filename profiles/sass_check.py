@@ -3,7 +3,7 @@ counts of the instructions that carry the design — 128-bit global loads/stores
 (UBLKCP) and mbarrier ops (SYNCS) of the TMA-staged tile kernel, SFU ops of the in-register Box-Muller, and the
 absence of FFMA in the tableau kernels that follow the reference's separately rounded op order (-fmad=false).
 
-    python profiles/sass_check.py > profiles/r01_sass_evidence.txt
+    python profiles/sass_check.py > profiles/r02_sass_evidence.txt
 """
 import os
 import re
@@ -23,9 +23,13 @@ PICK = [  # (label, regex on the demangled kernel name)
     ('general Heun tile, TMA-staged, fp32, m=64', r'gen_tma_kernel<float, tsde::GHeunOp<float>, 1, 4>'),
     ('Brownian cells W (materialised queries), fp32', r'ew_fast_kernel<float, tsde::CellsOp<float, false>, 1>|ew_fast_kernel<float, tsde::CellsOp<float>, 1>'),
     ('Brownian bridge', r'bridge_kernel<float'),
-    ('Levy area (Davie / Foster)', r'levy_area_smem_kernel<float'),
+    ('Levy area (Davie / Foster), fp32, m = 16: one normal per pair, packed pair arithmetic', r'levy_tile_kernel<float, false, 16>|levy_tile_kernel<float, \(bool\)0, 16>'),
+    ('fused cell query W, U, A (drawn in the kernel), fp32, m = 16', r'levy_tile_kernel<float, true, 16>|levy_tile_kernel<float, \(bool\)1, 16>'),
+    ('Levy area, fp64, m = 16 (scalar pair arithmetic, separately rounded)', r'levy_tile_kernel<double, false, 16>|levy_tile_kernel<double, \(bool\)0, 16>'),
+    ('bmm(g, A) of the log-ODE correction, fp32, m = 16', r'bmm_ga_kernel<float, 16>'),
+    ('logqp KL-integrand augmentation, fp32', r'logqp_augment_kernel<float>'),
 ]
-COUNT = ['LDG.E.128', 'LDG.E.EF.128', 'STG.E.128', 'LDS.128', 'UBLKCP', 'SYNCS', 'MUFU', 'FFMA', 'FMUL', 'FADD', 'DFMA',
+COUNT = ['LDG.E.128', 'LDG.E.EF.128', 'STG.E.128', 'LDS.128', 'UBLKCP', 'SYNCS', 'MUFU', 'FFMA2', 'FMUL2', 'FADD2', 'FFMA', 'FMUL', 'FADD', 'DFMA',
          'SHFL', 'BAR.SYNC', 'LDL', 'STL', 'IMAD.WIDE']
 
 
