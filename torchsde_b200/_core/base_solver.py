@@ -440,6 +440,10 @@ class BaseSDESolver(metaclass=abc.ABCMeta):
     def _error_estimate(self, y_full, y_half):
         """compute_error of adaptive_stepping.py:42-69: RMS of (y11 - y12) / tol, reduced on the GPU."""
         eps = 1e-7
+        # (an empty batch has no error to estimate: the reference's mean over zero elements is nan and trips the
+        # same assertion, adaptive_stepping.py:67-68)
+        assert y_full.numel() > 0, ('Found nans in the error estimate. Try increasing the tolerance or regularizing '
+                                    'the dynamics.')
         if self._err_buf is None:
             self._err_buf = torch.zeros(1024, dtype=torch.float64, device=self.device)
         buf = self._err_buf
